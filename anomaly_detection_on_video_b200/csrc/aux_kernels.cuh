@@ -1,0 +1,296 @@
+// HBM-bound helper kernels of the extraction path (everything that is not a contraction):
+//   K0  ingest        fp32 NCTHW clip -> bf16 stem layout            (extract_features.py:83-86)
+//   K1  preprocess    u8 frames -> PIL-exact resize -> crops -> standardise -> clip tensors
+//                                                                    (src/gtransforms.py:9-73,115-132)
+//   K3  max-pool 3D   channels-last, optional SAME padding / channel-slice destination
+//                                                                    (src/i3d.py:212-217,306,309)
+//   K4  avg-pool      global mean over (T,H,W) -> fp32 features      (src/i3d.py:244,314)
+//       segment mean  (n_clips, crops, C) -> (crops, 32, C)          (extract_features.py:159-185)
+//       add magnitude append the L2 norm                             (src/dataset.py:121-124)
+#pragma once
+
+#include "ptx_sm100.cuh"
+
+namespace vad {
+
+// ------------------------------------------------------------------------------------------- K0
+// one thread per stem-layout pixel (8 bytes out); reads are coalesced along W in each channel plane
+__global__ void ingest_ncthw_f32_kernel(const float* __restrict__ x, int B, int T, int H, int W, int pad_left,
+                                        uint2* __restrict__ out) {
+  const int Wp = W + 8;
+  const long long total = (long long)B * T * H * Wp;
+  const long long plane = (long long)T * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp);
+    const long long r = i / Wp;  // (b*T + t)*H + h
+    const int w = wp - pad_left;
+    uint2 o = make_uint2(0u, 0u);
+    if (w >= 0 && w < W) {
+      const long long b = r / ((long long)T * H);
+      const long long th = r - b * (long long)T * H;  // t*H + h
+      const float* px = x + b * 3 * plane + th * W + w;
+      o.x = pack_bf16x2(px[0], px[plane]);
+      o.y = pack_bf16x2(px[2 * plane], 0.f);
+    }
+    out[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- K1
+struct PreprocParams {
+  const uint8_t* frames;  // [n_frames, H, W, 3]
+  int n_frames, H, W;
+  int rh, rw;             // resized size
+  int ksize_h, ksize_v;
+  const int* bounds_h;    // [rw][2] (xmin, count)
+  const int* coef_h;      // [rw][ksize_h]  22-bit fixed point
+  const int* bounds_v;    // [rh][2]
+  const int* coef_v;      // [rh][ksize_v]
+  int crop, ncrops;
+  int tops[10], lefts[10], flips[10];
+  int clip_start, fpc;
+  int out_mode, pad_left;
+  void* out;
+};
+
+__device__ __forceinline__ int clip8_q22(int acc) {
+  const int v = acc >> 22;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// grid = (resized rows, frame slots); one block resamples one output row of one frame into shared
+// memory (horizontal pass rounded to u8, then vertical pass, exactly Pillow's order) and then
+// writes that row into every crop that contains it.
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) {
+  extern __shared__ uint8_t s_row[];  // rw*3 bytes (+ LUTs after, 16B aligned)
+  const int row_bytes = (p.rw * 3 + 15) & ~15;
+  float* lut_f = reinterpret_cast<float*>(s_row + row_bytes);
+  __nv_bfloat16* lut_h = reinterpret_cast<__nv_bfloat16*>(lut_f + 256);
+
+  const int y = blockIdx.x;
+  const int slot = blockIdx.y;
+  const int clip_local = slot / p.fpc;
+  const int t = slot - clip_local * p.fpc;
+  const int clip = p.clip_start + clip_local;
+  int L = p.n_frames - clip * p.fpc;      // real frames in this clip (LoopPad, gtransforms.py:115-132)
+  L = L > p.fpc ? p.fpc : L;
+  const int src_frame = clip * p.fpc + (t % L);
+  const uint8_t* frame = p.frames + (long long)src_frame * p.H * p.W * 3;
+
+  if (threadIdx.x < 256) {
+    // GroupStandardizationTenCrop: t.sub_(114.75).div_(57.375), two fp32 roundings
+    const float v = __fdiv_rn(__fsub_rn((float)threadIdx.x, 114.75f), 57.375f);
+    lut_f[threadIdx.x] = v;
+    lut_h[threadIdx.x] = __float2bfloat16_rn(v);
+  }
+
+  const int ymin = p.bounds_v[2 * y];
+  const int ycnt = p.bounds_v[2 * y + 1];
+  const int* kv = p.coef_v + y * p.ksize_v;
+  for (int i = threadIdx.x; i < p.rw * 3; i += blockDim.x) {
+    const int x = i / 3;
+    const int c = i - x * 3;
+    const int xmin = p.bounds_h[2 * x];
+    const int xcnt = p.bounds_h[2 * x + 1];
+    const int* kh = p.coef_h + x * p.ksize_h;
+    int acc_v = 1 << 21;
+    for (int r = 0; r < ycnt; ++r) {
+      const uint8_t* src = frame + ((long long)(ymin + r) * p.W + xmin) * 3 + c;
+      int acc_h = 1 << 21;
+      for (int j = 0; j < xcnt; ++j) acc_h += (int)src[j * 3] * kh[j];
+      acc_v += clip8_q22(acc_h) * kv[r];
+    }
+    s_row[i] = (uint8_t)clip8_q22(acc_v);
+  }
+  __syncthreads();
+
+  const int crop = p.crop;
+  for (int k = 0; k < p.ncrops; ++k) {
+    const int yo = y - p.tops[k];
+    if (yo < 0 || yo >= crop) continue;
+    const int left = p.lefts[k];
+    const int flip = p.flips[k];
+    if (p.out_mode == 1) {
+      // stem layout [clipcrop, t, crop, crop + 8, 4] bf16 ; two pixels (16 B) per thread
+      const int Wp = crop + 8;
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                            ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * crop + yo) *
+                                                Wp * 4);
+      for (int i = threadIdx.x; i < Wp / 2; i += blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int xo = 2 * i + h - p.pad_left;
+          if (xo >= 0 && xo < crop) {
+            const int xs = flip ? left + crop - 1 - xo : left + xo;
+            const uint8_t* px = s_row + xs * 3;
+            const uint32_t r = __bfloat16_as_ushort(lut_h[px[0]]);
+            const uint32_t g = __bfloat16_as_ushort(lut_h[px[1]]);
+            const uint32_t b = __bfloat16_as_ushort(lut_h[px[2]]);
+            w[2 * h] = r | (g << 16);
+            w[2 * h + 1] = b;
+          }
+        }
+        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      // dataset layout [clip, crop_idx, t, 3, crop, crop] fp32
+      float* dst = reinterpret_cast<float*>(p.out) +
+                   ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * 3) * crop * crop + (long long)yo * crop;
+      for (int i = threadIdx.x; i < 3 * crop; i += blockDim.x) {
+        const int c = i / crop;
+        const int xo = i - c * crop;
+        const int xs = flip ? left + crop - 1 - xo : left + xo;
+        dst[(long long)c * crop * crop + xo] = lut_f[s_row[xs * 3 + c]];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- K3
+struct PoolParams {
+  const __nv_bfloat16* in;
+  __nv_bfloat16* out;  // already offset by dst_c_off
+  int B, Ti, Hi, Wi, C;
+  int To, Ho, Wo;
+  int kt, kh, kw, st, sh, sw;
+  int pt, ph, pw;   // front padding
+  int pad_zero;     // 1: out-of-range taps contribute 0 (SAME-padding port), 0: they are ignored
+  int ldo;          // dst row pitch (elements)
+};
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// one thread per (output pixel, 8-channel vector): 128-bit loads/stores, channel vectors of a pixel
+// are adjacent threads so every tap is a contiguous row segment
+__global__ void __launch_bounds__(256) maxpool3d_kernel(const PoolParams p) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)p.B * p.To * p.Ho * p.Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long m = i / cv;
+    const long long m_out = m;
+    const int wo = (int)(m % p.Wo); m /= p.Wo;
+    const int ho = (int)(m % p.Ho); m /= p.Ho;
+    const int to = (int)(m % p.To); m /= p.To;
+    const long long b = m;
+    const uint32_t neg_inf2 = 0xFF80FF80u;
+    uint4 acc = make_uint4(neg_inf2, neg_inf2, neg_inf2, neg_inf2);
+    bool any_oob = false;
+    for (int dt = 0; dt < p.kt; ++dt) {
+      const int ti = to * p.st - p.pt + dt;
+      for (int dh = 0; dh < p.kh; ++dh) {
+        const int hi = ho * p.sh - p.ph + dh;
+        for (int dw = 0; dw < p.kw; ++dw) {
+          const int wi = wo * p.sw - p.pw + dw;
+          if ((unsigned)ti < (unsigned)p.Ti && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi) {
+            const uint4 x = *reinterpret_cast<const uint4*>(
+                p.in + ((((b * p.Ti + ti) * p.Hi + hi) * p.Wi + wi) * (long long)p.C) + v * 8);
+            acc.x = bf16x2_max(acc.x, x.x);
+            acc.y = bf16x2_max(acc.y, x.y);
+            acc.z = bf16x2_max(acc.z, x.z);
+            acc.w = bf16x2_max(acc.w, x.w);
+          } else {
+            any_oob = true;
+          }
+        }
+      }
+    }
+    if (any_oob && p.pad_zero) {
+      acc.x = bf16x2_max(acc.x, 0u);
+      acc.y = bf16x2_max(acc.y, 0u);
+      acc.z = bf16x2_max(acc.z, 0u);
+      acc.w = bf16x2_max(acc.w, 0u);
+    }
+    *reinterpret_cast<uint4*>(p.out + m_out * p.ldo + v * 8) = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- K4
+// global average pool: in [B, P, C] bf16 -> out [B, C] fp32.  A warp covers 64 channels: lane =
+// pg*8 + cv reads 16 B of channel vector cv at positions pg, pg+4, ... (4 x 128 B contiguous per
+// step), then the four position groups are combined with warp shuffles.
+__global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int P, int C,
+                                                      float* __restrict__ out) {
+  const int warps_per_clip = C >> 6;
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)B * warps_per_clip) return;
+  const int b = (int)(gw / warps_per_clip);
+  const int c0 = (int)(gw % warps_per_clip) * 64 + (lane & 7) * 8;
+  const int pg = lane >> 3;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* base = in + (long long)b * P * C + c0;
+  for (int pos = pg; pos < P; pos += 4) {
+    const uint4 x = *reinterpret_cast<const uint4*>(base + (long long)pos * C);
+    acc[0] += bf16_lo(x.x); acc[1] += bf16_hi(x.x);
+    acc[2] += bf16_lo(x.y); acc[3] += bf16_hi(x.y);
+    acc[4] += bf16_lo(x.z); acc[5] += bf16_hi(x.z);
+    acc[6] += bf16_lo(x.w); acc[7] += bf16_hi(x.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  }
+  if (pg == 0) {
+    const float inv = 1.f / (float)P;
+    float4* o = reinterpret_cast<float4*>(out + (long long)b * C + c0);
+    o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  }
+}
+
+// segment mean: feats [n_clips, ncrops, C] -> out [ncrops, seg, C].  Bin edges i*n/seg are the
+// integer form of np.linspace(0, n, seg+1, dtype=int); rows are added in clip order and divided
+// once (IEEE), which is what np.mean over axis 0 does, so the result is bit-identical.
+// Lanes span channels (coalesced); the clip axis is a serial loop by construction.
+__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ feats, int n_clips, int ncrops,
+                                                           int C, int seg, float* __restrict__ out) {
+  const long long total = (long long)ncrops * seg * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int s = (int)((i / C) % seg);
+    const int k = (int)(i / ((long long)C * seg));
+    const int a = (int)(((long long)s * n_clips) / seg);
+    const int b = (int)(((long long)(s + 1) * n_clips) / seg);
+    const float* col = feats + (long long)k * C + c;
+    const long long stride = (long long)ncrops * C;
+    float r;
+    if (a != b) {
+      float sum = col[a * stride];
+      for (int j = a + 1; j < b; ++j) sum = __fadd_rn(sum, col[j * stride]);
+      r = __fdiv_rn(sum, (float)(b - a));
+    } else {
+      r = col[a * stride];
+    }
+    out[i] = r;
+  }
+}
+
+// add_magnitude: one warp per row; out[row] = concat(feat[row], ||feat[row]||_2)
+__global__ void __launch_bounds__(256) add_magnitude_kernel(const float* __restrict__ feats, long long rows, int C,
+                                                            float* __restrict__ out) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = feats + row * C;
+  float* dst = out + row * (C + 1);
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = src[c];
+    dst[c] = v;
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) dst[C] = sqrtf(ss);
+}
+
+}  // namespace vad

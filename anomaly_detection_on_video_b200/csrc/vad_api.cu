@@ -1,0 +1,614 @@
+// Host side of libvad_b200.so: the C ABI declared in include/vad_b200.h.
+// Shape inference, tensor-map encoding and kernel launches.  No device allocations happen here
+// except the few KB of resampling tables a preprocessing handle owns.
+#include "../../include/vad_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "conv_umma.cuh"
+
+using namespace vad;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define VAD_CUDA_CHECK(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(VAD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                                       \
+  } while (0)
+
+extern "C" const char* vad_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t vad_abi_version(void) { return VAD_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------ driver API
+// cuTensorMapEncode* live in libcuda; resolve them through the runtime so the library has no
+// link-time dependency on the driver (it must load on a GPU-less build box).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int32_t driver_symbol(const char* name, void** fn) {
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || *fn == nullptr)
+    return fail(VAD_ERR_DRIVER_SYMBOL, "cannot resolve driver symbol %s (%s)", name, cudaGetErrorString(e));
+  return VAD_OK;
+}
+
+static int32_t require_sm100(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(VAD_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(VAD_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  VAD_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VAD_ERR_UNSUPPORTED_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device,
+                prop.major, prop.minor);
+  return VAD_OK;
+}
+
+// ------------------------------------------------------------------------------------ plan
+struct SlotInfo {
+  int T = 0, H = 0, W = 0, C = 0;
+  uint64_t offset = UINT64_MAX, bytes = 0;
+  bool defined = false;
+};
+
+struct OpRuntime {
+  ConvParams cp;
+  PoolParams pp;
+  CUtensorMap tmA, tmB;
+  int bn = 0;
+  int grid = 0;
+  int a_mode = 0;
+  int avg_P = 0, avg_C = 0;
+  // for tensor-map encoding
+  int Ci = 0, Ti = 0, Hi = 0, Wi = 0;
+  int K_pad = 0;
+};
+
+struct vad_plan {
+  std::vector<vad_op_desc> ops;
+  int n_slots = 0;
+  const uint8_t* params = nullptr;
+  uint64_t params_bytes = 0;
+  int in_pad_left = 0;
+  int in_channels = 0;
+  int device = 0;
+  int batch = 0, T = 0, H = 0, W = 0;
+  bool configured = false;
+  std::vector<SlotInfo> slots;
+  uint64_t ws_bytes = 0;
+  std::vector<OpRuntime> rt;
+  const void* bound_x = nullptr;
+  void* bound_ws = nullptr;
+  double flops = 0.0;
+  int feat_c = 0;
+  EncodeTiledFn encode_tiled = nullptr;
+  EncodeIm2colFn encode_im2col = nullptr;
+  int driver_version = 0;
+};
+
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, int32_t n_ops, int32_t n_slots,
+                                   const void* params_dev, uint64_t params_bytes, int32_t in_channels,
+                                   int32_t in_pad_left, int32_t device) {
+  if (!plan || !ops || n_ops <= 0 || n_slots <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_create: null/empty argument");
+  if (in_pad_left < 0 || in_pad_left > 8) return fail(VAD_ERR_INVALID_ARGUMENT, "in_pad_left must be in [0,8]");
+  if (in_channels < 0 || in_channels % 8) return fail(VAD_ERR_INVALID_ARGUMENT, "in_channels must be 0 (stem layout) or a multiple of 8");
+  int32_t rc = require_sm100(device);
+  if (rc != VAD_OK) return rc;
+  for (int i = 0; i < n_ops; ++i) {
+    const vad_op_desc& d = ops[i];
+    if (d.kind < VAD_OP_CONV || d.kind > VAD_OP_AVGPOOL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad kind %d", i, d.kind);
+    if (d.src < 0 || d.src >= n_slots) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: src slot %d out of range", i, d.src);
+    if (d.kind != VAD_OP_AVGPOOL && (d.dst <= 0 || d.dst >= n_slots))
+      return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: dst slot %d out of range (slot 0 is the read-only input)", i, d.dst);
+    if (d.kind != VAD_OP_AVGPOOL && d.dst == d.src) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: in-place ops are not supported", i);
+    if (d.kind == VAD_OP_CONV) {
+      const bool fold = d.flags & VAD_FLAG_STEM_FOLD_W;
+      if (fold ? (d.cin != 4) : (d.cin % 8 != 0 || d.cin <= 0))
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: cin=%d must be a multiple of 8 (4 with STEM_FOLD_W)", i, d.cin);
+      if (d.cout <= 0 || d.cout % 8) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: cout=%d must be a multiple of 8", i, d.cout);
+      if (d.dst_c_off % 8) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: dst_c_off must be a multiple of 8", i);
+      if (d.res >= n_slots) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: res slot out of range", i);
+      if (d.w_off % 128 || d.scale_off % 16 || d.shift_off % 16)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: parameter offsets must be aligned (weights 128 B, scale/shift 16 B)", i);
+      if (d.kt < 1 || d.kh < 1 || d.kw < 1 || d.st < 1 || d.sh < 1 || d.sw < 1 || d.pt < 0 || d.ph < 0 || d.pw < 0)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad kernel/stride/pad", i);
+      if (fold && in_channels != 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs the stem input layout (in_channels == 0)", i);
+      if (fold && (d.kw > 8 || d.src != 0 || in_pad_left < d.pw || ((in_pad_left - d.pw) & 1) || (d.sw & 1)))
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs src=0, kw<=8, even sw, in_pad_left-pw even and >=0", i);
+    }
+  }
+  vad_plan* p = new vad_plan();
+  p->ops.assign(ops, ops + n_ops);
+  p->n_slots = n_slots;
+  p->params = static_cast<const uint8_t*>(params_dev);
+  p->params_bytes = params_bytes;
+  p->in_pad_left = in_pad_left;
+  p->in_channels = in_channels;
+  p->device = device;
+  void* fn = nullptr;
+  rc = driver_symbol("cuTensorMapEncodeTiled", &fn);
+  if (rc != VAD_OK) { delete p; return rc; }
+  p->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  rc = driver_symbol("cuTensorMapEncodeIm2col", &fn);
+  if (rc != VAD_OK) { delete p; return rc; }
+  p->encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  cudaDriverGetVersion(&p->driver_version);
+  *plan = p;
+  return VAD_OK;
+}
+
+extern "C" void vad_plan_destroy(vad_plan_t* plan) { delete plan; }
+
+static int pool_out_same(int in, int s) { return (in + s - 1) / s; }
+
+extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, int32_t h, int32_t w,
+                                      uint64_t* workspace_bytes) {
+  if (!p) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_configure: null plan");
+  if (batch <= 0 || t <= 0 || h <= 0 || w <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_configure: bad size");
+  p->configured = false;
+  p->slots.assign(p->n_slots, SlotInfo());
+  p->rt.assign(p->ops.size(), OpRuntime());
+  p->flops = 0.0;
+  p->feat_c = 0;
+  SlotInfo& s0 = p->slots[0];
+  s0.T = t; s0.H = h; s0.defined = true;
+  if (p->in_channels == 0) { s0.W = w + 8; s0.C = 4; } else { s0.W = w; s0.C = p->in_channels; }
+  s0.bytes = (uint64_t)batch * t * h * s0.W * s0.C * 2;
+
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const vad_op_desc& d = p->ops[i];
+    const SlotInfo src = p->slots[d.src];
+    if (!src.defined) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu reads slot %d before it is written", i, d.src);
+    OpRuntime& r = p->rt[i];
+    int To, Ho, Wo, Cdst;
+    if (d.kind == VAD_OP_CONV) {
+      const bool fold = d.flags & VAD_FLAG_STEM_FOLD_W;
+      const int Wi = fold ? src.W - 8 : src.W;
+      if (src.C != d.cin) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: cin=%d but slot %d has C=%d", i, d.cin, d.src, src.C);
+      To = (src.T + 2 * d.pt - d.kt) / d.st + 1;
+      Ho = (src.H + 2 * d.ph - d.kh) / d.sh + 1;
+      Wo = (Wi + 2 * d.pw - d.kw) / d.sw + 1;
+      if (To <= 0 || Ho <= 0 || Wo <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: empty output", i);
+      Cdst = d.dst_c_total ? d.dst_c_total : d.cout;
+      if (d.dst_c_off + d.cout > Cdst) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: channel slice exceeds dst_c_total", i);
+      const long long M = (long long)batch * To * Ho * Wo;
+      if (M > 0x7fffffffLL - 256) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: too many output pixels (%lld)", i, M);
+      if (fold && d.sw * (Wo - 1) - d.pw + p->in_pad_left + 7 > src.W - 1)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: folded stem window overruns the padded row", i);
+      ConvParams& c = r.cp;
+      memset(&c, 0, sizeof(c));
+      c.M = (int)M; c.N = d.cout;
+      c.To = To; c.Ho = Ho; c.Wo = Wo;
+      c.Ti = src.T; c.Hi = src.H;
+      c.kt = d.kt; c.kh = d.kh; c.st = d.st; c.sh = d.sh; c.pt = d.pt; c.ph = d.ph;
+      if (fold) {
+        c.Wi = Wo; c.kw = 1; c.sw = 1; c.pw = 0;
+        c.cin_eff = 32; c.ntaps = d.kt * d.kh;
+        c.sW = d.sw * 4; c.sH = (long long)src.W * 4; c.sT = c.sH * src.H; c.sN = c.sT * src.T;
+      } else {
+        c.Wi = Wi; c.kw = d.kw; c.sw = d.sw; c.pw = d.pw;
+        c.cin_eff = d.cin; c.ntaps = d.kt * d.kh * d.kw;
+        c.sW = d.cin; c.sH = (long long)Wi * d.cin; c.sT = c.sH * src.H; c.sN = c.sT * src.T;
+      }
+      const int K = c.ntaps * c.cin_eff;
+      r.K_pad = (int)align_up(K, kBlockK);
+      c.num_kb = r.K_pad / kBlockK;
+      c.relu = (d.flags & VAD_FLAG_RELU) ? 1 : 0;
+      c.ldo = Cdst;
+      const bool unit = d.kt == 1 && d.kh == 1 && d.kw == 1 && d.st == 1 && d.sh == 1 && d.sw == 1 && !d.pt && !d.ph && !d.pw;
+      if (fold || (d.cin % kBlockK) || (d.flags & VAD_FLAG_FORCE_GATHER) || d.pt > 15 || d.ph > 15 || d.pw > 15 ||
+          d.kt > 16 || d.kh > 16 || d.kw > 16 || d.st > 8 || d.sh > 8 || d.sw > 8)
+        r.a_mode = A_GATHER;
+      else if (unit)
+        r.a_mode = A_TMA_2D;
+      else
+        r.a_mode = A_TMA_IM2COL;
+      c.a_mode = r.a_mode;
+      r.bn = d.cout > 128 ? 256 : (d.cout > 64 ? 128 : 64);
+      const long long m_tiles = (M + kBlockM - 1) / kBlockM;
+      const long long n_tiles = (d.cout + r.bn - 1) / r.bn;
+      if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
+      r.grid = (int)(m_tiles * n_tiles);
+      r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi;
+      const uint64_t need_w = d.w_off + (uint64_t)d.cout * r.K_pad * 2;
+      if (need_w > p->params_bytes || d.scale_off + 4ull * d.cout > p->params_bytes || d.shift_off + 4ull * d.cout > p->params_bytes)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: parameters exceed the blob (%llu > %llu)", i,
+                    (unsigned long long)need_w, (unsigned long long)p->params_bytes);
+      if (d.res >= 0) {
+        const SlotInfo& rs = p->slots[d.res];
+        if (!rs.defined || rs.T != To || rs.H != Ho || rs.W != Wo || rs.C < d.cout)
+          return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: residual slot %d shape mismatch", i, d.res);
+        c.ldr = rs.C;
+      }
+      const int cin_real = fold ? 3 : d.cin;
+      p->flops += 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;
+    } else if (d.kind == VAD_OP_MAXPOOL) {
+      PoolParams& q = r.pp;
+      memset(&q, 0, sizeof(q));
+      if (src.C % 8) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: max-pool needs C %% 8 == 0", i);
+      if (d.flags & VAD_FLAG_POOL_SAME) {
+        To = pool_out_same(src.T, d.st); Ho = pool_out_same(src.H, d.sh); Wo = pool_out_same(src.W, d.sw);
+        auto front = [](int in, int out, int k, int s) { int tot = (out - 1) * s + k - in; if (tot < 0) tot = 0; return tot / 2; };
+        q.pt = front(src.T, To, d.kt, d.st); q.ph = front(src.H, Ho, d.kh, d.sh); q.pw = front(src.W, Wo, d.kw, d.sw);
+        q.pad_zero = 1;
+      } else {
+        To = (src.T + 2 * d.pt - d.kt) / d.st + 1;
+        Ho = (src.H + 2 * d.ph - d.kh) / d.sh + 1;
+        Wo = (src.W + 2 * d.pw - d.kw) / d.sw + 1;
+        q.pt = d.pt; q.ph = d.ph; q.pw = d.pw; q.pad_zero = 0;
+      }
+      if (To <= 0 || Ho <= 0 || Wo <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: empty output", i);
+      Cdst = d.dst_c_total ? d.dst_c_total : src.C;
+      if (d.dst_c_off % 8 || d.dst_c_off + src.C > Cdst) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: bad channel slice", i);
+      q.B = batch; q.Ti = src.T; q.Hi = src.H; q.Wi = src.W; q.C = src.C;
+      q.To = To; q.Ho = Ho; q.Wo = Wo;
+      q.kt = d.kt; q.kh = d.kh; q.kw = d.kw; q.st = d.st; q.sh = d.sh; q.sw = d.sw;
+      q.ldo = Cdst;
+    } else {  // AVGPOOL
+      if (src.C % 64) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: avg-pool needs C %% 64 == 0", i);
+      r.avg_P = src.T * src.H * src.W;
+      r.avg_C = src.C;
+      p->feat_c = src.C;
+      continue;
+    }
+    SlotInfo& dst = p->slots[d.dst];
+    if (dst.defined && (dst.T != To || dst.H != Ho || dst.W != Wo || dst.C != Cdst)) {
+      // a slot may be reused with a new shape once its previous contents are dead
+      dst.T = To; dst.H = Ho; dst.W = Wo; dst.C = Cdst;
+    } else if (!dst.defined) {
+      dst.T = To; dst.H = Ho; dst.W = Wo; dst.C = Cdst; dst.defined = true;
+    }
+    const uint64_t bytes = (uint64_t)batch * To * Ho * Wo * Cdst * 2;
+    if (bytes > dst.bytes) dst.bytes = bytes;
+  }
+  uint64_t off = 0;
+  for (int s = 1; s < p->n_slots; ++s) {
+    if (!p->slots[s].defined) continue;
+    p->slots[s].offset = off;
+    // + one tile of slack: TMA boxes of the last (partial) tile never leave the allocation
+    off += align_up(p->slots[s].bytes + 1024, 1024);
+  }
+  p->ws_bytes = off;
+  p->batch = batch; p->T = t; p->H = h; p->W = w;
+  p->bound_x = nullptr; p->bound_ws = nullptr;
+  p->configured = true;
+  if (workspace_bytes) *workspace_bytes = off;
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_plan_slot_info(const vad_plan_t* p, int32_t slot, int32_t dims[4], uint64_t* offset,
+                                      uint64_t* bytes) {
+  if (!p || !p->configured) return fail(VAD_ERR_NOT_CONFIGURED, "plan is not configured");
+  if (slot < 0 || slot >= p->n_slots || !p->slots[slot].defined) return fail(VAD_ERR_INVALID_ARGUMENT, "slot %d undefined", slot);
+  const SlotInfo& s = p->slots[slot];
+  if (dims) { dims[0] = s.T; dims[1] = s.H; dims[2] = s.W; dims[3] = s.C; }
+  if (offset) *offset = s.offset;
+  if (bytes) *bytes = s.bytes;
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_plan_num_launches(const vad_plan_t* p) { return p ? (int32_t)p->ops.size() : 0; }
+extern "C" double vad_plan_flops(const vad_plan_t* p) { return (p && p->configured) ? p->flops : 0.0; }
+
+// Slot shapes change while the op list runs (slots are reused), so shapes are re-derived here in
+// op order; only pointers and tensor maps are (re)bound.
+static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
+  auto slot_ptr = [&](int s) -> uint8_t* {
+    return s == 0 ? const_cast<uint8_t*>(static_cast<const uint8_t*>(x)) : static_cast<uint8_t*>(ws) + p->slots[s].offset;
+  };
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const vad_op_desc& d = p->ops[i];
+    OpRuntime& r = p->rt[i];
+    if (d.kind == VAD_OP_CONV) {
+      ConvParams& c = r.cp;
+      const bool fold = d.flags & VAD_FLAG_STEM_FOLD_W;
+      c.in = reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.src)) + (fold ? (p->in_pad_left - d.pw) * 4 : 0);
+      c.out = reinterpret_cast<__nv_bfloat16*>(slot_ptr(d.dst)) + d.dst_c_off;
+      c.res = d.res >= 0 ? reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.res)) : nullptr;
+      c.scale = reinterpret_cast<const float*>(p->params + d.scale_off);
+      c.shift = reinterpret_cast<const float*>(p->params + d.shift_off);
+      // weights: [cout][K_pad] bf16, box = 64 (K) x BN (rows), 128B swizzle
+      {
+        cuuint64_t gdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)r.K_pad * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)r.bn};
+        cuuint32_t es[2] = {1, 1};
+        CUresult cr = p->encode_tiled(&r.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), gdim,
+                                      gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(weights) failed: %d", i, (int)cr);
+      }
+      memset(&r.tmA, 0, sizeof(r.tmA));
+      if (r.a_mode == A_TMA_2D) {
+        cuuint64_t gdim[2] = {(cuuint64_t)r.Ci, (cuuint64_t)c.M};
+        cuuint64_t gstr[1] = {(cuuint64_t)r.Ci * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockM};
+        cuuint32_t es[2] = {1, 1};
+        CUresult cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)slot_ptr(d.src), gdim, gstr,
+                                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(A) failed: %d", i, (int)cr);
+      } else if (r.a_mode == A_TMA_IM2COL) {
+        // (C, W, H, D, N); the bounding box of base pixels runs from -pad to (extent - 1 + pad - (k-1))
+        cuuint64_t gdim[5] = {(cuuint64_t)r.Ci, (cuuint64_t)r.Wi, (cuuint64_t)r.Hi, (cuuint64_t)r.Ti, (cuuint64_t)p->batch};
+        cuuint64_t gstr[4];
+        gstr[0] = (cuuint64_t)r.Ci * 2;
+        gstr[1] = gstr[0] * r.Wi;
+        gstr[2] = gstr[1] * r.Hi;
+        gstr[3] = gstr[2] * r.Ti;
+        int lower[3] = {-d.pw, -d.ph, -d.pt};
+        int upper[3] = {d.pw - (d.kw - 1), d.ph - (d.kh - 1), d.pt - (d.kt - 1)};
+        cuuint32_t es[5] = {1, (cuuint32_t)d.sw, (cuuint32_t)d.sh, (cuuint32_t)d.st, 1};
+        CUresult cr = p->encode_im2col(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)slot_ptr(d.src), gdim, gstr,
+                                       lower, upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, es,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeIm2col failed: %d", i, (int)cr);
+        // Drivers up to 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (bit 21 of the
+        // second descriptor word must be cleared); public CUTLASS applies the same fix-up.
+        const uint64_t tensor_bytes = gstr[3] * (uint64_t)p->batch;
+        if (p->driver_version <= 13010 && tensor_bytes < 131072)
+          reinterpret_cast<uint64_t*>(&r.tmA)[1] &= ~(1ull << 21);
+      }
+    } else if (d.kind == VAD_OP_MAXPOOL) {
+      r.pp.in = reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.src));
+      r.pp.out = reinterpret_cast<__nv_bfloat16*>(slot_ptr(d.dst)) + d.dst_c_off;
+    }
+  }
+  p->bound_x = x;
+  p->bound_ws = ws;
+  return VAD_OK;
+}
+
+template <int BN>
+static cudaError_t launch_conv(const OpRuntime& r, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvCfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_umma_kernel<BN><<<r.grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(r.tmA, r.tmB, r.cp);
+  return cudaGetLastError();
+}
+
+static int grid_for(long long total, int threads, int cap = 148 * 32) {
+  long long g = (total + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* workspace_dev, uint64_t workspace_bytes,
+                                    float* feat_out_dev, void* stream) {
+  if (!p || !p->configured) return fail(VAD_ERR_NOT_CONFIGURED, "vad_plan_forward: plan is not configured");
+  if (!x_dev || (!workspace_dev && p->ws_bytes)) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_forward: null pointer");
+  if (workspace_bytes < p->ws_bytes)
+    return fail(VAD_ERR_WORKSPACE_TOO_SMALL, "workspace %llu < required %llu", (unsigned long long)workspace_bytes,
+                (unsigned long long)p->ws_bytes);
+  if (((uintptr_t)x_dev & 15) || ((uintptr_t)workspace_dev & 1023))
+    return fail(VAD_ERR_INVALID_ARGUMENT, "x must be 16 B aligned and the workspace 1024 B aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->bound_x != x_dev || p->bound_ws != workspace_dev) {
+    int32_t rc = bind_plan(p, x_dev, workspace_dev);
+    if (rc != VAD_OK) return rc;
+  }
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const vad_op_desc& d = p->ops[i];
+    const OpRuntime& r = p->rt[i];
+    cudaError_t e = cudaSuccess;
+    if (d.kind == VAD_OP_CONV) {
+      e = r.bn == 256 ? launch_conv<256>(r, st) : (r.bn == 128 ? launch_conv<128>(r, st) : launch_conv<64>(r, st));
+    } else if (d.kind == VAD_OP_MAXPOOL) {
+      const long long total = (long long)r.pp.B * r.pp.To * r.pp.Ho * r.pp.Wo * (r.pp.C / 8);
+      maxpool3d_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(r.pp);
+      e = cudaGetLastError();
+    } else {
+      if (!feat_out_dev) return fail(VAD_ERR_INVALID_ARGUMENT, "plan ends in AVGPOOL but feat_out_dev is null");
+      const uint8_t* src = d.src == 0 ? static_cast<const uint8_t*>(x_dev)
+                                      : static_cast<const uint8_t*>(workspace_dev) + p->slots[d.src].offset;
+      const long long warps = (long long)p->batch * (r.avg_C / 64);
+      avgpool_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), p->batch,
+                                                                     r.avg_P, r.avg_C, feat_out_dev);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "op %zu launch failed: %s", i, cudaGetErrorString(e));
+  }
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_ingest_ncthw_f32(const float* x_dev, int32_t batch, int32_t t, int32_t h, int32_t w,
+                                        int32_t pad_left, void* out_dev, void* stream) {
+  if (!x_dev || !out_dev || batch <= 0 || t <= 0 || h <= 0 || w <= 0 || pad_left < 0 || pad_left > 8)
+    return fail(VAD_ERR_INVALID_ARGUMENT, "vad_ingest_ncthw_f32: bad argument");
+  const long long total = (long long)batch * t * h * (w + 8);
+  ingest_ncthw_f32_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_dev, batch, t, h, w, pad_left, static_cast<uint2*>(out_dev));
+  VAD_CUDA_CHECK(cudaGetLastError());
+  return VAD_OK;
+}
+
+// ------------------------------------------------------------------------------------ preprocessing
+struct vad_preproc {
+  int src_h = 0, src_w = 0, rh = 0, rw = 0, crop = 0, ncrops = 0, device = 0;
+  int ksize_h = 0, ksize_v = 0;
+  int tops[10] = {0}, lefts[10] = {0}, flips[10] = {0};
+  int* tables_dev = nullptr;  // bounds_h | coef_h | bounds_v | coef_v
+  size_t off_bh = 0, off_ch = 0, off_bv = 0, off_cv = 0;
+};
+
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc for the BILINEAR filter (support 1.0):
+// double-precision triangle weights, normalised, then quantised to 22 fractional bits.
+static void resample_tables(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& coefs, int& ksize) {
+  const double scale = (double)in_size / (double)out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  ksize = (int)ceil(support) * 2 + 1;
+  bounds.assign((size_t)out_size * 2, 0);
+  coefs.assign((size_t)out_size * ksize, 0);
+  std::vector<double> k(ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0.0) a = -a;
+      const double w = a < 1.0 ? 1.0 - a : 0.0;
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) k[x] /= ww;
+      const double v = k[x] * (double)(1 << 22);
+      coefs[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v) : (int)(0.5 + v);
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+}
+
+extern "C" int32_t vad_preproc_create(vad_preproc_t** out, int32_t src_h, int32_t src_w, int32_t resize, int32_t crop,
+                                      int32_t ncrops, int32_t device) {
+  if (!out || src_h <= 0 || src_w <= 0 || resize <= 0 || crop <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_preproc_create: bad size");
+  if (ncrops != 1 && ncrops != 10) return fail(VAD_ERR_INVALID_ARGUMENT, "ncrops must be 1 or 10");
+  if (crop & 1) return fail(VAD_ERR_INVALID_ARGUMENT, "crop must be even");
+  int32_t rc = require_sm100(device);
+  if (rc != VAD_OK) return rc;
+  vad_preproc* pp = new vad_preproc();
+  pp->src_h = src_h; pp->src_w = src_w; pp->crop = crop; pp->ncrops = ncrops; pp->device = device;
+  // torchvision Resize(int): shorter side -> resize, longer -> int(resize * long / short)
+  if (src_w <= src_h) { pp->rw = resize; pp->rh = (int)((double)((long long)resize * src_h) / (double)src_w); }
+  else                { pp->rh = resize; pp->rw = (int)((double)((long long)resize * src_w) / (double)src_h); }
+  if (pp->rh < crop || pp->rw < crop) { delete pp; return fail(VAD_ERR_INVALID_ARGUMENT, "crop %d larger than resized image %dx%d", crop, pp->rh, pp->rw); }
+  // torchvision five_crop order tl, tr, bl, br, center(round-half-even); then the h-flipped image
+  const int ct = (int)nearbyint((pp->rh - crop) / 2.0), cl = (int)nearbyint((pp->rw - crop) / 2.0);
+  const int t5[5] = {0, 0, pp->rh - crop, pp->rh - crop, ct};
+  const int l5[5] = {0, pp->rw - crop, 0, pp->rw - crop, cl};
+  if (ncrops == 10) {
+    for (int k = 0; k < 5; ++k) {
+      pp->tops[k] = t5[k]; pp->lefts[k] = l5[k]; pp->flips[k] = 0;
+      pp->tops[5 + k] = t5[k]; pp->lefts[5 + k] = pp->rw - crop - l5[k]; pp->flips[5 + k] = 1;
+    }
+  } else {
+    pp->tops[0] = ct; pp->lefts[0] = cl; pp->flips[0] = 0;
+  }
+  std::vector<int> bh, ch, bv, cv;
+  resample_tables(src_w, pp->rw, bh, ch, pp->ksize_h);
+  resample_tables(src_h, pp->rh, bv, cv, pp->ksize_v);
+  std::vector<int> all;
+  pp->off_bh = 0;               all.insert(all.end(), bh.begin(), bh.end());
+  pp->off_ch = all.size();      all.insert(all.end(), ch.begin(), ch.end());
+  pp->off_bv = all.size();      all.insert(all.end(), bv.begin(), bv.end());
+  pp->off_cv = all.size();      all.insert(all.end(), cv.begin(), cv.end());
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&pp->tables_dev, all.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(pp->tables_dev, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (pp->tables_dev) cudaFree(pp->tables_dev);
+    delete pp;
+    return fail(VAD_ERR_CUDA, "vad_preproc_create: %s", cudaGetErrorString(e));
+  }
+  *out = pp;
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_preproc_info(const vad_preproc_t* pp, int32_t resized_hw[2], int32_t* tops, int32_t* lefts,
+                                    int32_t* flips) {
+  if (!pp) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_preproc_info: null handle");
+  if (resized_hw) { resized_hw[0] = pp->rh; resized_hw[1] = pp->rw; }
+  for (int k = 0; k < pp->ncrops; ++k) {
+    if (tops) tops[k] = pp->tops[k];
+    if (lefts) lefts[k] = pp->lefts[k];
+    if (flips) flips[k] = pp->flips[k];
+  }
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_preproc_run(vad_preproc_t* pp, const uint8_t* frames_dev, int32_t n_frames, int32_t clip_start,
+                                   int32_t n_clips, int32_t frames_per_clip, int32_t out_mode, int32_t pad_left,
+                                   void* out_dev, void* stream) {
+  if (!pp || !frames_dev || !out_dev) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_preproc_run: null pointer");
+  if (n_frames <= 0 || frames_per_clip <= 0 || n_clips <= 0 || clip_start < 0) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_preproc_run: bad counts");
+  const int total_clips = (n_frames - 1) / frames_per_clip + 1;  // src/dataset.py:171-173
+  if (clip_start + n_clips > total_clips) return fail(VAD_ERR_INVALID_ARGUMENT, "clips [%d,%d) exceed the %d clips of %d frames", clip_start, clip_start + n_clips, total_clips, n_frames);
+  if (out_mode != VAD_OUT_DATASET_F32 && out_mode != VAD_OUT_STEM_BF16) return fail(VAD_ERR_INVALID_ARGUMENT, "bad out_mode");
+  if (pad_left < 0 || pad_left > 8) return fail(VAD_ERR_INVALID_ARGUMENT, "pad_left must be in [0,8]");
+  if ((long long)n_clips * frames_per_clip > 65535) return fail(VAD_ERR_INVALID_ARGUMENT, "at most 65535 frame slots per call");
+  PreprocParams q;
+  memset(&q, 0, sizeof(q));
+  q.frames = frames_dev; q.n_frames = n_frames; q.H = pp->src_h; q.W = pp->src_w;
+  q.rh = pp->rh; q.rw = pp->rw; q.ksize_h = pp->ksize_h; q.ksize_v = pp->ksize_v;
+  q.bounds_h = pp->tables_dev + pp->off_bh; q.coef_h = pp->tables_dev + pp->off_ch;
+  q.bounds_v = pp->tables_dev + pp->off_bv; q.coef_v = pp->tables_dev + pp->off_cv;
+  q.crop = pp->crop; q.ncrops = pp->ncrops;
+  for (int k = 0; k < 10; ++k) { q.tops[k] = pp->tops[k]; q.lefts[k] = pp->lefts[k]; q.flips[k] = pp->flips[k]; }
+  q.clip_start = clip_start; q.fpc = frames_per_clip; q.out_mode = out_mode; q.pad_left = pad_left; q.out = out_dev;
+  const size_t smem = ((size_t)pp->rw * 3 + 15) / 16 * 16 + 256 * 4 + 256 * 2;
+  dim3 grid(pp->rh, n_clips * frames_per_clip);
+  preprocess_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  VAD_CUDA_CHECK(cudaGetLastError());
+  return VAD_OK;
+}
+
+extern "C" void vad_preproc_destroy(vad_preproc_t* pp) {
+  if (!pp) return;
+  if (pp->tables_dev) cudaFree(pp->tables_dev);
+  delete pp;
+}
+
+// ------------------------------------------------------------------------------------ segment / magnitude
+extern "C" int32_t vad_segment_mean(const float* feats_dev, int32_t n_clips, int32_t ncrops, int32_t c,
+                                    int32_t seg_length, float* out_dev, void* stream) {
+  if (!feats_dev || !out_dev || n_clips <= 0 || ncrops <= 0 || c <= 0 || seg_length <= 0)
+    return fail(VAD_ERR_INVALID_ARGUMENT, "vad_segment_mean: bad argument");
+  const long long total = (long long)ncrops * seg_length * c;
+  segment_mean_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feats_dev, n_clips, ncrops, c,
+                                                                                         seg_length, out_dev);
+  VAD_CUDA_CHECK(cudaGetLastError());
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_add_magnitude(const float* feats_dev, int64_t rows, int32_t c, float* out_dev, void* stream) {
+  if (!feats_dev || !out_dev || rows <= 0 || c <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_add_magnitude: bad argument");
+  const long long threads = rows * 32;
+  add_magnitude_kernel<<<(int)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feats_dev, rows, c, out_dev);
+  VAD_CUDA_CHECK(cudaGetLastError());
+  return VAD_OK;
+}

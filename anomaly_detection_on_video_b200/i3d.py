@@ -1,0 +1,211 @@
+"""Drop-in for the reference backbone module ``src/i3d.py``.
+
+``I3Res50`` keeps the reference's parameter names (``conv1``, ``bn1``, ``layerL.B.convK``,
+``layerL.B.bnK``, ``layerL.0.downsample.{0,1}``; reference src/i3d.py:60-121,198-300) so its
+checkpoints load with ``load_state_dict``, and the reference's call contract
+``model(crop: [B,3,T,H,W] fp32 cuda) -> [B,2048,1,1,1] fp32`` (extract_features.py:86-89).
+The forward itself is not torch: the modules only *hold* parameters; they are folded
+(BatchNorm -> per-channel scale/shift), packed to bf16 and executed by the sm_100a kernels behind
+``libvad_b200.so``.  There is no CPU forward.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .engine import BackbonePlan, Op, ParamPacker, fold_bn, ingest_ncthw
+
+# (planes, blocks, spatial stride, temporal-conv flag per block): reference src/i3d.py:220-243
+I3RES50_STAGES: Tuple[Tuple[int, int, int, Tuple[int, ...]], ...] = (
+    (64, 3, 1, (1, 1, 1)),
+    (128, 4, 2, (1, 0, 1, 0)),
+    (256, 6, 2, (1, 0, 1, 0, 1, 0)),
+    (512, 3, 2, (0, 1, 0)),
+)
+STEM_PAD_LEFT = 3  # == stem pw, so the folded window of output column wo starts at padded pixel 2*wo
+
+
+class Bottleneck(nn.Module):
+    """Parameter container for one residual block (reference src/i3d.py:60-121)."""
+
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int, temp_conv: int, with_downsample: bool) -> None:
+        super().__init__()
+        kt = 1 + 2 * temp_conv
+        self.conv1 = nn.Conv3d(inplanes, planes, (kt, 1, 1), stride=1, padding=(temp_conv, 0, 0), bias=False)
+        self.bn1 = nn.BatchNorm3d(planes)
+        self.conv2 = nn.Conv3d(planes, planes, (1, 3, 3), stride=(1, stride, stride), padding=(0, 1, 1), bias=False)
+        self.bn2 = nn.BatchNorm3d(planes)
+        self.conv3 = nn.Conv3d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm3d(planes * 4)
+        self.downsample: Optional[nn.Sequential] = None
+        if with_downsample:
+            self.downsample = nn.Sequential(
+                nn.Conv3d(inplanes, planes * 4, 1, stride=(1, stride, stride), bias=False),
+                nn.BatchNorm3d(planes * 4),
+            )
+        self.stride = stride
+
+
+def _conv_geom(conv: nn.Conv3d):
+    return tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)
+
+
+class _NativeBackbone(nn.Module):
+    """Shared machinery: build the op table from the module tree, run it through the C ABI."""
+
+    feature_dim = 0
+
+    def __init__(self) -> None:
+        super().__init__()
+        self._plan: Optional[BackbonePlan] = None
+        self._plan_key = None
+        self.force_gather = False  # debug: feed every conv through the cp.async gather producer
+
+    # subclasses return (ops, packer, n_slots)
+    def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
+        raise NotImplementedError
+
+    def _conv_op(self, packer: ParamPacker, conv: nn.Conv3d, bn: nn.BatchNorm3d, src: int, dst: int, relu: bool,
+                 res: int = -1, fold_w: bool = False, name: str = "", dst_c_off: int = 0, dst_c_total: int = 0) -> Op:
+        scale, shift = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        if conv.bias is not None:
+            shift = shift + conv.bias.detach().float() * scale
+        w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, fold_w=fold_w)
+        k, s, p = _conv_geom(conv)
+        flags = (_lib.VAD_FLAG_RELU if relu else 0) | (_lib.VAD_FLAG_STEM_FOLD_W if fold_w else 0)
+        if self.force_gather:
+            flags |= _lib.VAD_FLAG_FORCE_GATHER
+        return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, res=res, cin=4 if fold_w else conv.in_channels,
+                  cout=conv.out_channels, kernel=k, stride=s, pad=p, flags=flags, dst_c_off=dst_c_off,
+                  dst_c_total=dst_c_total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
+
+    def _param_key(self):
+        # rebuild the packed blob whenever a parameter / buffer tensor was replaced or modified in place
+        return tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers()))
+
+    def plan(self, device: torch.device) -> BackbonePlan:
+        key = (self._param_key(), str(device), self.force_gather)
+        if self._plan is None or self._plan_key != key:
+            ops, packer, n_slots = self._build_table()
+            self._plan = BackbonePlan(ops, packer.blob(), n_slots, STEM_PAD_LEFT, device)
+            self._plan_key = key
+        return self._plan
+
+    def op_table(self) -> List[Op]:
+        return self._build_table()[0]
+
+    def forward_stem_layout(self, x_stem: torch.Tensor) -> torch.Tensor:
+        """bf16 stem-layout clips [B, T, H, W+8, 4] (what ``Preprocessor`` emits) -> [B, C] fp32."""
+        if self.training:
+            raise RuntimeError("the native backbone is inference-only: call .eval() first (extract_features.py:36)")
+        return self.plan(x_stem.device).forward(x_stem)
+
+    def forward(self, batch: torch.Tensor) -> torch.Tensor:
+        """[B, 3, T, H, W] fp32 on the GPU -> [B, C, 1, 1, 1] fp32 (reference src/i3d.py:302-318)."""
+        if not batch.is_cuda:
+            raise RuntimeError("I3D features are computed by sm_100a kernels only; move the input (and the model) "
+                               "to a CUDA device. There is no CPU fallback.")
+        feats = self.forward_stem_layout(ingest_ncthw(batch.float(), STEM_PAD_LEFT))
+        return feats.view(feats.shape[0], feats.shape[1], 1, 1, 1)
+
+
+class I3Res50(_NativeBackbone):
+    """I3D-ResNet50 feature extractor (reference src/i3d.py:198-318), 2048-d output."""
+
+    feature_dim = 2048
+
+    def __init__(self, layers: Sequence[int] = (3, 4, 6, 3), use_nl: bool = False) -> None:
+        super().__init__()
+        if use_nl:
+            raise NotImplementedError("non-local blocks are dead code in every shipped reference configuration "
+                                      "(src/i3d.py:338 always passes use_nl=False) and are not built")
+        self.conv1 = nn.Conv3d(3, 64, (5, 7, 7), stride=(2, 2, 2), padding=(2, 3, 3), bias=False)
+        self.bn1 = nn.BatchNorm3d(64)
+        inplanes = 64
+        for li, ((planes, _, stride, temp_conv), nblocks) in enumerate(zip(I3RES50_STAGES, layers), start=1):
+            blocks = []
+            for b in range(nblocks):
+                first = b == 0
+                need_ds = first and (stride != 1 or inplanes != planes * 4)
+                blocks.append(Bottleneck(inplanes, planes, stride if first else 1, temp_conv[b % len(temp_conv)], need_ds))
+                inplanes = planes * 4
+            setattr(self, f"layer{li}", nn.Sequential(*blocks))
+        # same initialisation as the reference constructor (src/i3d.py:246-251)
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out")
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
+        pk = ParamPacker()
+        ops: List[Op] = []
+        T1, T2, DS = 3, 4, 5  # bottleneck temporaries; slots 1/2 ping-pong the block input/output
+        ops.append(self._conv_op(pk, self.conv1, self.bn1, src=0, dst=1, relu=True, fold_w=True, name="conv1"))
+        ops.append(Op(kind=_lib.VAD_OP_MAXPOOL, src=1, dst=2, kernel=(2, 3, 3), stride=(2, 2, 2), name="maxpool1"))
+        cur = 2
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                nxt = 1 if cur == 2 else 2
+                n = f"layer{li}.{bi}"
+                ops.append(self._conv_op(pk, blk.conv1, blk.bn1, cur, T1, relu=True, name=n + ".conv1"))
+                ops.append(self._conv_op(pk, blk.conv2, blk.bn2, T1, T2, relu=True, name=n + ".conv2"))
+                res = cur
+                if blk.downsample is not None:
+                    ops.append(self._conv_op(pk, blk.downsample[0], blk.downsample[1], cur, DS, relu=False, name=n + ".downsample"))
+                    res = DS
+                ops.append(self._conv_op(pk, blk.conv3, blk.bn3, T2, nxt, relu=True, res=res, name=n + ".conv3"))
+                cur = nxt
+            if li == 1:
+                nxt = 1 if cur == 2 else 2
+                ops.append(Op(kind=_lib.VAD_OP_MAXPOOL, src=cur, dst=nxt, kernel=(2, 1, 1), stride=(2, 1, 1), name="maxpool2"))
+                cur = nxt
+        ops.append(Op(kind=_lib.VAD_OP_AVGPOOL, src=cur, name="avgpool"))
+        return ops, pk, 6
+
+
+MODEL_ZOO: Dict[str, str] = {
+    # file names of the reference's hub checkpoints (src/i3d.py:12-18); loaded from a local path here
+    "i3d_8x8_r50": "I3D_8x8_R50.pyth",
+    "tushar-n-baseline": "converted_ref_i3d.pt",
+}
+
+
+def print_model_size(model: nn.Module) -> None:
+    bits = sum(p.numel() * (torch.finfo(p.dtype).bits if p.is_floating_point() else torch.iinfo(p.dtype).bits)
+               for p in model.parameters())
+    print(f"model size: {bits} / bit | {bits / 8e6:.2f} / MB")
+
+
+def build_i3d_feature_extractor(model_name: str = "tushar-n-baseline", check_model_size: bool = True,
+                                strict: bool = False, state_dict_path: Optional[str] = None) -> nn.Module:
+    """Same signature as the reference factory (src/i3d.py:332-364) plus ``state_dict_path``.
+
+    The reference downloads the checkpoint from the HF hub; this environment has no network, so
+    weights come from ``state_dict_path`` (or stay at the constructor's random init).
+    ``i3d_8x8_r50`` is pytorchvideo's third-party backbone, which the reference does not vendor.
+    """
+    if model_name == "tushar-n-baseline":
+        model = I3Res50(use_nl=False)
+    elif model_name == "i3d_8x8_r50":
+        raise NotImplementedError("i3d_8x8_r50 is pytorchvideo's create_resnet (third-party, un-vendored, version "
+                                  "unpinned in the reference); only 'tushar-n-baseline' (I3Res50) is built")
+    else:
+        raise AttributeError(model_name)
+    if state_dict_path is not None:
+        sd = torch.load(state_dict_path, map_location="cpu")
+        missing, unexpected = model.load_state_dict(sd, strict=strict)
+        if missing or unexpected:  # the reference ignores these silently; say so
+            print(f"load_state_dict: {len(missing)} missing, {len(unexpected)} unexpected keys")
+    if check_model_size:
+        print_model_size(model)
+    return model
+
+
+__all__ = ["I3Res50", "Bottleneck", "build_i3d_feature_extractor", "print_model_size", "MODEL_ZOO", "STEM_PAD_LEFT"]

@@ -1,0 +1,180 @@
+/*
+ * vad_b200.h -- C ABI of libvad_b200.so: the B200 (sm_100a) hot path of
+ * jinmang2/anomaly_detection_on_video (I3D snippet-feature extraction).
+ *
+ * The reference has no FFI: its boundary is plain Python call sites.  Every entry point below
+ * names the reference call site(s) it replaces (file:line relative to the reference root) so a
+ * maintainer can bind it with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every function returns VAD_OK (0) or a negative vad_status; the message for the calling
+ *     thread's last failure is available from vad_last_error()
+ *   - pointers named *_dev are device pointers on the handle's device, owned by the caller
+ *     (PyTorch in our host code); the library borrows them for the duration of the call
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it and no
+ *     call synchronises the device
+ *   - handles are bound to one device, are not thread-safe, and own only host memory plus (for the
+ *     preprocessing handle) a few KB of resampling-coefficient tables
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute call fails
+ *     with VAD_ERR_CUDA / VAD_ERR_UNSUPPORTED_DEVICE
+ */
+#ifndef VAD_B200_H_
+#define VAD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAD_ABI_VERSION 1
+
+typedef enum vad_status {
+  VAD_OK = 0,
+  VAD_ERR_INVALID_ARGUMENT = -1,
+  VAD_ERR_CUDA = -2,
+  VAD_ERR_UNSUPPORTED_DEVICE = -3,
+  VAD_ERR_WORKSPACE_TOO_SMALL = -4,
+  VAD_ERR_NOT_CONFIGURED = -5,
+  VAD_ERR_DRIVER_SYMBOL = -6
+} vad_status;
+
+/* Message describing the last failure on the calling thread ("" if none). Never NULL. */
+const char* vad_last_error(void);
+int32_t vad_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backbone plan: a list of ops over numbered activation slots.
+ *
+ * Replaces the torch.nn graph of I3Res50 (src/i3d.py:198-318: conv1/bn1/relu/maxpool1, Bottleneck
+ * stacks src/i3d.py:60-121 incl. downsample src/i3d.py:262-272, maxpool2, avgpool) that
+ * extract_features.py:88 calls as `model(crop)`.  The same op list expresses an InceptionV1-3D
+ * (Unit3D / MaxPool3dSamePadding / channel-slice concat) -- only the table differs.
+ *
+ * Activations are channels-last bf16: slot tensor = [batch, T, H, W, C] with C a multiple of 8.
+ * Slot 0 is the network input in *stem layout*: [batch, T, H, W + 8, 4] bf16 (RGB + one zero
+ * channel; `in_pad_left` zero pixels on the left of every row, 8 - in_pad_left on the right), which
+ * is what vad_preproc_run(out_mode = VAD_OUT_STEM_BF16) and vad_ingest_ncthw_f32() produce.
+ * ---------------------------------------------------------------------------------------------- */
+
+enum { VAD_OP_CONV = 0, VAD_OP_MAXPOOL = 1, VAD_OP_AVGPOOL = 2 };
+
+/* vad_op_desc.flags */
+enum {
+  VAD_FLAG_RELU = 1,        /* ReLU after (scale,shift) and the optional residual add               */
+  VAD_FLAG_STEM_FOLD_W = 2, /* conv reads slot 0 in stem layout; the kw taps of one row are folded
+                               into the contraction dim (window of 8 px x 4 ch, 64-byte aligned)    */
+  VAD_FLAG_POOL_SAME = 4,   /* TF "SAME" padding for max-pool (MaxPool3dSamePadding); pad value 0   */
+  VAD_FLAG_FORCE_GATHER = 8 /* conv: feed the A operand with the cp.async gather producer instead
+                               of TMA (debug / comparison; results are identical)                   */
+};
+
+typedef struct vad_op_desc {
+  int32_t kind;           /* VAD_OP_*                                                               */
+  int32_t src;            /* input slot                                                             */
+  int32_t dst;            /* output slot (ignored by AVGPOOL: it writes the fp32 feature output)    */
+  int32_t res;            /* CONV: slot added before ReLU (`out += residual`, src/i3d.py:115), or -1 */
+  int32_t cin;            /* CONV: input channels as stored (multiple of 8; 4 with STEM_FOLD_W)     */
+  int32_t cout;           /* CONV: output channels (multiple of 8)                                  */
+  int32_t kt, kh, kw;     /* kernel                                                                 */
+  int32_t st, sh, sw;     /* stride                                                                 */
+  int32_t pt, ph, pw;     /* zero padding (front == back), ignored with VAD_FLAG_POOL_SAME          */
+  int32_t flags;          /* VAD_FLAG_*                                                             */
+  int32_t dst_c_off;      /* first channel written inside the dst slot (Inception concat), else 0   */
+  int32_t dst_c_total;    /* channel count of the dst slot tensor; 0 means `cout` (or C of src)     */
+  uint64_t w_off;         /* CONV: byte offset of bf16 weights [cout][K_pad] in the parameter blob; K
+                             order is (kt, kh, kw, cin), K_pad = K rounded up to 64, zero padded    */
+  uint64_t scale_off;     /* CONV: byte offset of fp32 scale[cout]  (gamma / sqrt(var + eps))       */
+  uint64_t shift_off;     /* CONV: byte offset of fp32 shift[cout]  (beta - mean * scale)           */
+} vad_op_desc;
+
+typedef struct vad_plan vad_plan_t;
+
+/* Build a plan.  `params_dev` (bf16 weights + fp32 scale/shift, laid out as the op offsets say) is
+ * borrowed for the life of the plan.  Replaces I3Res50.__init__ / _make_layer (src/i3d.py:199-300)
+ * plus load_state_dict (src/i3d.py:356-359) on the device side.
+ * in_channels == 0: slot 0 is the stem layout described above (the production case).
+ * in_channels  > 0: slot 0 is a plain [batch, T, H, W, in_channels] bf16 tensor (multiple of 8);
+ *                   used to run any sub-graph (e.g. a single conv) on its own. */
+int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, int32_t n_ops, int32_t n_slots,
+                        const void* params_dev, uint64_t params_bytes, int32_t in_channels,
+                        int32_t in_pad_left, int32_t device);
+
+/* Fix the problem size (clips per forward, frames, crop height/width); infers every slot shape and
+ * returns the workspace the caller must provide to vad_plan_forward. */
+int32_t vad_plan_configure(vad_plan_t* plan, int32_t batch, int32_t t, int32_t h, int32_t w,
+                           uint64_t* workspace_bytes);
+
+/* Run the op list: x_dev (slot 0, stem layout) -> feat_out_dev fp32 [batch, C_last] when the plan
+ * ends in AVGPOOL.  Replaces `model(crop)` at extract_features.py:86-89 (I3Res50.forward,
+ * src/i3d.py:302-318) for `batch` clip-crops at once. */
+int32_t vad_plan_forward(vad_plan_t* plan, const void* x_dev, void* workspace_dev,
+                         uint64_t workspace_bytes, float* feat_out_dev, void* stream);
+
+/* Shape / location of a slot after configure (for tests and for chaining): dims = {T,H,W,C},
+ * byte offset inside the workspace (slot 0 lives outside the workspace: offset = UINT64_MAX). */
+int32_t vad_plan_slot_info(const vad_plan_t* plan, int32_t slot, int32_t dims[4], uint64_t* offset,
+                           uint64_t* bytes);
+
+/* Number of kernels one vad_plan_forward launches (for the bench's gpu_launches count). */
+int32_t vad_plan_num_launches(const vad_plan_t* plan);
+
+/* Conv FLOPs (2 * MAC, useful taps only) of one forward at the configured size. */
+double vad_plan_flops(const vad_plan_t* plan);
+
+void vad_plan_destroy(vad_plan_t* plan);
+
+/* fp32 NCTHW clips (what the reference feeds its model: extract_features.py:83-86) -> stem layout.
+ * x_dev: [batch, 3, T, H, W] fp32.  out_dev: [batch, T, H, W + 8, 4] bf16. */
+int32_t vad_ingest_ncthw_f32(const float* x_dev, int32_t batch, int32_t t, int32_t h, int32_t w,
+                             int32_t pad_left, void* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused clip preprocessing.  Replaces src/gtransforms.py:9-73,115-132 (GroupResize, GroupTenCrop,
+ * ToTensorTenCrop, GroupStandardizationTenCrop, LoopPad) and the permutes at src/dataset.py:188-195
+ * / extract_features.py:83.  The resize is Pillow's two-pass fixed-point bilinear resample, so
+ * the fp32 output is bit-identical to the reference's.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  VAD_OUT_DATASET_F32 = 0, /* [n_clips, ncrops, frames_per_clip, 3, crop, crop] fp32: the stacked
+                              TenCropVideoFrameDataset.__getitem__ tensors (src/dataset.py:188-195) */
+  VAD_OUT_STEM_BF16 = 1    /* [n_clips * ncrops, frames_per_clip, crop, crop + 8, 4] bf16 stem layout */
+};
+
+typedef struct vad_preproc vad_preproc_t;
+
+/* ncrops is 10 (TenCrop order: tl, tr, bl, br, center, then the same five of the h-flipped image)
+ * or 1 (center crop == TenCrop index 4). */
+int32_t vad_preproc_create(vad_preproc_t** pp, int32_t src_h, int32_t src_w, int32_t resize,
+                           int32_t crop, int32_t ncrops, int32_t device);
+/* resized_hw = {H, W} after GroupResize; tops/lefts hold ncrops entries (offsets in the resized,
+ * un-flipped image of the pixel block each crop reads; flipped crops read it right-to-left). */
+int32_t vad_preproc_info(const vad_preproc_t* pp, int32_t resized_hw[2], int32_t* tops, int32_t* lefts,
+                         int32_t* flips);
+/* frames_dev: [n_frames, src_h, src_w, 3] uint8.  Clip i covers frames [i*fpc, (i+1)*fpc); a short
+ * last clip is loop-padded (frame j <- frame j mod L).  Processes clips
+ * [clip_start, clip_start + n_clips). */
+int32_t vad_preproc_run(vad_preproc_t* pp, const uint8_t* frames_dev, int32_t n_frames,
+                        int32_t clip_start, int32_t n_clips, int32_t frames_per_clip, int32_t out_mode,
+                        int32_t pad_left, void* out_dev, void* stream);
+void vad_preproc_destroy(vad_preproc_t* pp);
+
+/* ------------------------------------------------------------------------------------------------
+ * 32-segment averaging.  Replaces segment() (extract_features.py:159-185): for each crop,
+ * r = linspace(0, n_clips, seg+1, dtype=int); out[i] = mean(f[r[i]:r[i+1]]) or f[r[i]] if empty.
+ * feats_dev: [n_clips, ncrops, C] fp32 -> out_dev: [ncrops, seg_length, C] fp32.  Clips are added in
+ * index order and divided once, which reproduces np.mean bit for bit.
+ * ---------------------------------------------------------------------------------------------- */
+int32_t vad_segment_mean(const float* feats_dev, int32_t n_clips, int32_t ncrops, int32_t c,
+                         int32_t seg_length, float* out_dev, void* stream);
+
+/* FeatureDataset.add_magnitude (src/dataset.py:121-124): [rows, C] fp32 -> [rows, C + 1] with the
+ * L2 norm of each row appended. */
+int32_t vad_add_magnitude(const float* feats_dev, int64_t rows, int32_t c, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAD_B200_H_ */
