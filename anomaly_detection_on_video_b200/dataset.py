@@ -1,0 +1,167 @@
+"""Drop-in for the reference clip source ``TenCropVideoFrameDataset`` (src/dataset.py:145-195) and the
+``add_magnitude`` step of its ``FeatureDataset`` (src/dataset.py:121-124).
+
+Same constructor, ``len()`` and ``[i] -> (10, 16, 3, 224, 224) float32`` contract; the whole transform
+chain of src/gtransforms.py runs as ONE fused sm_100a kernel (``vad_preproc_run``), bit-identical to
+the reference's PIL/torchvision result.  Frames are uploaded once as uint8 and every clip tensor is
+produced on the GPU; ``clips_stem`` hands the native backbone its bf16 input layout directly.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from . import _lib
+from .engine import Preprocessor, add_magnitude as _add_magnitude
+
+try:  # PIL is only needed to accept List[PIL.Image] like the reference does
+    from PIL import Image
+except Exception:  # pragma: no cover
+    Image = None
+
+BILINEAR = 2  # PIL.Image.BILINEAR
+
+
+class FrameSource:
+    """Random access to decoded frames: ``len()`` and ``[i] -> (H, W, 3) uint8``.
+
+    Stands where ``decord.VideoReader`` stands in the reference (src/dataset.py:155-159,
+    extract_features.py:123).  ``.npy`` files hold pre-decoded frames (synthetic videos); real
+    containers are decoded with decord when installed, else OpenCV.  Decoding is host I/O and not
+    part of the accelerated path.
+    """
+
+    def __init__(self, uri: str) -> None:
+        self.uri = uri
+        self._arr = None
+        self._reader = None
+        self._cv = None
+        if uri.endswith(".npy"):
+            self._arr = np.load(uri, mmap_mode="r")
+            if self._arr.ndim != 4 or self._arr.shape[3] != 3 or self._arr.dtype != np.uint8:
+                raise ValueError(f"{uri}: expected a uint8 [n_frames, H, W, 3] array")
+            return
+        try:
+            import decord  # type: ignore
+
+            self._reader = decord.VideoReader(uri=uri)
+            return
+        except ImportError:
+            pass
+        import cv2  # type: ignore
+
+        cap = cv2.VideoCapture(uri)
+        if not cap.isOpened():
+            raise RuntimeError(f"cannot open video {uri}")
+        frames = []
+        while True:
+            ok, bgr = cap.read()
+            if not ok:
+                break
+            frames.append(bgr[:, :, ::-1])
+        cap.release()
+        if not frames:
+            raise RuntimeError(f"{uri}: no frames decoded")
+        self._arr = np.stack(frames)
+
+    def __len__(self) -> int:
+        return len(self._arr) if self._arr is not None else len(self._reader)
+
+    def __getitem__(self, i: int) -> np.ndarray:
+        if self._arr is not None:
+            return np.asarray(self._arr[i])
+        return self._reader[i].asnumpy()
+
+    def read(self, start: int, stop: int) -> np.ndarray:
+        stop = min(stop, len(self))
+        if self._arr is not None:
+            return np.ascontiguousarray(self._arr[start:stop])
+        return np.stack([self._reader[i].asnumpy() for i in range(start, stop)])
+
+
+def _frames_to_tensor(src) -> torch.Tensor:
+    """Any accepted frame container -> uint8 [n, H, W, 3] tensor (CPU or already on the GPU)."""
+    if isinstance(src, torch.Tensor):
+        t = src
+    elif isinstance(src, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(src))
+    elif isinstance(src, FrameSource):
+        t = torch.from_numpy(src.read(0, len(src)))
+    elif isinstance(src, str):
+        fs = FrameSource(src)
+        t = torch.from_numpy(fs.read(0, len(fs)))
+    elif isinstance(src, (list, tuple)) and len(src) > 0 and Image is not None and isinstance(src[0], Image.Image):
+        t = torch.from_numpy(np.stack([np.asarray(im.convert("RGB")) for im in src]))
+    else:
+        raise ValueError(
+            "The type of `video_path_or_images` must be either `str` or `List[PIL.Image.Image]` "
+            "(a uint8 [n, H, W, 3] numpy array / torch tensor is accepted too). "
+            f"The type of your input is {type(src)}."
+        )
+    if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3:
+        raise ValueError("frames must be uint8 [n_frames, H, W, 3]")
+    return t
+
+
+class TenCropVideoFrameDataset(Dataset):
+    """GPU clip source with the reference's interface (src/dataset.py:145-195)."""
+
+    def __init__(self, video_path_or_images: Union[str, Sequence, np.ndarray, torch.Tensor], frames_per_clip: int = 16,
+                 resize: int = 256, cropsize: int = 224, resample: int = BILINEAR,
+                 device: Optional[torch.device] = None, ncrops: int = 10) -> None:
+        if resample != BILINEAR:
+            raise NotImplementedError("only PIL.Image.BILINEAR (the reference default) is implemented")
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("TenCropVideoFrameDataset preprocesses on the GPU only (no CPU fallback)")
+        frames = _frames_to_tensor(video_path_or_images)
+        # one H2D copy of the raw uint8 frames; pinned staging keeps it asynchronous
+        if not frames.is_cuda:
+            frames = frames.contiguous()
+            try:
+                frames = frames.pin_memory()
+            except RuntimeError:
+                pass
+            frames = frames.to(self.device, non_blocking=True)
+        self.frames = frames.contiguous()
+        self.frames_per_clip = frames_per_clip
+        self.ncrops = ncrops
+        self.cropsize = cropsize
+        n_frames = self.frames.shape[0]
+        self.indices = list(range((n_frames - 1) // frames_per_clip + 1))  # src/dataset.py:171-173
+        self._pp = Preprocessor(self.frames.shape[1], self.frames.shape[2], resize, cropsize, ncrops, self.device)
+
+    def __len__(self) -> int:
+        return len(self.indices)
+
+    def __getitem__(self, idx: int) -> torch.Tensor:
+        """(ncrops, clip_len, 3, H, W) float32 on the GPU -- values identical to the reference's."""
+        if idx < 0:
+            idx += len(self)
+        if not 0 <= idx < len(self):
+            raise IndexError(idx)
+        return self._pp.run(self.frames, idx, 1, self.frames_per_clip, _lib.VAD_OUT_DATASET_F32)[0]
+
+    def clips_f32(self, start: int, n: int) -> torch.Tensor:
+        """(n, ncrops, clip_len, 3, H, W) float32: ``torch.stack([self[i] for i in range(start, start+n)])``."""
+        return self._pp.run(self.frames, start, n, self.frames_per_clip, _lib.VAD_OUT_DATASET_F32)
+
+    def clips_stem(self, start: int, n: int, pad_left: int = 3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bf16 stem layout (n * ncrops, clip_len, H, W + 8, 4), clip-major then crop: the direct input of
+        ``I3Res50.forward_stem_layout`` (skips the fp32 NCTHW tensor the reference materialises)."""
+        return self._pp.run(self.frames, start, n, self.frames_per_clip, _lib.VAD_OUT_STEM_BF16, pad_left, out=out)
+
+
+def add_magnitude(feature: Union[np.ndarray, torch.Tensor]) -> Union[np.ndarray, torch.Tensor]:
+    """``FeatureDataset.add_magnitude`` (src/dataset.py:121-124) on the GPU: (..., C) -> (..., C + 1)."""
+    if isinstance(feature, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(feature, dtype=np.float32)).cuda()
+        return _add_magnitude(t).cpu().numpy()
+    return _add_magnitude(feature)
+
+
+__all__ = ["TenCropVideoFrameDataset", "FrameSource", "add_magnitude", "BILINEAR"]
+_ = List

@@ -1,0 +1,233 @@
+"""-m gpu: every CUDA kernel against the oracle / fp32 torch ops, called through the C ABI."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import preprocess as P
+from oracle import segment as S
+
+pytestmark = pytest.mark.gpu
+
+# (name, cin, cout, kernel, stride, pad, B, T, H, W, residual, relu)
+CONV_CASES = [
+    ("1x1 64->256 layer1.conv3", 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 4, 13, 13, False, False),
+    ("1x1 256->64", 256, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 4, 13, 13, False, True),
+    ("1x1 1024->512 two n-tiles", 1024, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 7, 7, False, False),
+    ("1x1 tiny M=5", 64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 1, 1, 5, False, False),
+    ("1x1 n-tail 136", 128, 136, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 6, 6, False, False),
+    ("1x1 256->256 +res", 256, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 2, 9, 9, True, True),
+    ("t3 64->64 pad1", 64, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 4, 7, 9, False, True),
+    ("t3 64->64 pad1 +res", 64, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 4, 7, 9, True, True),
+    ("t3 256->64 K=768", 256, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, 4, 9, 9, False, True),
+    ("s3x3 64->64", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 3, 11, 13, False, True),
+    ("s3x3 row 55", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 2, 55, 55, False, True),
+    ("s3x3 stride 2 odd", 128, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), 2, 2, 15, 15, False, True),
+    ("1x1 stride 2 downsample", 256, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), 2, 2, 15, 15, False, False),
+    ("3x3x3 64->192 (Inception)", 64, 192, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 4, 10, 10, False, True),
+    ("t3 T=1 all-padding edges", 64, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 3, 1, 5, 5, False, True),
+]
+GATHER_ONLY = [
+    ("cin 24 3x3x3", 24, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 4, 10, 10, False, True),
+    ("cin 16 1x1 cout 48", 16, 48, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 9, 9, False, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("force_gather", [False, True], ids=["tma", "gather"])
+def test_conv_matches_fp32_reference(cuda_device, case, force_gather):
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    out, ref = run_conv_case(*case[1:], force_gather=force_gather)
+    assert out.shape == ref.shape
+    assert_bf16_close(out, ref)
+
+
+@pytest.mark.parametrize("case", CONV_CASES[6:13], ids=[c[0] for c in CONV_CASES[6:13]])
+def test_tma_im2col_and_gather_producers_agree_bitwise(cuda_device, case):
+    """Both A-operand producers must deliver the same tile, so the outputs are bit-identical."""
+    from gpu_util import run_conv_case
+
+    a, _ = run_conv_case(*case[1:], force_gather=False)
+    b, _ = run_conv_case(*case[1:], force_gather=True)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("case", GATHER_ONLY, ids=[c[0] for c in GATHER_ONLY])
+def test_conv_narrow_channels(cuda_device, case):
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    out, ref = run_conv_case(*case[1:])
+    assert_bf16_close(out, ref)
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 32, 32), (2, 8, 64, 64), (1, 16, 224, 224), (1, 6, 50, 38)])
+def test_stem_conv_folded_window(cuda_device, shape):
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+    from gpu_util import assert_bf16_close
+
+    B, T, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, T, H, W, generator=g).clamp(-2, 2.44)
+    w = (torch.randn(64, 3, 5, 7, 7, generator=g) * 0.045).to(torch.bfloat16).float()
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    xb = x.to(torch.bfloat16).float()
+    ref = F.relu(F.conv3d(xb, w, None, (2, 2, 2), (2, 3, 3)) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, scale, shift, fold_w=True)
+    ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=4, cout=64, kernel=(5, 7, 7), stride=(2, 2, 2), pad=(2, 3, 3),
+                  flags=lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W, w_off=w_off, scale_off=s_off, shift_off=b_off)]
+    plan = eng.BackbonePlan(ops, pk.blob(), 2, 3, cuda_device)
+    xs = eng.ingest_ncthw(x.to(cuda_device), 3)
+    want_stem = torch.zeros(B, T, H, W + 8, 4)
+    want_stem[:, :, :, 3:3 + W, :3] = xb.permute(0, 2, 3, 4, 1)
+    assert torch.equal(xs.float().cpu(), want_stem), "ingest (fp32 NCTHW -> bf16 stem layout) is a pure relayout"
+    plan.forward(xs)
+    torch.cuda.synchronize()
+    out = plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3)
+    assert_bf16_close(out, ref)
+
+
+@pytest.mark.parametrize("name,C,k,s,T,H,W", [("maxpool1", 64, (2, 3, 3), (2, 2, 2), 8, 30, 30),
+                                              ("maxpool1 odd", 64, (2, 3, 3), (2, 2, 2), 8, 112, 112),
+                                              ("maxpool2", 256, (2, 1, 1), (2, 1, 1), 4, 11, 11)])
+def test_maxpool_is_exact(cuda_device, name, C, k, s, T, H, W):
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+
+    x = torch.randn(2, C, T, H, W, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    ref = F.max_pool3d(x.float(), k, s, 0)
+    plan = eng.BackbonePlan([eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=1, kernel=k, stride=s)],
+                            torch.zeros(16, dtype=torch.uint8), 2, 0, cuda_device, in_channels=C)
+    plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
+    torch.cuda.synchronize()
+    assert torch.equal(plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3), ref)
+
+
+def test_maxpool_same_padding_into_channel_slice(cuda_device):
+    """MaxPool3dSamePadding (3x3x3, stride 1, zero pad) written into channels [64, 128) of a 192-wide slot."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+
+    x = torch.randn(1, 64, 4, 7, 7, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    ref = F.max_pool3d(F.pad(x.float(), (1, 1, 1, 1, 1, 1)), (3, 3, 3), (1, 1, 1), 0)
+    op = eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=1, kernel=(3, 3, 3), stride=(1, 1, 1), flags=lib.VAD_FLAG_POOL_SAME,
+                dst_c_off=64, dst_c_total=192)
+    plan = eng.BackbonePlan([op], torch.zeros(16, dtype=torch.uint8), 2, 0, cuda_device, in_channels=64)
+    plan.configure(1, 4, 7, 7)
+    plan.slot_tensor(1).fill_(-7.0)
+    plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
+    torch.cuda.synchronize()
+    out = plan.slot_tensor(1).float().cpu()
+    assert torch.equal(out[..., 64:128].permute(0, 4, 1, 2, 3), ref)
+    assert (out[..., :64] == -7.0).all() and (out[..., 128:] == -7.0).all(), "neighbouring channel slices untouched"
+
+
+def test_avgpool(cuda_device):
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+
+    x = torch.randn(3, 2048, 2, 7, 7, generator=torch.Generator().manual_seed(6)).to(torch.bfloat16)
+    plan = eng.BackbonePlan([eng.Op(kind=lib.VAD_OP_AVGPOOL, src=0)], torch.zeros(16, dtype=torch.uint8), 1, 0, cuda_device,
+                            in_channels=2048)
+    out = plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device)).cpu()
+    torch.testing.assert_close(out, x.float().mean(dim=(2, 3, 4)), rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- preprocessing (bit-exact)
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _frames(seed, n, h, w):
+    return np.random.default_rng(seed).integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+
+
+def test_preprocess_small_golden_bit_exact(cuda_device, golden_dir):
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+
+    g = np.load(os.path.join(golden_dir, "preprocess_small.npz"))
+    want = ((g["clips_u8"].astype(np.float32) - np.float32(114.75)) / np.float32(57.375)).astype(np.float32)
+    ds = TenCropVideoFrameDataset(g["frames"], frames_per_clip=int(g["frames_per_clip"]), resize=int(g["resize"]),
+                                  cropsize=int(g["crop"]), device=cuda_device)
+    assert len(ds) == 2
+    for ci in range(2):
+        got = ds[ci]
+        assert got.dtype == torch.float32 and tuple(got.shape) == want[ci].shape
+        assert np.array_equal(got.cpu().numpy(), want[ci])
+
+
+@pytest.mark.parametrize("tag,clips", [("ucf_240x320", (0, 2)), ("down_360x480", (0,)), ("portrait_300x256", (0,))])
+def test_preprocess_fullsize_matches_reference_digest(cuda_device, golden_dir, tag, clips):
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+
+    g = np.load(os.path.join(golden_dir, "preprocess_digests.npz"))
+    seed, n, h, w = eval(str(g[f"{tag}/spec"]))
+    ds = TenCropVideoFrameDataset(_frames(seed, n, h, w), device=cuda_device)
+    for ci in clips:
+        assert _sha(ds[ci].cpu().numpy()) == str(g[f"{tag}/clip{ci}"])
+
+
+def test_preprocess_stem_layout_and_center_crop(cuda_device):
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+
+    frames = _frames(4, 21, 120, 160)
+    ds = TenCropVideoFrameDataset(frames, device=cuda_device)
+    stem = ds.clips_stem(0, len(ds)).float().cpu().numpy()          # (2*10, 16, 224, 232, 4)
+    for ci in range(len(ds)):
+        ref = P.clip_tensor(frames, ci)
+        want = torch.from_numpy(P.to_stem_layout(ref)).to(torch.bfloat16).float().numpy()
+        assert np.array_equal(stem[ci * 10:(ci + 1) * 10], want)
+    one = TenCropVideoFrameDataset(frames, device=cuda_device, ncrops=1)
+    assert torch.equal(one[1][0], ds[1][4]), "center crop == TenCrop index 4"
+
+
+def test_preprocess_properties_at_ucf_size(cuda_device):
+    """Size-independent properties on a 2,000-frame UCF-Crime-shaped video (too big for the CPU oracle)."""
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+
+    frames = _frames(11, 2000 - 7, 240, 320)  # 1993 frames: last clip holds 9 frames
+    ds = TenCropVideoFrameDataset(frames, device=cuda_device)
+    assert len(ds) == 125
+    # clip i of the video == clip 0 of its own 16 frames (frames are independent)
+    sub = TenCropVideoFrameDataset(frames[16 * 77:16 * 78], device=cuda_device)
+    assert torch.equal(ds[77], sub[0])
+    # LoopPad: the short last clip == a clip built from its frames repeated cyclically
+    tail = frames[16 * 124:]
+    cyc = tail[np.arange(16) % len(tail)]
+    assert torch.equal(ds[124], TenCropVideoFrameDataset(cyc, device=cuda_device)[0])
+    # batched and per-clip paths agree; flipped crops are mirror images of the un-flipped block
+    batch = ds.clips_f32(3, 4)
+    assert torch.equal(batch[2], ds[5])
+    c = ds[0]
+    for flipped, plain in ((5, 1), (6, 0), (7, 3), (8, 2)):  # corner crops of the h-flipped image
+        assert torch.equal(c[flipped], torch.flip(c[plain], dims=[-1]))
+
+
+# ----------------------------------------------------------------------------- segment / magnitude
+@pytest.mark.parametrize("n", [2, 5, 31, 32, 33, 47, 125, 188])
+def test_segment_golden_bit_exact(cuda_device, golden_dir, n):
+    from anomaly_detection_on_video_b200.engine import segment_mean
+
+    g = np.load(os.path.join(golden_dir, "segment.npz"))
+    out = segment_mean(torch.from_numpy(g[f"n{n}/in"]).to(cuda_device), 32).cpu().numpy()
+    assert out.dtype == np.float32 and np.array_equal(out, g[f"n{n}/out"])
+
+
+@pytest.mark.parametrize("n", [1, 2000, 12345])
+def test_segment_large_matches_oracle_bit_exact(cuda_device, n):
+    from anomaly_detection_on_video_b200.engine import segment_mean
+
+    f = (np.random.default_rng(n).standard_normal((n, 10, 2048)) * 3).astype(np.float32)
+    out = segment_mean(torch.from_numpy(f).to(cuda_device), 32).cpu().numpy()
+    assert np.array_equal(out, S.segment_features(f, 32))
+
+
+def test_add_magnitude(cuda_device):
+    from anomaly_detection_on_video_b200.dataset import add_magnitude
+
+    f = (np.random.default_rng(2).standard_normal((10, 32, 2048)) * 3).astype(np.float32)
+    out = add_magnitude(torch.from_numpy(f).to(cuda_device)).cpu().numpy()
+    ref = S.add_magnitude(f)
+    assert out.shape == (10, 32, 2049) and np.array_equal(out[..., :2048], f)
+    np.testing.assert_allclose(out[..., 2048], ref[..., 2048], rtol=1e-6)

@@ -1,0 +1,145 @@
+"""Host-side logic that needs no GPU: op table, BN folding, weight packing, work queue (gloo, world 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from anomaly_detection_on_video_b200 import _lib
+from anomaly_detection_on_video_b200.engine import ParamPacker, fold_bn
+from anomaly_detection_on_video_b200.i3d import I3Res50, build_i3d_feature_extractor
+from oracle import i3res50 as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_keys_match_reference_checkpoint_format():
+    m = I3Res50()
+    sd, ref = m.state_dict(), O.seeded_state_dict(0)
+    assert set(sd) == set(ref)
+    assert all(sd[k].shape == ref[k].shape for k in ref)
+    missing, unexpected = m.load_state_dict(ref, strict=True)
+    assert not missing and not unexpected
+    assert sum(p.numel() for p in m.parameters()) == 27_223_872  # 27.22 M
+
+
+def test_op_table_matches_appendix_a():
+    ops = I3Res50().op_table()
+    convs = [o for o in ops if o.kind == _lib.VAD_OP_CONV]
+    assert len(ops) == 56 and len(convs) == 53
+    assert [o.name for o in ops if o.kind == _lib.VAD_OP_MAXPOOL] == ["maxpool1", "maxpool2"]
+    assert ops[-1].kind == _lib.VAD_OP_AVGPOOL
+    stem = convs[0]
+    assert stem.kernel == (5, 7, 7) and stem.stride == (2, 2, 2) and stem.pad == (2, 3, 3)
+    assert stem.flags & _lib.VAD_FLAG_STEM_FOLD_W and stem.cin == 4 and stem.cout == 64
+    by = {o.name: o for o in convs}
+    assert by["layer2.0.conv2"].stride == (1, 2, 2) and by["layer2.0.conv2"].kernel == (1, 3, 3)
+    assert by["layer2.0.downsample"].stride == (1, 2, 2) and not by["layer2.0.downsample"].flags & _lib.VAD_FLAG_RELU
+    # temporal-conv pattern per stage (src/i3d.py:221,228,237,242)
+    tk = lambda n: by[n].kernel[0]
+    assert [tk(f"layer1.{b}.conv1") for b in range(3)] == [3, 3, 3]
+    assert [tk(f"layer2.{b}.conv1") for b in range(4)] == [3, 1, 3, 1]
+    assert [tk(f"layer3.{b}.conv1") for b in range(6)] == [3, 1, 3, 1, 3, 1]
+    assert [tk(f"layer4.{b}.conv1") for b in range(3)] == [1, 3, 1]
+    # every conv3 adds a residual and applies the ReLU after it (src/i3d.py:115-116)
+    for o in convs:
+        if o.name.endswith("conv3"):
+            assert o.res >= 0 and o.flags & _lib.VAD_FLAG_RELU
+        assert o.src != o.dst and o.dst != 0 and o.res != o.dst
+        assert o.w_off % 128 == 0 and o.scale_off % 16 == 0 and o.shift_off % 16 == 0
+
+
+def test_fold_bn_equals_batchnorm_eval():
+    g = torch.Generator().manual_seed(0)
+    bn = torch.nn.BatchNorm3d(16).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(16, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(16, generator=g))
+        bn.running_mean.copy_(torch.randn(16, generator=g))
+        bn.running_var.copy_(torch.rand(16, generator=g) + 0.5)
+    x = torch.randn(2, 16, 3, 5, 5, generator=g)
+    scale, shift = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    got = x * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    torch.testing.assert_close(got, bn(x), rtol=1e-5, atol=1e-5)
+
+
+def test_param_packer_layout():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 16, 3, 1, 1, generator=g)  # K = 48 -> padded to 64
+    pk = ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, torch.ones(8), torch.zeros(8))
+    blob = pk.blob()
+    assert w_off == 0 and s_off % 16 == 0 and b_off % 16 == 0
+    wk = blob[w_off:w_off + 8 * 64 * 2].view(torch.bfloat16).view(8, 64).float()
+    want = w.permute(0, 2, 3, 4, 1).reshape(8, 48).to(torch.bfloat16).float()  # K order (kt, kh, kw, cin)
+    assert torch.equal(wk[:, :48], want) and torch.count_nonzero(wk[:, 48:]) == 0
+    # folded stem: (kt, kh, 8 px, 4 ch) with zero weights for pixel 7 and channel 3
+    ws = torch.randn(64, 3, 5, 7, 7, generator=g)
+    pk2 = ParamPacker()
+    off, _, _ = pk2.add_conv(ws, torch.ones(64), torch.zeros(64), fold_w=True)
+    kpad = (5 * 7 * 32 + 63) // 64 * 64
+    wf = pk2.blob()[off:off + 64 * kpad * 2].view(torch.bfloat16).view(64, kpad).float()
+    wf = wf[:, :5 * 7 * 32].view(64, 5, 7, 8, 4)
+    assert torch.equal(wf[:, :, :, :7, :3], ws.permute(0, 2, 3, 4, 1).to(torch.bfloat16).float())
+    assert torch.count_nonzero(wf[:, :, :, 7]) == 0 and torch.count_nonzero(wf[..., 3]) == 0
+
+
+def test_factory_signature_and_unbuilt_backbone():
+    with pytest.raises(NotImplementedError, match="pytorchvideo"):
+        build_i3d_feature_extractor("i3d_8x8_r50", check_model_size=False)
+    with pytest.raises(AttributeError):
+        build_i3d_feature_extractor("nope")
+    m = build_i3d_feature_extractor("tushar-n-baseline", check_model_size=False)
+    assert isinstance(m, I3Res50) and m.feature_dim == 2048
+
+
+# ----------------------------------------------------------------------------- work queue, world_size 2, gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _wq_worker(rank, world, port, dynamic, outdir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from anomaly_detection_on_video_b200.workqueue import WorkQueue
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q = WorkQueue.from_process_group(dynamic=dynamic)
+    mine = []
+    for n_items in (37, 5):  # two phases, like extract() then segment()
+        got = list(q.claim(n_items, tag=f"phase{n_items}"))
+        # the "work": a deterministic function of the item only -> identical bytes whoever computes it
+        for i in got:
+            np.save(os.path.join(outdir, f"item_{n_items}_{i}.npy"), np.full(4, i * 3 + n_items, dtype=np.float32))
+        mine.append(got)
+        q.barrier()
+    np.save(os.path.join(outdir, f"claims_{rank}.npy"), np.array([len(m) for m in mine]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_workqueue_two_ranks_cover_every_item_once(tmp_path, dynamic):
+    world, port = 2, _free_port()
+    mp.spawn(_wq_worker, args=(world, port, dynamic, str(tmp_path)), nprocs=world, join=True)
+    for n_items in (37, 5):
+        for i in range(n_items):
+            a = np.load(tmp_path / f"item_{n_items}_{i}.npy")
+            assert np.array_equal(a, np.full(4, i * 3 + n_items, dtype=np.float32))
+    claims = sum(np.load(tmp_path / f"claims_{r}.npy") for r in range(world))
+    assert list(claims) == [37, 5]  # nothing claimed twice
+
+
+def test_workqueue_single_process_is_identity():
+    from anomaly_detection_on_video_b200.workqueue import WorkQueue
+
+    assert list(WorkQueue().claim(7)) == list(range(7))
+    assert WorkQueue.from_env() is None or int(os.environ.get("WORLD_SIZE", "1")) > 1
