@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = (
     "vad_plan_slot_info",
     "vad_plan_num_launches",
     "vad_plan_flops",
+    "vad_plan_profile_begin",
+    "vad_plan_profile_end",
     "vad_plan_destroy",
     "vad_ingest_ncthw_f32",
     "vad_preproc_create",
@@ -96,6 +98,10 @@ def load() -> ctypes.CDLL:
     lib.vad_plan_num_launches.argtypes = [c_void_p]
     lib.vad_plan_flops.restype = c_double
     lib.vad_plan_flops.argtypes = [c_void_p]
+    lib.vad_plan_profile_begin.restype = c_int32
+    lib.vad_plan_profile_begin.argtypes = [c_void_p]
+    lib.vad_plan_profile_end.restype = c_int32
+    lib.vad_plan_profile_end.argtypes = [c_void_p, c_int32, POINTER(c_double), POINTER(c_int32), POINTER(c_double), POINTER(c_double)]
     lib.vad_plan_destroy.restype = None
     lib.vad_plan_destroy.argtypes = [c_void_p]
     lib.vad_ingest_ncthw_f32.restype = c_int32

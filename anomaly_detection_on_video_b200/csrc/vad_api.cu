@@ -112,6 +112,17 @@ struct vad_plan {
   EncodeTiledFn encode_tiled = nullptr;
   EncodeIm2colFn encode_im2col = nullptr;
   int driver_version = 0;
+  // optional per-op timing (vad_plan_profile_begin/end): events bracket every launch
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;   // recycled events
+  std::vector<cudaEvent_t> ev_used;   // (n_ops + 1) events per profiled forward, in order
+  std::vector<double> op_flops;       // useful FLOPs per op at the configured size
+  std::vector<double> op_bytes;       // algorithmic bytes per op (inputs read once + outputs written once)
+  std::vector<double> prof_flops, prof_bytes;  // totals over the profiled launches
+  ~vad_plan() {
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_used) cudaEventDestroy(e);
+  }
 };
 
 static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -178,6 +189,8 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
   p->configured = false;
   p->slots.assign(p->n_slots, SlotInfo());
   p->rt.assign(p->ops.size(), OpRuntime());
+  p->op_flops.assign(p->ops.size(), 0.0);
+  p->op_bytes.assign(p->ops.size(), 0.0);
   p->flops = 0.0;
   p->feat_c = 0;
   SlotInfo& s0 = p->slots[0];
@@ -251,7 +264,11 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         c.ldr = rs.C;
       }
       const int cin_real = fold ? 3 : d.cin;
-      p->flops += 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;
+      p->op_flops[i] = 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;
+      p->flops += p->op_flops[i];
+      // activations read once, weights once, output written once (+ residual read)
+      p->op_bytes[i] = 2.0 * ((double)batch * src.T * src.H * src.W * src.C + (double)d.cout * r.K_pad +
+                              (double)M * d.cout * (d.res >= 0 ? 2 : 1));
     } else if (d.kind == VAD_OP_MAXPOOL) {
       PoolParams& q = r.pp;
       memset(&q, 0, sizeof(q));
@@ -274,11 +291,13 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       q.To = To; q.Ho = Ho; q.Wo = Wo;
       q.kt = d.kt; q.kh = d.kh; q.kw = d.kw; q.st = d.st; q.sh = d.sh; q.sw = d.sw;
       q.ldo = Cdst;
+      p->op_bytes[i] = 2.0 * ((double)batch * src.T * src.H * src.W * src.C + (double)batch * To * Ho * Wo * src.C);
     } else {  // AVGPOOL
       if (src.C % 64) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: avg-pool needs C %% 64 == 0", i);
       r.avg_P = src.T * src.H * src.W;
       r.avg_C = src.C;
       p->feat_c = src.C;
+      p->op_bytes[i] = 2.0 * batch * (double)r.avg_P * src.C + 4.0 * batch * src.C;
       continue;
     }
     SlotInfo& dst = p->slots[d.dst];
@@ -424,6 +443,15 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
     int32_t rc = bind_plan(p, x_dev, workspace_dev);
     if (rc != VAD_OK) return rc;
   }
+  auto mark = [&]() -> cudaError_t {
+    if (!p->profiling) return cudaSuccess;
+    cudaEvent_t ev;
+    if (!p->ev_pool.empty()) { ev = p->ev_pool.back(); p->ev_pool.pop_back(); }
+    else { cudaError_t ce = cudaEventCreate(&ev); if (ce != cudaSuccess) return ce; }
+    p->ev_used.push_back(ev);
+    return cudaEventRecord(ev, st);
+  };
+  if (mark() != cudaSuccess) return fail(VAD_ERR_CUDA, "profiling event failed");
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const vad_op_desc& d = p->ops[i];
     const OpRuntime& r = p->rt[i];
@@ -444,7 +472,47 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
       e = cudaGetLastError();
     }
     if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "op %zu launch failed: %s", i, cudaGetErrorString(e));
+    if (mark() != cudaSuccess) return fail(VAD_ERR_CUDA, "profiling event failed");
+    if (p->profiling) { p->prof_flops[i] += p->op_flops[i]; p->prof_bytes[i] += p->op_bytes[i]; }
   }
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_plan_profile_begin(vad_plan_t* p) {
+  if (!p) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_profile_begin: null plan");
+  for (cudaEvent_t e : p->ev_used) p->ev_pool.push_back(e);
+  p->ev_used.clear();
+  p->prof_flops.assign(p->ops.size(), 0.0);
+  p->prof_bytes.assign(p->ops.size(), 0.0);
+  p->profiling = true;
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_plan_profile_end(vad_plan_t* p, int32_t n_ops, double* op_ms_sum, int32_t* op_calls,
+                                        double* op_flops, double* op_bytes) {
+  if (!p || !p->profiling) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_profile_end: profiling was not started");
+  p->profiling = false;
+  const size_t n = p->ops.size();
+  if (n_ops != (int32_t)n) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_profile_end: expected %zu ops", n);
+  for (size_t i = 0; i < n; ++i) {
+    if (op_ms_sum) op_ms_sum[i] = 0.0;
+    if (op_calls) op_calls[i] = 0;
+    if (op_flops) op_flops[i] = p->prof_flops[i];
+    if (op_bytes) op_bytes[i] = p->prof_bytes[i];
+  }
+  if (p->ev_used.empty()) return VAD_OK;
+  VAD_CUDA_CHECK(cudaEventSynchronize(p->ev_used.back()));
+  const size_t per = n + 1;
+  for (size_t f = 0; f + per <= p->ev_used.size(); f += per) {
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      VAD_CUDA_CHECK(cudaEventElapsedTime(&ms, p->ev_used[f + i], p->ev_used[f + i + 1]));
+      if (op_ms_sum) op_ms_sum[i] += ms;
+      if (op_calls) op_calls[i] += 1;
+    }
+  }
+  for (cudaEvent_t e : p->ev_used) p->ev_pool.push_back(e);
+  p->ev_used.clear();
   return VAD_OK;
 }
 

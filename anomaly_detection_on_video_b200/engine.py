@@ -174,6 +174,20 @@ class BackbonePlan:
     def num_launches(self) -> int:
         return int(self.lib.vad_plan_num_launches(self._h))
 
+    def profile_begin(self) -> None:
+        check(self.lib.vad_plan_profile_begin(self._h), "vad_plan_profile_begin")
+
+    def profile_end(self) -> List[Dict[str, object]]:
+        """Per-op totals since ``profile_begin``: name, kind, ms, launches, useful FLOPs, algorithmic bytes."""
+        n = len(self.ops)
+        ms = (ctypes.c_double * n)()
+        calls = (ctypes.c_int32 * n)()
+        flops = (ctypes.c_double * n)()
+        nbytes = (ctypes.c_double * n)()
+        check(self.lib.vad_plan_profile_end(self._h, n, ms, calls, flops, nbytes), "vad_plan_profile_end")
+        return [{"name": op.name, "kind": op.kind, "ms": float(ms[i]), "calls": int(calls[i]), "flops": float(flops[i]),
+                 "bytes": float(nbytes[i])} for i, op in enumerate(self.ops)]
+
     def feature_dim(self) -> int:
         for op in reversed(self.ops):
             if op.kind == _lib.VAD_OP_AVGPOOL:

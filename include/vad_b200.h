@@ -124,6 +124,14 @@ int32_t vad_plan_num_launches(const vad_plan_t* plan);
 /* Conv FLOPs (2 * MAC, useful taps only) of one forward at the configured size. */
 double vad_plan_flops(const vad_plan_t* plan);
 
+/* Per-op device timing for roofline reports.  Between begin and end every vad_plan_forward brackets
+ * each launch with CUDA events on the launching stream (no synchronisation is added); end waits for
+ * the last event and returns, per op, totals over the timed launches: milliseconds, launch count,
+ * useful FLOPs and algorithmic bytes (each input / output tensor touched once). */
+int32_t vad_plan_profile_begin(vad_plan_t* plan);
+int32_t vad_plan_profile_end(vad_plan_t* plan, int32_t n_ops, double* op_ms_sum, int32_t* op_calls,
+                             double* op_flops, double* op_bytes);
+
 void vad_plan_destroy(vad_plan_t* plan);
 
 /* fp32 NCTHW clips (what the reference feeds its model: extract_features.py:83-86) -> stem layout.
