@@ -62,7 +62,7 @@ def test_features_track_the_bf16_emulating_oracle(model, cuda_device):
     y16, _ = O.forward(x, sd, emulate_bf16=True)
     y = model(x.to(cuda_device)).cpu()
     scale = y32.abs().max()
-    assert ((y - y16).abs().max() / scale).item() < 7e-3
+    assert ((y - y16).abs().max() / scale).item() < 8e-3
     assert ((y - y32).abs().max() / scale).item() < MAX_NORM_TOL
 
 
