@@ -262,12 +262,14 @@ def section_timing():
     m = I3Res50()
     m.load_state_dict(O.seeded_state_dict(0))
     m.eval().cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
     res = []
-    for B in [16, 64, 160]:
-        xs = torch.randn(B, 16, 224, 232, 4, device="cuda").to(torch.bfloat16)
+    for B in [16, 160]:
+        xs = torch.randn(B, 16, 224, 232, 4, device=dev).to(torch.bfloat16)
         for _ in range(2):
             m.forward_stem_layout(xs)
         torch.cuda.synchronize()
+        plan = m.plan(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 5
         e0.record()
@@ -276,11 +278,30 @@ def section_timing():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        plan = m.plan(torch.device("cuda"))
-        rec = {"name": f"forward B={B}", "ms": ms, "clips_per_s": B / ms * 1e3, "tflops": plan.flops / ms / 1e9,
-               "flops_per_clip": plan.flops / B}
+        rec = {"name": f"forward B={B}", "ms": ms, "clips_per_s": B / ms * 1e3, "tflops": plan.flops / ms / 1e9}
         print(json.dumps(rec), flush=True)
         res.append(rec)
+        if B == 160:
+            plan.profile_begin()
+            for _ in range(3):
+                m.forward_stem_layout(xs)
+            prof = plan.profile_end()
+            for p in prof:
+                if not p["calls"]:
+                    continue
+                t = p["ms"] / p["calls"]
+                print("%-22s %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s(alg)" % (p["name"], t, p["flops"] / p["calls"] / t / 1e9,
+                                                                      p["bytes"] / p["calls"] / t / 1e6), flush=True)
+    # host link
+    h = torch.empty(460_800_000, dtype=torch.uint8).pin_memory()
+    d = torch.empty_like(h, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        t0 = time.perf_counter()
+        d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    print(json.dumps({"name": "h2d pinned 460.8MB", "ms": dt * 1e3, "GB/s": 0.4608 / dt}), flush=True)
     return res
 
 
