@@ -55,20 +55,27 @@ struct ConvParams {
 constexpr int kBlockM = 128;
 constexpr int kUmmaK = 16;
 
-template <int BN, int BK, bool GATHER>
+template <int BN, int BK, bool GATHER, bool EPI>
 struct ConvCfg {
   static_assert(BK == 64 || BK == 32, "BK is one swizzle row: 64 (SW128) or 32 (SW64) bf16");
   static_assert(!GATHER || BK == 64, "the gather producer writes 128-byte swizzled rows");
+  static_assert(!EPI || BN <= 128, "the staged epilogue keeps two 128 x BN bf16 tiles in shared memory");
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kABytes = kBlockM * kRowBytes;
   static constexpr int kBBytes = BN * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 16 ? 16 : (196608 / kStageBytes);
+  // EPI: residual tile prefetched by TMA / output tile written back by TMA, double buffered;
+  // laid out as BN/64 sub-tiles of [128 rows x 64 cols] (128-byte rows, SWIZZLE_128B)
+  static constexpr int kEpiSubBytes = kBlockM * 128;
+  static constexpr int kEpiBufBytes = EPI ? (BN / 64) * kEpiSubBytes : 0;
+  static constexpr int kPipeBudget = 196608 - 2 * kEpiBufBytes;
+  static constexpr int kStages = (kPipeBudget / kStageBytes) > 16 ? 16 : (kPipeBudget / kStageBytes);
   static constexpr int kThreads = GATHER ? 320 : 192;
   static constexpr int kGatherLag = kStages - 2 > 6 ? 6 : kStages - 2;  // cp.async groups in flight per thread
   static constexpr int kTmemCols = 2 * BN;                              // two accumulator stages
   // stages + scale/shift staging + barriers + tmem slot, + 1024 for manual alignment
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * BN * 4 + (2 * kStages + 4) * 8 + 16 + 1024;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 2 * kEpiBufBytes + 2 * BN * 4 + (2 * kStages + 8) * 8 + 16 + 1024;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -88,11 +95,12 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN, int BK, bool GATHER>
-__global__ void __launch_bounds__(ConvCfg<BN, BK, GATHER>::kThreads, 1)
+template <int BN, int BK, bool GATHER, bool EPI>
+__global__ void __launch_bounds__(ConvCfg<BN, BK, GATHER, EPI>::kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvParams p) {
-  using Cfg = ConvCfg<BN, BK, GATHER>;
+  using Cfg = ConvCfg<BN, BK, GATHER, EPI>;
   constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -100,13 +108,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   uint8_t* stage_base = smem;
-  float* s_scale = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* epi_base = smem + STAGES * Cfg::kStageBytes;  // 2 x kEpiBufBytes, 1024-aligned
+  float* s_scale = reinterpret_cast<float*>(epi_base + 2 * Cfg::kEpiBufBytes);
   float* s_shift = s_scale + BN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;    // [2] residual tile landed (EPI)
+  uint64_t* res_empty_bar = res_full_bar + 2;     // [2] epilogue buffer free again (EPI)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,6 +132,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&res_full_bar[a], 1);
+      mbar_init(&res_empty_bar[a], 4);
+    }
+    if (EPI) {
+      tma_prefetch_desc(&tmR);
+      tma_prefetch_desc(&tmO);
     }
     fence_barrier_init();
   }
@@ -137,10 +154,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t tx = GATHER ? Cfg::kBBytes : Cfg::kStageBytes;
-      int kbc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int kbc = 0, tcp = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcp) {
         const int n0 = (tile % p.n_tiles) * BN;
         const int m0 = (tile / p.n_tiles) * kBlockM;
+        if (EPI) {
+          // residual tile of this output tile -> epilogue buffer (free once the stores of the tile that
+          // used it two tiles ago have been read out)
+          const int rb = tcp & 1;
+          mbar_wait(&res_empty_bar[rb], ((tcp >> 1) & 1) ^ 1);
+          int nsub = (p.N - n0 + 63) / 64;
+          nsub = nsub > BN / 64 ? BN / 64 : nsub;
+          mbar_arrive_expect_tx(&res_full_bar[rb], (uint32_t)(nsub * Cfg::kEpiSubBytes));
+          for (int j = 0; j < nsub; ++j)
+            tma_load_2d(epi_base + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, &res_full_bar[rb], n0 + 64 * j, m0);
+        }
         int wq = 0, hq = 0, dq = 0, nq = 0;
         if (!GATHER && p.a_mode == A_TMA_IM2COL) {
           int t = m0;
@@ -233,6 +261,58 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if (EPI) {
+        // residual (TMA-prefetched) is read from, and the bf16 result written back to, the same swizzled
+        // shared-memory tile; each warp then TMA-stores its 32 rows (full 128-byte lines, clipped at M / N)
+        mbar_wait(&res_full_bar[acc], aph);
+        const int lrow = q * 32 + lane;
+        const uint32_t buf = smem_u32(epi_base + acc * Cfg::kEpiBufBytes) + (uint32_t)lrow * 128u;
+        const uint32_t xr = (uint32_t)(lrow & 7);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = c * 32 + g * 8;
+            const uint32_t addr = buf + (uint32_t)(col >> 6) * Cfg::kEpiSubBytes + ((((uint32_t)(col & 63) >> 3) ^ xr) << 4);
+            uint4 r;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col + j], s_shift[col + j]);
+            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+            f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+            f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            const uint32_t o0 = pack_bf16x2(f[0], f[1]), o1 = pack_bf16x2(f[2], f[3]);
+            const uint32_t o2 = pack_bf16x2(f[4], f[5]), o3 = pack_bf16x2(f[6], f[7]);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may start tile i+2
+        fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+          int nsub = (p.N - n0 + 63) / 64;
+          nsub = nsub > BN / 64 ? BN / 64 : nsub;
+          for (int j = 0; j < nsub; ++j)
+            tma_store_2d(&tmO, epi_base + acc * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes + q * 32 * 128, n0 + 64 * j,
+                         m0 + q * 32);
+          tma_store_commit();
+          tma_store_wait_read<0>();          // smem may be overwritten once the store engine has read it
+          mbar_arrive(&res_empty_bar[acc]);  // 4 arrivals (one per epilogue warp) free the buffer
+        }
+        __syncwarp();
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -336,6 +416,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
+  if (EPI && warp >= 2 && warp < 6 && lane == 0) tma_store_wait<0>();  // bulk stores fully complete
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

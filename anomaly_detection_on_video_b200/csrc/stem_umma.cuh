@@ -1,0 +1,202 @@
+// K2s: the I3D stem (conv 5x7x7, stride 2, 3 -> 64 channels + BN + ReLU; src/i3d.py:202-209,303-305) as
+// a dedicated tcgen05 kernel.
+//
+// The generic implicit-GEMM kernel loads one 128-pixel x 64-byte im2col column per (dt, dh) tap, i.e. it
+// pulls every input pixel ~35 times through L2 -- the stem is then L2-bandwidth bound, not tensor bound.
+// Here an output tile is a 16 (w) x 8 (h) block of one output frame, so for a fixed dt the seven dh taps
+// read overlapping input rows: rows 2*ho0 - 3 + dh + 2*i, i = 0..7.  All even dh share ONE TMA box of 11
+// rows (stride 2), all odd dh one box of 10 rows; tap dh is the same shared-memory box at a row offset of
+// (dh / 2) * 16 pixels = 1024 B (a multiple of the 512-byte SWIZZLE_64B atom, so UMMA descriptors can
+// point straight into the box).  L2 -> SM traffic drops from 35 x 8 KB to 5 x 21 KB per tile, and the
+// 140 KB of weights stay resident in shared memory for the whole persistent CTA.
+//
+// A operand: the padded input [N, T, H, Wp, 4] bf16 viewed through a rank-5 *tiled* tensor map as
+// (C' = 32, W' = Wo, H, T, N): pixel w' is the 8-pixel x 4-channel window at padded column 2 * w'
+// (W' stride 16 B < 64 B extent: windows overlap), kw folded into the contraction like the generic path.
+// TMA zero-fills every out-of-range row / frame, which implements the conv padding.
+#pragma once
+
+#include "conv_umma.cuh"
+
+namespace vad {
+
+struct StemParams {
+  int B, To, Ho, Wo;
+  int kt, kh, st, pt, ph;  // sh == sw == 2, kw folded
+  int tiles_w, tiles_h, num_tiles;
+  int rows_even, rows_odd;  // box rows: 8 + (#taps of that parity) - 1
+  int off_odd;              // byte offset of the odd-row box inside a stage
+  int stage_bytes;
+  int n_stages;
+  int relu;
+  int ldo;
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out;
+};
+
+constexpr int kStemThreads = 192;
+constexpr int kStemTapBytes = 64 * 64;  // one tap of weights: 64 output channels x 32 bf16
+
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmOdd,
+                 const __grid_constant__ CUtensorMap tmW, const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int ntaps = p.kt * p.kh;
+  uint8_t* w_smem = smem;                                  // ntaps x 4 KB, resident
+  uint8_t* stage_base = smem + ntaps * kStemTapBytes;      // n_stages x stage_bytes
+  float* s_scale = reinterpret_cast<float*>(stage_base + p.n_stages * p.stage_bytes);
+  float* s_shift = s_scale + 64;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 64);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* w_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.n_stages;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmE);
+    tma_prefetch_desc(&tmOdd);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);  // two 64-column accumulators
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 64) {
+      s_scale[t] = p.scale[t];
+      s_shift[t] = p.shift[t];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
+      for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
+      int kc = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int wb = r % p.tiles_w; r /= p.tiles_w;
+        const int hb = r % p.tiles_h; r /= p.tiles_h;
+        const int to = r % p.To;
+        const int n = r / p.To;
+        const int h_start = 2 * (hb * 8) - p.ph;
+        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+          const int s = kc % S;
+          const uint32_t ph = (kc / S) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* dst = stage_base + s * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+          const int ti = to * p.st - p.pt + dt;
+          tma_load_5d(dst, &tmE, &full_bar[s], 0, wb * 16, h_start, ti, n);
+          tma_load_5d(dst + p.off_odd, &tmOdd, &full_bar[s], 0, wb * 16, h_start + 1, ti, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+      mbar_wait(w_bar, 0);
+      int kc = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+        const int acc = tc & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+          const int s = kc % S;
+          mbar_wait(&full_bar[s], (kc / S) & 1);
+          tc_fence_after();
+          const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
+          for (int dh = 0; dh < p.kh; ++dh) {
+            const uint32_t a_addr = st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * 1024u;
+            const uint32_t b_addr = smem_u32(w_smem) + (uint32_t)(dt * p.kh + dh) * kStemTapBytes;
+            const uint64_t adesc = umma_desc_kmajor<64>(a_addr);
+            const uint64_t bdesc = umma_desc_kmajor<64>(b_addr);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dt | dh | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int lrow = q * 32 + lane;  // tile row = TMEM lane: (h_i, w_i) = (lrow / 16, lrow % 16)
+    int tc = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+      int r = tile;
+      const int wb = r % p.tiles_w; r /= p.tiles_w;
+      const int hb = r % p.tiles_h; r /= p.tiles_h;
+      const int to = r % p.To;
+      const int n = r / p.To;
+      const int ho = hb * 8 + (lrow >> 4);
+      const int wo = wb * 16 + (lrow & 15);
+      const bool ok = ho < p.Ho && wo < p.Wo;
+      const int acc = tc & 1;
+      mbar_wait(&tmem_full_bar[acc], (tc >> 1) & 1);
+      tc_fence_after();
+      __nv_bfloat16* out_px = p.out + ((((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo) * (long long)p.ldo;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = c * 32 + g * 8;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col + j], s_shift[col + j]);
+              if (p.relu) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(out_px + col) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+}  // namespace vad

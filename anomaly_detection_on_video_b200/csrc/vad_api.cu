@@ -13,6 +13,7 @@
 
 #include "aux_kernels.cuh"
 #include "conv_umma.cuh"
+#include "stem_umma.cuh"
 
 using namespace vad;
 
@@ -83,11 +84,17 @@ struct SlotInfo {
 struct OpRuntime {
   ConvParams cp;
   PoolParams pp;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmR, tmO;
+  bool epi = false;   // residual prefetched / output stored by TMA through shared memory
+  int res_c = 0, dst_c = 0;
   int bn = 0;
   int bk = 64;
   int grid = 0;
   bool fold = false;
+  bool stem = false;  // dedicated stem kernel (spatial tiles, resident weights)
+  StemParams sp;
+  CUtensorMap tmE, tmOdd, tmW;
+  int stem_smem = 0;
   int a_mode = 0;
   int avg_P = 0, avg_C = 0;
   // for tensor-map encoding
@@ -104,6 +111,8 @@ struct vad_plan {
   int in_channels = 0;
   int device = 0;
   int sm_count = 148;
+  bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
+  bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool stem_gather = false;  // VAD_STEM_GATHER=1: feed the stem through the cp.async gather producer
   int batch = 0, T = 0, H = 0, W = 0;
   bool configured = false;
@@ -183,6 +192,10 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   if (p->sm_count <= 0) p->sm_count = 148;
   const char* sg = getenv("VAD_STEM_GATHER");
   p->stem_gather = sg && sg[0] == '1';
+  const char* sgen = getenv("VAD_STEM_GENERIC");
+  p->stem_generic = sgen && sgen[0] == '1';
+  const char* ne = getenv("VAD_NO_EPI");
+  p->no_epi = ne && ne[0] == '1';
   *plan = p;
   return VAD_OK;
 }
@@ -246,6 +259,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       r.K_pad = (int)align_up(K, 64);  // packed weight rows are padded to 64 whatever BK the kernel uses
       c.relu = (d.flags & VAD_FLAG_RELU) ? 1 : 0;
       c.ldo = Cdst;
+      r.dst_c = Cdst;
       const bool unit = d.kt == 1 && d.kh == 1 && d.kw == 1 && d.st == 1 && d.sh == 1 && d.sw == 1 && !d.pt && !d.ph && !d.pw;
       const bool tma_geom_ok = d.pt <= 15 && d.ph <= 15 && d.pw <= 15 && d.kt <= 16 && d.kh <= 16 && d.kw <= 16 &&
                                d.st <= 8 && d.sh <= 8 && d.sw <= 8;
@@ -261,7 +275,8 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         r.a_mode = A_TMA_IM2COL;
       c.a_mode = r.a_mode;
       c.num_kb = r.bk == 64 ? r.K_pad / 64 : (K + 31) / 32;
-      r.bn = d.cout > 128 ? 256 : (d.cout > 64 ? 128 : 64);
+      r.epi = d.res >= 0 && !p->no_epi;  // residual layers: staged epilogue (two 128 x BN tiles in smem)
+      r.bn = (d.cout > 128 && !r.epi) ? 256 : (d.cout > 64 ? 128 : 64);
       const long long m_tiles = (M + kBlockM - 1) / kBlockM;
       const long long n_tiles = (d.cout + r.bn - 1) / r.bn;
       if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
@@ -269,6 +284,30 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
+      r.stem = false;
+      if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0) {
+        StemParams& q = r.sp;
+        memset(&q, 0, sizeof(q));
+        q.B = batch; q.To = To; q.Ho = Ho; q.Wo = Wo;
+        q.kt = d.kt; q.kh = d.kh; q.st = d.st; q.pt = d.pt; q.ph = d.ph;
+        q.tiles_w = (Wo + 15) / 16; q.tiles_h = (Ho + 7) / 8;
+        const long long nt = (long long)batch * To * q.tiles_h * q.tiles_w;
+        q.rows_even = 8 + (d.kh + 1) / 2 - 1;
+        q.rows_odd = 8 + d.kh / 2 - 1;
+        q.off_odd = q.rows_even * 1024;
+        q.stage_bytes = (q.rows_even + (d.kh > 1 ? q.rows_odd : 0)) * 1024;
+        const int w_bytes = d.kt * d.kh * kStemTapBytes;
+        int ns = (220 * 1024 - w_bytes) / q.stage_bytes;
+        if (ns > 4) ns = 4;
+        if (ns >= 2 && nt <= 0x7fffffffLL && d.kh > 1) {
+          q.n_stages = ns;
+          q.num_tiles = (int)nt;
+          q.relu = c.relu; q.ldo = Cdst;
+          r.stem_smem = w_bytes + ns * q.stage_bytes + 2 * 64 * 4 + (8 + 8 + 2 + 2 + 1) * 8 + 16 + 1024;
+          r.stem = true;
+          r.grid = q.num_tiles < p->sm_count ? q.num_tiles : p->sm_count;
+        }
+      }
       const uint64_t need_w = d.w_off + (uint64_t)d.cout * r.K_pad * 2;
       if (need_w > p->params_bytes || d.scale_off + 4ull * d.cout > p->params_bytes || d.shift_off + 4ull * d.cout > p->params_bytes)
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: parameters exceed the blob (%llu > %llu)", i,
@@ -278,6 +317,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         if (!rs.defined || rs.T != To || rs.H != Ho || rs.W != Wo || rs.C < d.cout)
           return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: residual slot %d shape mismatch", i, d.res);
         c.ldr = rs.C;
+        r.res_c = rs.C;
       }
       const int cin_real = fold ? 3 : d.cin;
       p->op_flops[i] = 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;
@@ -385,7 +425,60 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(weights) failed: %d", i, (int)cr);
       }
       memset(&r.tmA, 0, sizeof(r.tmA));
-      if (r.a_mode == A_TMA_2D) {
+      memset(&r.tmR, 0, sizeof(r.tmR));
+      memset(&r.tmO, 0, sizeof(r.tmO));
+      if (r.epi) {
+        // residual [M, res_c] -> 128-row x 64-channel boxes; output slice [M, cout] (row pitch dst_c) <- 32-row boxes
+        cuuint64_t rdim[2] = {(cuuint64_t)r.res_c, (cuuint64_t)c.M};
+        cuuint64_t rstr[1] = {(cuuint64_t)r.res_c * 2};
+        cuuint32_t rbox[2] = {64, (cuuint32_t)kBlockM};
+        cuuint32_t es2[2] = {1, 1};
+        CUresult cr = p->encode_tiled(&r.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c.res, rdim, rstr, rbox, es2,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(residual) failed: %d", i, (int)cr);
+        cuuint64_t odim[2] = {(cuuint64_t)d.cout, (cuuint64_t)c.M};
+        cuuint64_t ostr[1] = {(cuuint64_t)r.dst_c * 2};
+        cuuint32_t obox[2] = {64, 32};
+        cr = p->encode_tiled(&r.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c.out, odim, ostr, obox, es2,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(output) failed: %d", i, (int)cr);
+      }
+      if (r.stem) {
+        // rank-5 tiled maps over the overlapping window view (C' = 32, W' = Wo, H, T, N); even / odd input
+        // rows of one dt are two boxes of 16 windows x rows (row stride 2)
+        StemParams& q = r.sp;
+        q.scale = c.scale; q.shift = c.shift; q.out = c.out;
+        const uint64_t wp = (uint64_t)p->slots[0].W;
+        cuuint64_t gdim[5] = {32, (cuuint64_t)c.Wo, (cuuint64_t)r.Hi, (cuuint64_t)r.Ti, (cuuint64_t)p->batch};
+        cuuint64_t gstr[4];
+        gstr[0] = (cuuint64_t)d.sw * 4 * 2;
+        gstr[1] = wp * 4 * 2;
+        gstr[2] = gstr[1] * r.Hi;
+        gstr[3] = gstr[2] * r.Ti;
+        cuuint32_t es[5] = {1, 1, 2, 1, 1};
+        cuuint32_t boxE[5] = {32, 16, (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
+        cuuint32_t boxO[5] = {32, 16, (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
+        CUresult cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxE, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS)
+          cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxO, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS) {
+          cuuint64_t wdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
+          cuuint64_t wstr[1] = {(cuuint64_t)r.K_pad * 2};
+          cuuint32_t wbox[2] = {32, 64};
+          cuuint32_t wes[2] = {1, 1};
+          cr = p->encode_tiled(&r.tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), wdim, wstr, wbox,
+                               wes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (cr != CUDA_SUCCESS)
+          return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(stem) failed: %d; set VAD_STEM_GENERIC=1", i, (int)cr);
+      } else if (r.a_mode == A_TMA_2D) {
         cuuint64_t gdim[2] = {(cuuint64_t)r.Ci, (cuuint64_t)c.M};
         cuuint64_t gstr[1] = {(cuuint64_t)r.Ci * 2};
         cuuint32_t box[2] = {(cuuint32_t)64, (cuuint32_t)kBlockM};
@@ -451,27 +544,31 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
   return VAD_OK;
 }
 
-template <int BN, int BK, bool GATHER>
+template <int BN, int BK, bool GATHER, bool EPI>
 static cudaError_t launch_conv(const OpRuntime& r, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, BK, GATHER>;
+  using Cfg = ConvCfg<BN, BK, GATHER, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, GATHER, EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_umma_kernel<BN, BK, GATHER><<<r.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(r.tmA, r.tmB, r.cp);
+  conv_umma_kernel<BN, BK, GATHER, EPI><<<r.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
   return cudaGetLastError();
 }
 
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
   const bool g = r.a_mode == A_GATHER;
-  if (r.bk == 32) return launch_conv<64, 32, false>(r, st);  // folded stem, TMA window view
+  if (r.bk == 32) return launch_conv<64, 32, false, false>(r, st);  // folded stem, TMA window view
+  if (r.epi) {
+    if (r.bn == 128) return g ? launch_conv<128, 64, true, true>(r, st) : launch_conv<128, 64, false, true>(r, st);
+    return g ? launch_conv<64, 64, true, true>(r, st) : launch_conv<64, 64, false, true>(r, st);
+  }
   switch (r.bn) {
-    case 256: return g ? launch_conv<256, 64, true>(r, st) : launch_conv<256, 64, false>(r, st);
-    case 128: return g ? launch_conv<128, 64, true>(r, st) : launch_conv<128, 64, false>(r, st);
-    default:  return g ? launch_conv<64, 64, true>(r, st) : launch_conv<64, 64, false>(r, st);
+    case 256: return g ? launch_conv<256, 64, true, false>(r, st) : launch_conv<256, 64, false, false>(r, st);
+    case 128: return g ? launch_conv<128, 64, true, false>(r, st) : launch_conv<128, 64, false, false>(r, st);
+    default:  return g ? launch_conv<64, 64, true, false>(r, st) : launch_conv<64, 64, false, false>(r, st);
   }
 }
 
@@ -510,7 +607,19 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
     const OpRuntime& r = p->rt[i];
     cudaError_t e = cudaSuccess;
     if (d.kind == VAD_OP_CONV) {
-      e = launch_conv_any(r, st);
+      if (r.stem) {
+        static bool stem_attr = false;
+        if (!stem_attr) {
+          e = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          stem_attr = (e == cudaSuccess);
+        }
+        if (e == cudaSuccess) {
+          stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.sp);
+          e = cudaGetLastError();
+        }
+      } else {
+        e = launch_conv_any(r, st);
+      }
     } else if (d.kind == VAD_OP_MAXPOOL) {
       const long long total = (long long)r.pp.B * r.pp.To * r.pp.Ho * r.pp.Wo * (r.pp.C / 8);
       maxpool3d_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(r.pp);
