@@ -322,6 +322,8 @@ def run_section(name: str):
         return _net((2, 3, 16, 224, 224))
     if name == "timing":
         return section_timing()
+    if name == "e2e":
+        return section_e2e_breakdown()
     raise SystemExit(f"unknown section {name}")
 
 
@@ -352,3 +354,40 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def section_e2e_breakdown():
+    """Where does the end-to-end (host frames -> host features) step spend its time?"""
+    import numpy as np
+    import torch
+
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+    from anomaly_detection_on_video_b200.engine import segment_mean
+    from anomaly_detection_on_video_b200.extract_features import extract_clip_features
+    from anomaly_detection_on_video_b200.i3d import I3Res50
+    from oracle import i3res50 as O
+
+    dev = torch.device("cuda", 0)
+    m = I3Res50()
+    m.load_state_dict(O.seeded_state_dict(0))
+    m.eval().to(dev)
+    frames = torch.from_numpy(np.random.default_rng(0).integers(0, 256, size=(2000, 240, 320, 3), dtype=np.uint8)).pin_memory()
+
+    def sync():
+        torch.cuda.synchronize()
+        return time.perf_counter()
+
+    for it in range(3):
+        t0 = sync()
+        ds = TenCropVideoFrameDataset(frames, device=dev)
+        t1 = sync()
+        feats = extract_clip_features(ds, m, dev, strict_compat=False, as_numpy=False)
+        t2 = sync()
+        seg = segment_mean(feats, 32)
+        t3 = sync()
+        fh, sh = feats.cpu(), seg.cpu()
+        t4 = sync()
+        del ds
+        t5 = sync()
+        print(json.dumps({"iter": it, "dataset_ctor_h2d_ms": (t1 - t0) * 1e3, "extract_ms": (t2 - t1) * 1e3,
+                          "segment_ms": (t3 - t2) * 1e3, "d2h_ms": (t4 - t3) * 1e3, "free_ms": (t5 - t4) * 1e3}), flush=True)
