@@ -218,10 +218,25 @@ def main():
 
     def step_e2e():
         """public API from pinned host frames: H2D of the frames, D2H of features + segments."""
+        dbg = os.environ.get("VAD_BENCH_DEBUG") == "1"
+        tt = [time.perf_counter()]
+
+        def lap():
+            if dbg:
+                torch.cuda.synchronize(dev)
+                tt.append(time.perf_counter())
+
         d = TenCropVideoFrameDataset(frames_host, device=dev)
+        lap()
         feats = extract_clip_features(d, model, dev, clips_per_batch=cpb, strict_compat=False, as_numpy=False)
+        lap()
         seg = segment_mean(feats, 32)
-        return feats.cpu(), seg.cpu()
+        out = feats.cpu(), seg.cpu()
+        lap()
+        if dbg:
+            print("e2e phases ms (ctor+h2d, extract, segment+d2h):", [round((b - a) * 1e3, 2) for a, b in zip(tt, tt[1:])],
+                  file=sys.stderr, flush=True)
+        return out
 
     for _ in range(W):
         step_resident()

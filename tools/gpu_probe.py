@@ -352,9 +352,6 @@ def main():
         json.dump(summary, f, indent=1)
 
 
-if __name__ == "__main__":
-    main()
-
 
 def section_e2e_breakdown():
     """Where does the end-to-end (host frames -> host features) step spend its time?"""
@@ -391,3 +388,6 @@ def section_e2e_breakdown():
         t5 = sync()
         print(json.dumps({"iter": it, "dataset_ctor_h2d_ms": (t1 - t0) * 1e3, "extract_ms": (t2 - t1) * 1e3,
                           "segment_ms": (t3 - t2) * 1e3, "d2h_ms": (t4 - t3) * 1e3, "free_ms": (t5 - t4) * 1e3}), flush=True)
+
+if __name__ == "__main__":
+    main()
