@@ -199,4 +199,203 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v2: no im2col copy at all.  An output tile is 8 (w) x 16 (h); for one input row the 8 windows of
+// 8 pixels x 4 channels start 16 B apart and overlap, and together cover one contiguous 176-byte segment
+// of the padded row.  A K-major SWIZZLE_NONE UMMA descriptor addresses the operand as
+//     addr(row r, 16-byte K chunk j) = start + (r % 8) * 16 + (r / 8) * SBO + j * LBO
+// so with LBO = 16 B (the window stride) and SBO = the 176-byte segment pitch, the tensor core reads the
+// sliding windows straight out of the raw segment: row (h_i, w_i) = h_i * 8 + w_i sees bytes
+// [16 * w_i, 16 * w_i + 64) of segment h_i.  A (dt) stage is two TMA boxes of raw segments (even / odd
+// input rows, 19 + 18 segments = 6.5 KB) instead of 35 KB of im2col columns.
+struct StemV2Params {
+  StemParams s;
+  int seg_bytes;  // bytes of one raw row segment (176 for stride 2)
+};
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100); layout type 0 = no swizzle
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+constexpr int kStemV2MaxStages = 8;
+
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_umma_v2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmOdd,
+                    const __grid_constant__ CUtensorMap tmW, const StemV2Params pp) {
+  const StemParams& p = pp.s;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int ntaps = p.kt * p.kh;
+  uint8_t* w_smem = smem;
+  uint8_t* stage_base = smem + ntaps * kStemTapBytes;
+  float* s_scale = reinterpret_cast<float*>(stage_base + p.n_stages * p.stage_bytes);
+  float* s_shift = s_scale + 64;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 64);
+  uint64_t* empty_bar = full_bar + kStemV2MaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kStemV2MaxStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* w_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.n_stages;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmE);
+    tma_prefetch_desc(&tmOdd);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 64) {
+      s_scale[t] = p.scale[t];
+      s_shift[t] = p.shift[t];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
+      for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
+      const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * pp.seg_bytes);
+      int kc = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int wb = r % p.tiles_w; r /= p.tiles_w;
+        const int hb = r % p.tiles_h; r /= p.tiles_h;
+        const int to = r % p.To;
+        const int n = r / p.To;
+        const int h_start = 2 * (hb * 16) - p.ph;
+        const int x_start = wb * 8 * 8;  // 8 windows x (2 px x 4 ch) elements
+        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+          const int s = kc % S;
+          mbar_wait(&empty_bar[s], ((kc / S) & 1) ^ 1);
+          uint8_t* dst = stage_base + s * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], tx);
+          const int ti = to * p.st - p.pt + dt;
+          tma_load_4d(dst, &tmE, &full_bar[s], x_start, h_start, ti, n);
+          tma_load_4d(dst + p.off_odd, &tmOdd, &full_bar[s], x_start, h_start + 1, ti, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+      mbar_wait(w_bar, 0);
+      int kc = 0, tc = 0;
+      const uint32_t seg = (uint32_t)pp.seg_bytes;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+        const int acc = tc & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+          const int s = kc % S;
+          mbar_wait(&full_bar[s], (kc / S) & 1);
+          tc_fence_after();
+          const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
+          for (int dh = 0; dh < p.kh; ++dh) {
+            const uint32_t a_addr = st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * seg;
+            const uint32_t b_addr = smem_u32(w_smem) + (uint32_t)(dt * p.kh + dh) * kStemTapBytes;
+            const uint64_t adesc = umma_desc_kmajor_noswizzle(a_addr, 16u, seg);
+            const uint64_t bdesc = umma_desc_kmajor<64>(b_addr);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dt | dh | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int lrow = q * 32 + lane;  // tile row = TMEM lane: (h_i, w_i) = (lrow / 8, lrow % 8)
+    int tc = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+      int r = tile;
+      const int wb = r % p.tiles_w; r /= p.tiles_w;
+      const int hb = r % p.tiles_h; r /= p.tiles_h;
+      const int to = r % p.To;
+      const int n = r / p.To;
+      const int ho = hb * 16 + (lrow >> 3);
+      const int wo = wb * 8 + (lrow & 7);
+      const bool ok = ho < p.Ho && wo < p.Wo;
+      const int acc = tc & 1;
+      mbar_wait(&tmem_full_bar[acc], (tc >> 1) & 1);
+      tc_fence_after();
+      __nv_bfloat16* out_px = p.out + ((((long long)n * p.To + to) * p.Ho + ho) * p.Wo + wo) * (long long)p.ldo;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = c * 32 + g * 8;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col + j], s_shift[col + j]);
+              if (p.relu) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(out_px + col) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 }  // namespace vad

@@ -95,6 +95,8 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW;
   int stem_smem = 0;
+  bool stem_v2 = false;
+  int stem_seg = 0;
   int a_mode = 0;
   int avg_P = 0, avg_C = 0;
   // for tensor-map encoding
@@ -111,6 +113,7 @@ struct vad_plan {
   int in_channels = 0;
   int device = 0;
   int sm_count = 148;
+  bool stem_v1 = false;      // VAD_STEM_V1=1: im2col-box stem kernel instead of the raw-segment (v2) one
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool stem_gather = false;  // VAD_STEM_GATHER=1: feed the stem through the cp.async gather producer
@@ -192,6 +195,8 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   if (p->sm_count <= 0) p->sm_count = 148;
   const char* sg = getenv("VAD_STEM_GATHER");
   p->stem_gather = sg && sg[0] == '1';
+  const char* sv1 = getenv("VAD_STEM_V1");
+  p->stem_v1 = sv1 && sv1[0] == '1';
   const char* sgen = getenv("VAD_STEM_GENERIC");
   p->stem_generic = sgen && sgen[0] == '1';
   const char* ne = getenv("VAD_NO_EPI");
@@ -290,21 +295,27 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         memset(&q, 0, sizeof(q));
         q.B = batch; q.To = To; q.Ho = Ho; q.Wo = Wo;
         q.kt = d.kt; q.kh = d.kh; q.st = d.st; q.pt = d.pt; q.ph = d.ph;
-        q.tiles_w = (Wo + 15) / 16; q.tiles_h = (Ho + 7) / 8;
+        const bool v2 = !p->stem_v1;
+        const int th = v2 ? 16 : 8, tw = v2 ? 8 : 16;  // output tile: v2 8 (w) x 16 (h), v1 16 (w) x 8 (h)
+        q.tiles_w = (Wo + tw - 1) / tw; q.tiles_h = (Ho + th - 1) / th;
         const long long nt = (long long)batch * To * q.tiles_h * q.tiles_w;
-        q.rows_even = 8 + (d.kh + 1) / 2 - 1;
-        q.rows_odd = 8 + d.kh / 2 - 1;
-        q.off_odd = q.rows_even * 1024;
-        q.stage_bytes = (q.rows_even + (d.kh > 1 ? q.rows_odd : 0)) * 1024;
+        q.rows_even = th + (d.kh + 1) / 2 - 1;
+        q.rows_odd = th + d.kh / 2 - 1;
+        const int seg = v2 ? ((8 - 1) * d.sw * 4 + 32) * 2 : 1024;  // bytes per input-row segment in smem
+        q.off_odd = (int)align_up((uint64_t)q.rows_even * seg, 128);
+        q.stage_bytes = (int)align_up((uint64_t)q.off_odd + (uint64_t)q.rows_odd * seg, v2 ? 128 : 1024);
         const int w_bytes = d.kt * d.kh * kStemTapBytes;
         int ns = (220 * 1024 - w_bytes) / q.stage_bytes;
-        if (ns > 4) ns = 4;
+        const int max_ns = v2 ? kStemV2MaxStages : 4;
+        if (ns > max_ns) ns = max_ns;
         if (ns >= 2 && nt <= 0x7fffffffLL && d.kh > 1) {
           q.n_stages = ns;
           q.num_tiles = (int)nt;
           q.relu = c.relu; q.ldo = Cdst;
           r.stem_smem = w_bytes + ns * q.stage_bytes + 2 * 64 * 4 + (8 + 8 + 2 + 2 + 1) * 8 + 16 + 1024;
           r.stem = true;
+          r.stem_v2 = v2;
+          r.stem_seg = seg;
           r.grid = q.num_tiles < p->sm_count ? q.num_tiles : p->sm_count;
         }
       }
@@ -457,16 +468,34 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         gstr[1] = wp * 4 * 2;
         gstr[2] = gstr[1] * r.Hi;
         gstr[3] = gstr[2] * r.Ti;
-        cuuint32_t es[5] = {1, 1, 2, 1, 1};
-        cuuint32_t boxE[5] = {32, 16, (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
-        cuuint32_t boxO[5] = {32, 16, (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
-        CUresult cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxE, es,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr == CUDA_SUCCESS)
-          cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxO, es,
+        CUresult cr;
+        if (r.stem_v2) {
+          // raw padded rows: (x = Wp * 4 elements, H, T, N); a box is 88 contiguous elements (the union of 8
+          // overlapping windows) x rows with stride 2, no swizzle
+          cuuint64_t rdim[4] = {(cuuint64_t)wp * 4, (cuuint64_t)r.Hi, (cuuint64_t)r.Ti, (cuuint64_t)p->batch};
+          cuuint64_t rstr[3] = {gstr[1], gstr[2], gstr[3]};
+          cuuint32_t res4[4] = {1, 2, 1, 1};
+          cuuint32_t bE[4] = {(cuuint32_t)(r.stem_seg / 2), (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
+          cuuint32_t bO[4] = {(cuuint32_t)(r.stem_seg / 2), (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
+          cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.in, rdim, rstr, bE, res4,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cr == CUDA_SUCCESS)
+            cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.in, rdim, rstr, bO, res4,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+          cuuint32_t es[5] = {1, 1, 2, 1, 1};
+          cuuint32_t boxE[5] = {32, 16, (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
+          cuuint32_t boxO[5] = {32, 16, (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
+          cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxE, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cr == CUDA_SUCCESS)
+            cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxO, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if (cr == CUDA_SUCCESS) {
           cuuint64_t wdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
           cuuint64_t wstr[1] = {(cuuint64_t)r.K_pad * 2};
@@ -614,8 +643,20 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
           stem_attr = (e == cudaSuccess);
         }
         if (e == cudaSuccess) {
-          stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.sp);
-          e = cudaGetLastError();
+          if (r.stem_v2) {
+            static bool v2_attr = false;
+            if (!v2_attr) {
+              e = cudaFuncSetAttribute(stem_umma_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+              v2_attr = (e == cudaSuccess);
+            }
+            StemV2Params sp2;
+            sp2.s = r.sp;
+            sp2.seg_bytes = r.stem_seg;
+            if (e == cudaSuccess) stem_umma_v2_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, sp2);
+          } else {
+            stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.sp);
+          }
+          if (e == cudaSuccess) e = cudaGetLastError();
         }
       } else {
         e = launch_conv_any(r, st);
