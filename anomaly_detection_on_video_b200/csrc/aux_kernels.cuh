@@ -62,11 +62,21 @@ __device__ __forceinline__ int clip8_q22(int acc) {
 // grid = (resized rows, frame slots); one block resamples one output row of one frame into shared
 // memory (horizontal pass rounded to u8, then vertical pass, exactly Pillow's order) and then
 // writes that row into every crop that contains it.
+//   phase 0  the ksize_v source rows the vertical filter needs are staged in shared memory with
+//            coalesced 128-bit loads (the 3-byte pixels make per-tap global loads byte-sized otherwise)
+//   phase 1  every (x, channel) of the resized row: sum_r kv[r] * clip8(sum_j kh[j] * src[r][xmin + j])
+//   phase 2  (crop, pixel-pair) work items are flattened over the block so all 256 threads store
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) {
-  extern __shared__ uint8_t s_row[];  // rw*3 bytes (+ LUTs after, 16B aligned)
+  extern __shared__ __align__(16) uint8_t s_mem[];
   const int row_bytes = (p.rw * 3 + 15) & ~15;
-  float* lut_f = reinterpret_cast<float*>(s_row + row_bytes);
+  const int src_row_bytes = p.W * 3;
+  const int src_pitch = (src_row_bytes + 15) & ~15;
+  uint8_t* s_row = s_mem;                                         // resized row, rw*3 bytes
+  float* lut_f = reinterpret_cast<float*>(s_mem + row_bytes);     // 256 fp32
   __nv_bfloat16* lut_h = reinterpret_cast<__nv_bfloat16*>(lut_f + 256);
+  uint8_t* s_src = reinterpret_cast<uint8_t*>(lut_h + 256);       // ksize_v source rows, pitch src_pitch
+  __shared__ int s_active[10];
+  __shared__ int s_nactive;
 
   const int y = blockIdx.x;
   const int slot = blockIdx.y;
@@ -78,16 +88,42 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) 
   const int src_frame = clip * p.fpc + (t % L);
   const uint8_t* frame = p.frames + (long long)src_frame * p.H * p.W * 3;
 
-  if (threadIdx.x < 256) {
+  {
     // GroupStandardizationTenCrop: t.sub_(114.75).div_(57.375), two fp32 roundings
     const float v = __fdiv_rn(__fsub_rn((float)threadIdx.x, 114.75f), 57.375f);
     lut_f[threadIdx.x] = v;
     lut_h[threadIdx.x] = __float2bfloat16_rn(v);
   }
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int k = 0; k < p.ncrops; ++k) {
+      const int yo = y - p.tops[k];
+      if (yo >= 0 && yo < p.crop) s_active[n++] = k;
+    }
+    s_nactive = n;
+  }
 
   const int ymin = p.bounds_v[2 * y];
   const int ycnt = p.bounds_v[2 * y + 1];
   const int* kv = p.coef_v + y * p.ksize_v;
+  {
+    const uint8_t* g0 = frame + (long long)ymin * src_row_bytes;
+    const bool vec = ((src_row_bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(g0) & 15) == 0);
+    if (vec) {
+      const int per_row = src_row_bytes >> 4;
+      for (int i = threadIdx.x; i < ycnt * per_row; i += blockDim.x) {
+        const int r = i / per_row, c = i - r * per_row;
+        reinterpret_cast<uint4*>(s_src + r * src_pitch)[c] = reinterpret_cast<const uint4*>(g0 + (long long)r * src_row_bytes)[c];
+      }
+    } else {
+      for (int i = threadIdx.x; i < ycnt * src_row_bytes; i += blockDim.x) {
+        const int r = i / src_row_bytes, c = i - r * src_row_bytes;
+        s_src[r * src_pitch + c] = g0[(long long)r * src_row_bytes + c];
+      }
+    }
+  }
+  __syncthreads();
+
   for (int i = threadIdx.x; i < p.rw * 3; i += blockDim.x) {
     const int x = i / 3;
     const int c = i - x * 3;
@@ -96,7 +132,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) 
     const int* kh = p.coef_h + x * p.ksize_h;
     int acc_v = 1 << 21;
     for (int r = 0; r < ycnt; ++r) {
-      const uint8_t* src = frame + ((long long)(ymin + r) * p.W + xmin) * 3 + c;
+      const uint8_t* src = s_src + r * src_pitch + xmin * 3 + c;
       int acc_h = 1 << 21;
       for (int j = 0; j < xcnt; ++j) acc_h += (int)src[j * 3] * kh[j];
       acc_v += clip8_q22(acc_h) * kv[r];
@@ -106,44 +142,53 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) 
   __syncthreads();
 
   const int crop = p.crop;
-  for (int k = 0; k < p.ncrops; ++k) {
-    const int yo = y - p.tops[k];
-    if (yo < 0 || yo >= crop) continue;
-    const int left = p.lefts[k];
-    const int flip = p.flips[k];
-    if (p.out_mode == 1) {
-      // stem layout [clipcrop, t, crop, crop + 8, 4] bf16 ; two pixels (16 B) per thread
-      const int Wp = crop + 8;
+  const int nact = s_nactive;
+  if (p.out_mode == 1) {
+    // stem layout [clipcrop, t, crop, crop + 8, 4] bf16 ; one work item = two pixels (16 B)
+    const int Wp = crop + 8;
+    const int per_crop = Wp / 2;
+    for (int idx = threadIdx.x; idx < nact * per_crop; idx += blockDim.x) {
+      const int a = idx / per_crop;
+      const int i = idx - a * per_crop;
+      const int k = s_active[a];
+      const int yo = y - p.tops[k];
+      const int left = p.lefts[k];
+      const int flip = p.flips[k];
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
                                             ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * crop + yo) *
                                                 Wp * 4);
-      for (int i = threadIdx.x; i < Wp / 2; i += blockDim.x) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int xo = 2 * i + h - p.pad_left;
-          if (xo >= 0 && xo < crop) {
-            const int xs = flip ? left + crop - 1 - xo : left + xo;
-            const uint8_t* px = s_row + xs * 3;
-            const uint32_t r = __bfloat16_as_ushort(lut_h[px[0]]);
-            const uint32_t g = __bfloat16_as_ushort(lut_h[px[1]]);
-            const uint32_t b = __bfloat16_as_ushort(lut_h[px[2]]);
-            w[2 * h] = r | (g << 16);
-            w[2 * h + 1] = b;
-          }
+      for (int h = 0; h < 2; ++h) {
+        const int xo = 2 * i + h - p.pad_left;
+        if (xo >= 0 && xo < crop) {
+          const int xs = flip ? left + crop - 1 - xo : left + xo;
+          const uint8_t* px = s_row + xs * 3;
+          const uint32_t r = __bfloat16_as_ushort(lut_h[px[0]]);
+          const uint32_t g = __bfloat16_as_ushort(lut_h[px[1]]);
+          const uint32_t b = __bfloat16_as_ushort(lut_h[px[2]]);
+          w[2 * h] = r | (g << 16);
+          w[2 * h + 1] = b;
         }
-        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
       }
-    } else {
-      // dataset layout [clip, crop_idx, t, 3, crop, crop] fp32
+      dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    // dataset layout [clip, crop_idx, t, 3, crop, crop] fp32
+    const int per_crop = 3 * crop;
+    for (int idx = threadIdx.x; idx < nact * per_crop; idx += blockDim.x) {
+      const int a = idx / per_crop;
+      const int i = idx - a * per_crop;
+      const int k = s_active[a];
+      const int yo = y - p.tops[k];
+      const int left = p.lefts[k];
+      const int flip = p.flips[k];
+      const int c = i / crop;
+      const int xo = i - c * crop;
+      const int xs = flip ? left + crop - 1 - xo : left + xo;
       float* dst = reinterpret_cast<float*>(p.out) +
                    ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * 3) * crop * crop + (long long)yo * crop;
-      for (int i = threadIdx.x; i < 3 * crop; i += blockDim.x) {
-        const int c = i / crop;
-        const int xo = i - c * crop;
-        const int xs = flip ? left + crop - 1 - xo : left + xo;
-        dst[(long long)c * crop * crop + xo] = lut_f[s_row[xs * 3 + c]];
-      }
+      dst[(long long)c * crop * crop + xo] = lut_f[s_row[xs * 3 + c]];
     }
   }
 }
@@ -206,6 +251,52 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const PoolParams p) {
       acc.y = bf16x2_max(acc.y, 0u);
       acc.z = bf16x2_max(acc.z, 0u);
       acc.w = bf16x2_max(acc.w, 0u);
+    }
+    *reinterpret_cast<uint4*>(p.out + m_out * p.ldo + v * 8) = acc;
+  }
+}
+
+// Fast path for un-padded windows with compile-time extents (every tap in range by construction: floor
+// output size, pad 0): the KT*KH*KW 128-bit loads of a thread are all issued before the first max, and
+// the streaming loads bypass L1 allocation, so enough bytes are in flight to approach HBM bandwidth.
+__device__ __forceinline__ uint4 ld_stream_16(const void* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(ptr));
+  return r;
+}
+
+template <int KT, int KH, int KW>
+__global__ void __launch_bounds__(256) maxpool3d_fixed_kernel(const PoolParams p) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)p.B * p.To * p.Ho * p.Wo * cv;
+  const long long sW = p.C, sH = (long long)p.Wi * p.C, sT = sH * p.Hi;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long m = i / cv;
+    const long long m_out = m;
+    const int wo = (int)(m % p.Wo); m /= p.Wo;
+    const int ho = (int)(m % p.Ho); m /= p.Ho;
+    const int to = (int)(m % p.To); m /= p.To;
+    // m is now the clip index; pad is 0, so the window origin is (to*st, ho*sh, wo*sw)
+    const __nv_bfloat16* base = p.in + (m * p.Ti + (long long)to * p.st) * sT + (long long)ho * p.sh * sH +
+                                (long long)wo * p.sw * sW + v * 8;
+    uint4 x[KT * KH * KW];
+#pragma unroll
+    for (int dt = 0; dt < KT; ++dt)
+#pragma unroll
+      for (int dh = 0; dh < KH; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < KW; ++dw) x[(dt * KH + dh) * KW + dw] = ld_stream_16(base + dt * sT + dh * sH + dw * sW);
+    uint4 acc = x[0];
+#pragma unroll
+    for (int k = 1; k < KT * KH * KW; ++k) {
+      acc.x = bf16x2_max(acc.x, x[k].x);
+      acc.y = bf16x2_max(acc.y, x[k].y);
+      acc.z = bf16x2_max(acc.z, x[k].z);
+      acc.w = bf16x2_max(acc.w, x[k].w);
     }
     *reinterpret_cast<uint4*>(p.out + m_out * p.ldo + v * 8) = acc;
   }

@@ -152,86 +152,93 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint32_t tx = GATHER ? Cfg::kBBytes : Cfg::kStageBytes;
-      int kbc = 0, tcp = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcp) {
-        const int n0 = (tile % p.n_tiles) * BN;
-        const int m0 = (tile / p.n_tiles) * kBlockM;
-        if (EPI) {
-          // residual tile of this output tile -> epilogue buffer (free once the stores of the tile that
-          // used it two tiles ago have been read out)
-          const int rb = tcp & 1;
-          mbar_wait(&res_empty_bar[rb], ((tcp >> 1) & 1) ^ 1);
-          int nsub = (p.N - n0 + 63) / 64;
-          nsub = nsub > BN / 64 ? BN / 64 : nsub;
+    // warp-uniform loops; only the issue itself is predicated on one elected lane
+    const uint32_t tx = GATHER ? Cfg::kBBytes : Cfg::kStageBytes;
+    int kbc = 0, tcp = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcp) {
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int m0 = (tile / p.n_tiles) * kBlockM;
+      if (EPI) {
+        // residual tile of this output tile -> epilogue buffer (free once the stores of the tile that
+        // used it two tiles ago have been read out)
+        const int rb = tcp & 1;
+        mbar_wait(&res_empty_bar[rb], ((tcp >> 1) & 1) ^ 1);
+        int nsub = (p.N - n0 + 63) / 64;
+        nsub = nsub > BN / 64 ? BN / 64 : nsub;
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&res_full_bar[rb], (uint32_t)(nsub * Cfg::kEpiSubBytes));
           for (int j = 0; j < nsub; ++j)
             tma_load_2d(epi_base + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, &res_full_bar[rb], n0 + 64 * j, m0);
         }
-        int wq = 0, hq = 0, dq = 0, nq = 0;
-        if (!GATHER && p.a_mode == A_TMA_IM2COL) {
-          int t = m0;
-          const int wo = t % p.Wo; t /= p.Wo;
-          const int ho = t % p.Ho; t /= p.Ho;
-          const int to = t % p.To; t /= p.To;
-          wq = wo * p.sw - p.pw;
-          hq = ho * p.sh - p.ph;
-          dq = to * p.st - p.pt;
-          nq = t;
-        }
-        int c0 = 0, dw = 0, dh = 0, dt = 0;  // walks (tap, channel block) without divisions
-        for (int kb = 0; kb < p.num_kb; ++kb, ++kbc) {
-          const int s = kbc % STAGES;
-          const uint32_t ph = (kbc / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* a_dst = stage_base + s * Cfg::kStageBytes;
-          uint8_t* b_dst = a_dst + Cfg::kABytes;
+        __syncwarp();
+      }
+      int wq = 0, hq = 0, dq = 0, nq = 0;
+      if (!GATHER && p.a_mode == A_TMA_IM2COL) {
+        int t = m0;
+        const int wo = t % p.Wo; t /= p.Wo;
+        const int ho = t % p.Ho; t /= p.Ho;
+        const int to = t % p.To; t /= p.To;
+        wq = wo * p.sw - p.pw;
+        hq = ho * p.sh - p.ph;
+        dq = to * p.st - p.pt;
+        nq = t;
+      }
+      int c0 = 0, dw = 0, dh = 0, dt = 0;  // walks (tap, channel block) without divisions
+      for (int kb = 0; kb < p.num_kb; ++kb, ++kbc) {
+        const int s = kbc % STAGES;
+        const uint32_t ph = (kbc / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = stage_base + s * Cfg::kStageBytes;
+        uint8_t* b_dst = a_dst + Cfg::kABytes;
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[s], tx);
           if (!GATHER) {
-            if (p.a_mode == A_TMA_2D) {
+            if (p.a_mode == A_TMA_2D)
               tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-            } else {
-              tma_load_im2col_5d(a_dst, &tmA, &full_bar[s], c0, wq, hq, dq, nq, (uint16_t)dw, (uint16_t)dh,
-                                 (uint16_t)dt);
-              c0 += BK;
-              if (c0 >= p.cin_eff) {
-                c0 = 0;
-                if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
-              }
-            }
+            else
+              tma_load_im2col_5d(a_dst, &tmA, &full_bar[s], c0, wq, hq, dq, nq, (uint16_t)dw, (uint16_t)dh, (uint16_t)dt);
           }
           tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+        }
+        __syncwarp();
+        if (!GATHER && p.a_mode != A_TMA_2D) {
+          c0 += BK;
+          if (c0 >= p.cin_eff) {
+            c0 = 0;
+            if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(BN);
-      int kbc = 0, tc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
-        const int acc = tc & 1;
-        const uint32_t aph = (tc >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], aph ^ 1);  // epilogue has drained this accumulator
+    constexpr uint32_t idesc = umma_idesc_bf16_m128(BN);
+    const uint64_t desc_hi = umma_desc_kmajor<Cfg::kRowBytes>(0);  // everything but the start address
+    int kbc = 0, tc = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+      const int acc = tc & 1;
+      const uint32_t aph = (tc >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], aph ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < p.num_kb; ++kb, ++kbc) {
+        const int s = kbc % STAGES;
+        const uint32_t ph = (kbc / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < p.num_kb; ++kb, ++kbc) {
-          const int s = kbc % STAGES;
-          const uint32_t ph = (kbc / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(stage_base + s * Cfg::kStageBytes);
-          const uint64_t adesc = umma_desc_kmajor<Cfg::kRowBytes>(a_addr);
-          const uint64_t bdesc = umma_desc_kmajor<Cfg::kRowBytes>(a_addr + Cfg::kABytes);
+        const uint32_t a_lo = smem_u32(stage_base + s * Cfg::kStageBytes) >> 4;
+        const uint64_t adesc = desc_hi | a_lo;
+        const uint64_t bdesc = desc_hi | (a_lo + (Cfg::kABytes >> 4));
+        if (elect_one_sync()) {
+          // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
+          if (kb) umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
+          else    umma_f16_c<false>(d_tmem, adesc, bdesc, idesc);
 #pragma unroll
-          for (int k = 0; k < BK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          for (int k = 1; k < BK / kUmmaK; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
+          umma_commit(&empty_bar[s]);                                 // frees the smem stage once these MMAs have read it
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp < 6) {

@@ -20,6 +20,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (the same lane every time).  Role loops stay warp-uniform and only
+// the TMA / tcgen05 issue is predicated on this, so descriptors live in uniform registers and ptxas
+// does not have to wrap every UTCHMMA / UTMALDG in a per-thread election loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      " .reg .pred P1;\n"
+      " elect.sync _|P1, 0xffffffff;\n"
+      " @P1 mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -146,6 +161,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// same with the accumulate flag known at compile time (no setp in the issue loop)
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, 0, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc)
+                 : "memory");
+  else
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, 0, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc)
+                 : "memory");
 }
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

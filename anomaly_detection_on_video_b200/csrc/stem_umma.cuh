@@ -290,57 +290,69 @@ stem_umma_v2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
       for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
-      const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * pp.seg_bytes);
-      int kc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int r = tile;
-        const int wb = r % p.tiles_w; r /= p.tiles_w;
-        const int hb = r % p.tiles_h; r /= p.tiles_h;
-        const int to = r % p.To;
-        const int n = r / p.To;
-        const int h_start = 2 * (hb * 16) - p.ph;
-        const int x_start = wb * 8 * 8;  // 8 windows x (2 px x 4 ch) elements
-        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
-          const int s = kc % S;
-          mbar_wait(&empty_bar[s], ((kc / S) & 1) ^ 1);
-          uint8_t* dst = stage_base + s * p.stage_bytes;
+    }
+    __syncwarp();
+    const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * pp.seg_bytes);
+    int kc = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int wb = r % p.tiles_w; r /= p.tiles_w;
+      const int hb = r % p.tiles_h; r /= p.tiles_h;
+      const int to = r % p.To;
+      const int n = r / p.To;
+      const int h_start = 2 * (hb * 16) - p.ph;
+      const int x_start = wb * 8 * 8;  // 8 windows x (2 px x 4 ch) elements
+      for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+        const int s = kc % S;
+        mbar_wait(&empty_bar[s], ((kc / S) & 1) ^ 1);
+        uint8_t* dst = stage_base + s * p.stage_bytes;
+        const int ti = to * p.st - p.pt + dt;
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[s], tx);
-          const int ti = to * p.st - p.pt + dt;
           tma_load_4d(dst, &tmE, &full_bar[s], x_start, h_start, ti, n);
           tma_load_4d(dst + p.off_odd, &tmOdd, &full_bar[s], x_start, h_start + 1, ti, n);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
-      mbar_wait(w_bar, 0);
-      int kc = 0, tc = 0;
-      const uint32_t seg = (uint32_t)pp.seg_bytes;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
-        const int acc = tc & 1;
-        mbar_wait(&tmem_empty_bar[acc], ((tc >> 1) & 1) ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+    mbar_wait(w_bar, 0);
+    int kc = 0, tc = 0;
+    const uint32_t seg = (uint32_t)pp.seg_bytes;
+    const uint32_t w_addr = smem_u32(w_smem);
+    // descriptor high words are loop invariant; only the 14-bit start-address field moves
+    const uint64_t a_hi = umma_desc_kmajor_noswizzle(0, 16u, seg);
+    const uint64_t b_hi = umma_desc_kmajor<64>(0);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+      const int acc = tc & 1;
+      mbar_wait(&tmem_empty_bar[acc], ((tc >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+      for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+        const int s = kc % S;
+        mbar_wait(&full_bar[s], (kc / S) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
-        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
-          const int s = kc % S;
-          mbar_wait(&full_bar[s], (kc / S) & 1);
-          tc_fence_after();
-          const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
-          for (int dh = 0; dh < p.kh; ++dh) {
-            const uint32_t a_addr = st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * seg;
-            const uint32_t b_addr = smem_u32(w_smem) + (uint32_t)(dt * p.kh + dh) * kStemTapBytes;
-            const uint64_t adesc = umma_desc_kmajor_noswizzle(a_addr, 16u, seg);
-            const uint64_t bdesc = umma_desc_kmajor<64>(b_addr);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dt | dh | k) ? 1u : 0u);
+        const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
+        if (elect_one_sync()) {
+          uint32_t b_lo = (w_addr + (uint32_t)(dt * p.kh) * kStemTapBytes) >> 4;
+          for (int dh = 0; dh < p.kh; ++dh, b_lo += kStemTapBytes >> 4) {
+            const uint32_t a_lo = (st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * seg) >> 4;
+            const uint64_t adesc = a_hi | a_lo;
+            const uint64_t bdesc = b_hi | b_lo;
+            if (dt | dh) umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
+            else         umma_f16_c<false>(d_tmem, adesc, bdesc, idesc);
+            umma_f16_c<true>(d_tmem, adesc + 2, bdesc + 2, idesc);
           }
           umma_commit(&empty_bar[s]);
+          if (dt == p.kt - 1) umma_commit(&tmem_full_bar[acc]);
         }
-        umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
       }
     }
   } else {

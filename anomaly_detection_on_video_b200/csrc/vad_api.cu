@@ -663,7 +663,18 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
       }
     } else if (d.kind == VAD_OP_MAXPOOL) {
       const long long total = (long long)r.pp.B * r.pp.To * r.pp.Ho * r.pp.Wo * (r.pp.C / 8);
-      maxpool3d_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(r.pp);
+      const PoolParams& q = r.pp;
+      const bool inb = !q.pt && !q.ph && !q.pw && (q.To - 1) * q.st + q.kt <= q.Ti && (q.Ho - 1) * q.sh + q.kh <= q.Hi &&
+                       (q.Wo - 1) * q.sw + q.kw <= q.Wi;
+      const int g = grid_for(total, 256, 148 * 64);
+      if (inb && q.kt == 2 && q.kh == 3 && q.kw == 3)
+        maxpool3d_fixed_kernel<2, 3, 3><<<g, 256, 0, st>>>(q);   // I3Res50 maxpool1
+      else if (inb && q.kt == 2 && q.kh == 1 && q.kw == 1)
+        maxpool3d_fixed_kernel<2, 1, 1><<<g, 256, 0, st>>>(q);   // I3Res50 maxpool2
+      else if (inb && q.kt == 1 && q.kh == 1 && q.kw == 1)
+        maxpool3d_fixed_kernel<1, 1, 1><<<g, 256, 0, st>>>(q);   // strided copy
+      else
+        maxpool3d_kernel<<<g, 256, 0, st>>>(q);
       e = cudaGetLastError();
     } else {
       if (!feat_out_dev) return fail(VAD_ERR_INVALID_ARGUMENT, "plan ends in AVGPOOL but feat_out_dev is null");
@@ -851,7 +862,11 @@ extern "C" int32_t vad_preproc_run(vad_preproc_t* pp, const uint8_t* frames_dev,
   q.crop = pp->crop; q.ncrops = pp->ncrops;
   for (int k = 0; k < 10; ++k) { q.tops[k] = pp->tops[k]; q.lefts[k] = pp->lefts[k]; q.flips[k] = pp->flips[k]; }
   q.clip_start = clip_start; q.fpc = frames_per_clip; q.out_mode = out_mode; q.pad_left = pad_left; q.out = out_dev;
-  const size_t smem = ((size_t)pp->rw * 3 + 15) / 16 * 16 + 256 * 4 + 256 * 2;
+  // resized row + fp32/bf16 LUTs + the ksize_v staged source rows
+  const size_t smem = ((size_t)pp->rw * 3 + 15) / 16 * 16 + 256 * 4 + 256 * 2 +
+                      (size_t)pp->ksize_v * (((size_t)pp->src_w * 3 + 15) / 16 * 16);
+  if (smem > 200 * 1024) return fail(VAD_ERR_INVALID_ARGUMENT, "source frames too wide for the resampling kernel (%zu B of shared memory)", smem);
+  if (smem > 48 * 1024) VAD_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(pp->rh, n_clips * frames_per_clip);
   preprocess_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(q);
   VAD_CUDA_CHECK(cudaGetLastError());
