@@ -30,6 +30,7 @@ struct StemParams {
   int n_stages;
   int relu;
   int ldo;
+  int dbg;  // VAD_STEM_DEBUG bit mask (bottleneck hunting only): 1 = no global stores, 2 = no MMA issue, 4 = no A loads
   const float* scale;
   const float* shift;
   __nv_bfloat16* out;
@@ -93,55 +94,65 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
       for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
-      int kc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int r = tile;
-        const int wb = r % p.tiles_w; r /= p.tiles_w;
-        const int hb = r % p.tiles_h; r /= p.tiles_h;
-        const int to = r % p.To;
-        const int n = r / p.To;
-        const int h_start = 2 * (hb * 8) - p.ph;
-        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
-          const int s = kc % S;
-          const uint32_t ph = (kc / S) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* dst = stage_base + s * p.stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
-          const int ti = to * p.st - p.pt + dt;
+    }
+    __syncwarp();
+    const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * 1024);
+    int kc = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int wb = r % p.tiles_w; r /= p.tiles_w;
+      const int hb = r % p.tiles_h; r /= p.tiles_h;
+      const int to = r % p.To;
+      const int n = r / p.To;
+      const int h_start = 2 * (hb * 8) - p.ph;
+      for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+        const int s = kc % S;
+        mbar_wait(&empty_bar[s], ((kc / S) & 1) ^ 1);
+        uint8_t* dst = stage_base + s * p.stage_bytes;
+        const int ti = to * p.st - p.pt + dt;
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full_bar[s], tx);
           tma_load_5d(dst, &tmE, &full_bar[s], 0, wb * 16, h_start, ti, n);
           tma_load_5d(dst + p.off_odd, &tmOdd, &full_bar[s], 0, wb * 16, h_start + 1, ti, n);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
-      mbar_wait(w_bar, 0);
-      int kc = 0, tc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
-        const int acc = tc & 1;
-        mbar_wait(&tmem_empty_bar[acc], ((tc >> 1) & 1) ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+    mbar_wait(w_bar, 0);
+    int kc = 0, tc = 0;
+    const uint32_t w_addr = smem_u32(w_smem);
+    const uint64_t d_hi = umma_desc_kmajor<64>(0);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+      const int acc = tc & 1;
+      mbar_wait(&tmem_empty_bar[acc], ((tc >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+      for (int dt = 0; dt < p.kt; ++dt, ++kc) {
+        const int s = kc % S;
+        mbar_wait(&full_bar[s], (kc / S) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
-        for (int dt = 0; dt < p.kt; ++dt, ++kc) {
-          const int s = kc % S;
-          mbar_wait(&full_bar[s], (kc / S) & 1);
-          tc_fence_after();
-          const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
-          for (int dh = 0; dh < p.kh; ++dh) {
-            const uint32_t a_addr = st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * 1024u;
-            const uint32_t b_addr = smem_u32(w_smem) + (uint32_t)(dt * p.kh + dh) * kStemTapBytes;
-            const uint64_t adesc = umma_desc_kmajor<64>(a_addr);
-            const uint64_t bdesc = umma_desc_kmajor<64>(b_addr);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dt | dh | k) ? 1u : 0u);
+        const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
+        if (elect_one_sync()) {
+          uint32_t b_lo = (w_addr + (uint32_t)(dt * p.kh) * kStemTapBytes) >> 4;
+          for (int dh = 0; dh < p.kh; ++dh, b_lo += kStemTapBytes >> 4) {
+            const uint32_t a_lo = (st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * 1024u) >> 4;
+            const uint64_t adesc = d_hi | a_lo;
+            const uint64_t bdesc = d_hi | b_lo;
+            if (dt | dh) umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
+            else         umma_f16_c<false>(d_tmem, adesc, bdesc, idesc);
+            umma_f16_c<true>(d_tmem, adesc + 2, bdesc + 2, idesc);
           }
           umma_commit(&empty_bar[s]);
+          if (dt == p.kt - 1) umma_commit(&tmem_full_bar[acc]);
         }
-        umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
       }
     }
   } else {
@@ -312,9 +323,13 @@ stem_umma_v2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
         uint8_t* dst = stage_base + s * p.stage_bytes;
         const int ti = to * p.st - p.pt + dt;
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full_bar[s], tx);
-          tma_load_4d(dst, &tmE, &full_bar[s], x_start, h_start, ti, n);
-          tma_load_4d(dst + p.off_odd, &tmOdd, &full_bar[s], x_start, h_start + 1, ti, n);
+          if (p.dbg & 4) {
+            mbar_arrive(&full_bar[s]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], tx);
+            tma_load_4d(dst, &tmE, &full_bar[s], x_start, h_start, ti, n);
+            tma_load_4d(dst + p.off_odd, &tmOdd, &full_bar[s], x_start, h_start + 1, ti, n);
+          }
         }
         __syncwarp();
       }
@@ -341,7 +356,7 @@ stem_umma_v2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
         const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
         if (elect_one_sync()) {
           uint32_t b_lo = (w_addr + (uint32_t)(dt * p.kh) * kStemTapBytes) >> 4;
-          for (int dh = 0; dh < p.kh; ++dh, b_lo += kStemTapBytes >> 4) {
+          for (int dh = 0; dh < ((p.dbg & 2) ? 0 : p.kh); ++dh, b_lo += kStemTapBytes >> 4) {
             const uint32_t a_lo = (st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * seg) >> 4;
             const uint64_t adesc = a_hi | a_lo;
             const uint64_t bdesc = b_hi | b_lo;
@@ -367,7 +382,7 @@ stem_umma_v2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
       const int n = r / p.To;
       const int ho = hb * 16 + (lrow >> 3);
       const int wo = wb * 8 + (lrow & 7);
-      const bool ok = ho < p.Ho && wo < p.Wo;
+      const bool ok = ho < p.Ho && wo < p.Wo && !(p.dbg & 1);
       const int acc = tc & 1;
       mbar_wait(&tmem_full_bar[acc], (tc >> 1) & 1);
       tc_fence_after();

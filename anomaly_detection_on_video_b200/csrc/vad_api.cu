@@ -312,6 +312,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
           q.n_stages = ns;
           q.num_tiles = (int)nt;
           q.relu = c.relu; q.ldo = Cdst;
+          { const char* sd = getenv("VAD_STEM_DEBUG"); q.dbg = sd ? atoi(sd) : 0; }
           r.stem_smem = w_bytes + ns * q.stage_bytes + 2 * 64 * 4 + (8 + 8 + 2 + 2 + 1) * 8 + 16 + 1024;
           r.stem = true;
           r.stem_v2 = v2;

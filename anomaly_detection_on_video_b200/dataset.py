@@ -118,14 +118,31 @@ class TenCropVideoFrameDataset(Dataset):
         if self.device.type != "cuda":
             raise RuntimeError("TenCropVideoFrameDataset preprocesses on the GPU only (no CPU fallback)")
         frames = _frames_to_tensor(video_path_or_images)
-        # one H2D copy of the raw uint8 frames; pinned staging keeps it asynchronous
+        self._ready = []  # (frames uploaded so far, event) per chunk of the pipelined H2D copy
         if not frames.is_cuda:
+            # One upload of the raw uint8 frames, pipelined: chunks go out on a copy stream and every
+            # preprocessing launch waits (on the device, not the host) only for the chunk it needs, so the
+            # PCIe transfer overlaps the backbone instead of preceding it.
             frames = frames.contiguous()
-            try:
-                frames = frames.pin_memory()
-            except RuntimeError:
-                pass
-            frames = frames.to(self.device, non_blocking=True)
+            if not frames.is_pinned():
+                try:
+                    frames = frames.pin_memory()
+                except RuntimeError:
+                    pass
+            dst = torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
+            copy_stream = torch.cuda.Stream(self.device)
+            copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            chunk = max(frames_per_clip, (256 // frames_per_clip) * frames_per_clip)
+            with torch.cuda.stream(copy_stream):
+                for c0 in range(0, frames.shape[0], chunk):
+                    c1 = min(frames.shape[0], c0 + chunk)
+                    dst[c0:c1].copy_(frames[c0:c1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    self._ready.append((c1, ev))
+            dst.record_stream(copy_stream)
+            self._host_frames = frames  # keep the pinned source alive until the copies are done
+            frames = dst
         self.frames = frames.contiguous()
         self.frames_per_clip = frames_per_clip
         self.ncrops = ncrops
@@ -137,21 +154,37 @@ class TenCropVideoFrameDataset(Dataset):
     def __len__(self) -> int:
         return len(self.indices)
 
+    def _wait_uploaded(self, clip_end: int) -> None:
+        """Make the current stream wait for the H2D chunks covering clips [0, clip_end)."""
+        if not self._ready:
+            return
+        need = min(self.frames.shape[0], clip_end * self.frames_per_clip)
+        cur = torch.cuda.current_stream(self.device)
+        while self._ready:
+            upto, ev = self._ready[0]
+            cur.wait_event(ev)
+            if upto >= need:
+                break
+            self._ready.pop(0)  # earlier chunks are implied by later events on the same copy stream
+
     def __getitem__(self, idx: int) -> torch.Tensor:
         """(ncrops, clip_len, 3, H, W) float32 on the GPU -- values identical to the reference's."""
         if idx < 0:
             idx += len(self)
         if not 0 <= idx < len(self):
             raise IndexError(idx)
+        self._wait_uploaded(idx + 1)
         return self._pp.run(self.frames, idx, 1, self.frames_per_clip, _lib.VAD_OUT_DATASET_F32)[0]
 
     def clips_f32(self, start: int, n: int) -> torch.Tensor:
         """(n, ncrops, clip_len, 3, H, W) float32: ``torch.stack([self[i] for i in range(start, start+n)])``."""
+        self._wait_uploaded(start + n)
         return self._pp.run(self.frames, start, n, self.frames_per_clip, _lib.VAD_OUT_DATASET_F32)
 
     def clips_stem(self, start: int, n: int, pad_left: int = 3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """bf16 stem layout (n * ncrops, clip_len, H, W + 8, 4), clip-major then crop: the direct input of
         ``I3Res50.forward_stem_layout`` (skips the fp32 NCTHW tensor the reference materialises)."""
+        self._wait_uploaded(start + n)
         return self._pp.run(self.frames, start, n, self.frames_per_clip, _lib.VAD_OUT_STEM_BF16, pad_left, out=out)
 
 

@@ -216,6 +216,8 @@ def main():
         launches["n"] += n_batches * (1 + plan_launches) + 1  # preprocess + backbone ops per batch, + segment
         return seg
 
+    e2e_last = [time.perf_counter()]
+
     def step_e2e():
         """public API from pinned host frames: H2D of the frames, D2H of features + segments."""
         dbg = os.environ.get("VAD_BENCH_DEBUG") == "1"
@@ -234,8 +236,11 @@ def main():
         out = feats.cpu(), seg.cpu()
         lap()
         if dbg:
-            print("e2e phases ms (ctor+h2d, extract, segment+d2h):", [round((b - a) * 1e3, 2) for a, b in zip(tt, tt[1:])],
-                  file=sys.stderr, flush=True)
+            del d, feats, seg
+            lap()
+            print("e2e phases ms (ctor+h2d, extract, segment+d2h, free):", [round((b - a) * 1e3, 2) for a, b in zip(tt, tt[1:])],
+                  "since previous step end:", round((tt[0] - e2e_last[0]) * 1e3, 2), file=sys.stderr, flush=True)
+            e2e_last[0] = time.perf_counter()
         return out
 
     for _ in range(W):
