@@ -22,6 +22,8 @@
 // tile i+1.
 #pragma once
 
+#include <type_traits>
+
 #include "ptx_sm100.cuh"
 
 namespace vad {
@@ -55,27 +57,43 @@ struct ConvParams {
 constexpr int kBlockM = 128;
 constexpr int kUmmaK = 16;
 
-template <int BN, int BK, bool GATHER, bool EPI>
+template <int BN, int BK, int KPS, bool GATHER, bool EPI>
 struct ConvCfg {
   static_assert(BK == 64 || BK == 32, "BK is one swizzle row: 64 (SW128) or 32 (SW64) bf16");
   static_assert(!GATHER || BK == 64, "the gather producer writes 128-byte swizzled rows");
   static_assert(!EPI || BN <= 128, "the staged epilogue keeps two 128 x BN bf16 tiles in shared memory");
+  static_assert(KPS == 1 || (KPS == 2 && !GATHER && BK == 64), "two k-blocks per stage: TMA producers, SW128 only");
   static constexpr int kRowBytes = BK * 2;
-  static constexpr int kABytes = kBlockM * kRowBytes;
-  static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kABytes = kBlockM * kRowBytes;   // one k-block of A
+  static constexpr int kBBytes = BN * kRowBytes;        // one k-block of B
+  static constexpr int kKbBytes = kABytes + kBBytes;
+  // A stage holds KPS k-blocks behind ONE full/empty barrier pair: [A_0 .. A_{KPS-1}][B_0 .. B_{KPS-1}].
+  // The issuing thread can run only about one MMA ahead of the tensor pipe, so whatever it does between two
+  // groups of MMAs (barrier wait, commit) is exposed unless a group is >= ~300 cycles of tensor work
+  // (tools/umma_bench.cu): 8 MMAs per barrier for BN <= 128, 4 for BN = 256.
+  static constexpr int kStageBytes = KPS * kKbBytes;
   // EPI: residual tile prefetched by TMA / output tile written back by TMA, double buffered;
   // laid out as BN/64 sub-tiles of [128 rows x 64 cols] (128-byte rows, SWIZZLE_128B)
   static constexpr int kEpiSubBytes = kBlockM * 128;
   static constexpr int kEpiBufBytes = EPI ? (BN / 64) * kEpiSubBytes : 0;
-  static constexpr int kPipeBudget = 196608 - 2 * kEpiBufBytes;
-  static constexpr int kStages = (kPipeBudget / kStageBytes) > 16 ? 16 : (kPipeBudget / kStageBytes);
-  static constexpr int kThreads = GATHER ? 320 : 192;
+  // The residual of tile i+kEpiBufs is requested when the epilogue of tile i has released its buffer, so the
+  // HBM round trip of that request has kEpiBufs-1 tile times to complete: three buffers, not two.
+  static constexpr int kEpiBufs = 3;
+  static constexpr int kPipeBudget = 196608 + (EPI ? 32768 : 0) - kEpiBufs * kEpiBufBytes;
+  static constexpr int kStages = (kPipeBudget / kStageBytes) > 8 ? 8 : (kPipeBudget / kStageBytes);
+  static_assert(kStages >= 2, "need a ring of at least two stages");
+  // Epilogue warps: the TMEM lane quarter a warp may read is (warp % 4); for BN >= 128 two warps share a
+  // quarter and split the columns, which halves the per-tile epilogue latency of the small-K layers.
+  static constexpr int kEpiWarps = BN >= 128 ? 8 : 4;
+  static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+  static constexpr int kEpiThreads = kEpiWarps * 32;
+  static constexpr int kThreads = 64 + kEpiThreads + (GATHER ? 128 : 0);
   static constexpr int kGatherLag = kStages - 2 > 6 ? 6 : kStages - 2;  // cp.async groups in flight per thread
   static constexpr int kTmemCols = 2 * BN;                              // two accumulator stages
-  // stages + scale/shift staging + barriers + tmem slot, + 1024 for manual alignment
+  // stages + epilogue buffers + scale/shift staging + barriers + tmem slot, + 1024 for manual alignment
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + 2 * kEpiBufBytes + 2 * BN * 4 + (2 * kStages + 8) * 8 + 16 + 1024;
+      kStages * kStageBytes + kEpiBufs * kEpiBufBytes + 2 * BN * 4 + (2 * kStages + 4 + 2 * kEpiBufs) * 8 + 16 + 1024;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -95,12 +113,12 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN, int BK, bool GATHER, bool EPI>
-__global__ void __launch_bounds__(ConvCfg<BN, BK, GATHER, EPI>::kThreads, 1)
+template <int BN, int BK, int KPS, bool GATHER, bool EPI>
+__global__ void __launch_bounds__(ConvCfg<BN, BK, KPS, GATHER, EPI>::kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvParams p) {
-  using Cfg = ConvCfg<BN, BK, GATHER, EPI>;
+  using Cfg = ConvCfg<BN, BK, KPS, GATHER, EPI>;
   constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -108,16 +126,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   uint8_t* stage_base = smem;
-  uint8_t* epi_base = smem + STAGES * Cfg::kStageBytes;  // 2 x kEpiBufBytes, 1024-aligned
-  float* s_scale = reinterpret_cast<float*>(epi_base + 2 * Cfg::kEpiBufBytes);
+  uint8_t* epi_base = smem + STAGES * Cfg::kStageBytes;  // kEpiBufs x kEpiBufBytes, 1024-aligned
+  constexpr int NB = Cfg::kEpiBufs;
+  float* s_scale = reinterpret_cast<float*>(epi_base + NB * Cfg::kEpiBufBytes);
   float* s_shift = s_scale + BN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* res_full_bar = tmem_empty_bar + 2;    // [2] residual tile landed (EPI)
-  uint64_t* res_empty_bar = res_full_bar + 2;     // [2] epilogue buffer free again (EPI)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;    // [NB] residual tile landed (EPI)
+  uint64_t* res_empty_bar = res_full_bar + NB;    // [NB] epilogue buffer free again (EPI)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,9 +150,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&tmem_empty_bar[a], Cfg::kEpiWarps);  // one arrival per epilogue warp
+    }
+    for (int a = 0; a < NB; ++a) {
       mbar_init(&res_full_bar[a], 1);
-      mbar_init(&res_empty_bar[a], 4);
+      mbar_init(&res_empty_bar[a], Cfg::kEpiWarps);
     }
     if (EPI) {
       tma_prefetch_desc(&tmR);
@@ -152,148 +173,193 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    // warp-uniform loops; only the issue itself is predicated on one elected lane
-    const uint32_t tx = GATHER ? Cfg::kBBytes : Cfg::kStageBytes;
-    int kbc = 0, tcp = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcp) {
-      const int n0 = (tile % p.n_tiles) * BN;
-      const int m0 = (tile / p.n_tiles) * kBlockM;
-      if (EPI) {
-        // residual tile of this output tile -> epilogue buffer (free once the stores of the tile that
-        // used it two tiles ago have been read out)
-        const int rb = tcp & 1;
-        mbar_wait(&res_empty_bar[rb], ((tcp >> 1) & 1) ^ 1);
-        int nsub = (p.N - n0 + 63) / 64;
-        nsub = nsub > BN / 64 ? BN / 64 : nsub;
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&res_full_bar[rb], (uint32_t)(nsub * Cfg::kEpiSubBytes));
-          for (int j = 0; j < nsub; ++j)
-            tma_load_2d(epi_base + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, &res_full_bar[rb], n0 + 64 * j, m0);
+    // One elected thread owns the whole loop: no per-stage election / reconvergence, and every barrier and
+    // stage address is a plain shared-window register.
+    if (elect_one_sync()) {
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
+      const uint32_t res_full0 = smem_u32(res_full_bar), res_empty0 = smem_u32(res_empty_bar), epi0 = smem_u32(epi_base);
+      uint32_t s = 0, ph = 0;    // ring slot and its phase
+      uint32_t rb = 0, rph = 0;  // epilogue buffer of this tile and its phase
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        const int m0 = (tile / p.n_tiles) * kBlockM;
+        int wq = 0, hq = 0, dq = 0, nq = 0;
+        if (!GATHER && p.a_mode == A_TMA_IM2COL) {
+          int t = m0;
+          const int wo = t % p.Wo; t /= p.Wo;
+          const int ho = t % p.Ho; t /= p.Ho;
+          const int to = t % p.To; t /= p.To;
+          wq = wo * p.sw - p.pw;
+          hq = ho * p.sh - p.ph;
+          dq = to * p.st - p.pt;
+          nq = t;
         }
-        __syncwarp();
-      }
-      int wq = 0, hq = 0, dq = 0, nq = 0;
-      if (!GATHER && p.a_mode == A_TMA_IM2COL) {
-        int t = m0;
-        const int wo = t % p.Wo; t /= p.Wo;
-        const int ho = t % p.Ho; t /= p.Ho;
-        const int to = t % p.To; t /= p.To;
-        wq = wo * p.sw - p.pw;
-        hq = ho * p.sh - p.ph;
-        dq = to * p.st - p.pt;
-        nq = t;
-      }
-      int c0 = 0, dw = 0, dh = 0, dt = 0;  // walks (tap, channel block) without divisions
-      for (int kb = 0; kb < p.num_kb; ++kb, ++kbc) {
-        const int s = kbc % STAGES;
-        const uint32_t ph = (kbc / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* a_dst = stage_base + s * Cfg::kStageBytes;
-        uint8_t* b_dst = a_dst + Cfg::kABytes;
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full_bar[s], tx);
-          if (!GATHER) {
-            if (p.a_mode == A_TMA_2D)
-              tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-            else
-              tma_load_im2col_5d(a_dst, &tmA, &full_bar[s], c0, wq, hq, dq, nq, (uint16_t)dw, (uint16_t)dh, (uint16_t)dt);
+        int c0 = 0, dw = 0, dh = 0, dt = 0;  // walks (tap, channel block) without divisions
+        for (int kb = 0; kb < p.num_kb; kb += KPS) {
+          const int nk = (KPS == 1 || kb + KPS <= p.num_kb) ? KPS : p.num_kb - kb;
+          mbar_wait_a(empty0 + s * 8, ph ^ 1u);
+          const uint32_t a_dst = stage0 + s * Cfg::kStageBytes;
+          const uint32_t b_dst = a_dst + KPS * Cfg::kABytes;
+          const uint32_t fb = full0 + s * 8;
+          mbar_arrive_expect_tx_a(fb, (uint32_t)nk * (GATHER ? Cfg::kBBytes : Cfg::kKbBytes));
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nk) {
+              if (!GATHER) {
+                if (p.a_mode == A_TMA_2D) {
+                  tma_load_2d_a(a_dst + j * Cfg::kABytes, &tmA, fb, (kb + j) * BK, m0);
+                } else {
+                  tma_load_im2col_5d_a(a_dst + j * Cfg::kABytes, &tmA, fb, c0, wq, hq, dq, nq, (uint16_t)dw, (uint16_t)dh,
+                                       (uint16_t)dt);
+                  c0 += BK;
+                  if (c0 >= p.cin_eff) {
+                    c0 = 0;
+                    if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
+                  }
+                }
+              }
+              tma_load_2d_a(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * BK, n0);
+            }
           }
-          tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
-        }
-        __syncwarp();
-        if (!GATHER && p.a_mode != A_TMA_2D) {
-          c0 += BK;
-          if (c0 >= p.cin_eff) {
-            c0 = 0;
-            if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
+          if (EPI && kb == 0 && p.res != nullptr) {
+            // residual tile of this output tile -> epilogue buffer (free once the stores of the tile that used it
+            // two tiles ago have been read out).  Issued after the tile's first operand stage so that the MMAs
+            // never queue behind the epilogue of an older tile.
+            mbar_wait_a(res_empty0 + rb * 8, rph ^ 1u);
+            int nsub = (p.N - n0 + 63) / 64;
+            nsub = nsub > BN / 64 ? BN / 64 : nsub;
+            mbar_arrive_expect_tx_a(res_full0 + rb * 8, (uint32_t)(nsub * Cfg::kEpiSubBytes));
+            for (int j = 0; j < nsub; ++j)
+              tma_load_2d_a(epi0 + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, res_full0 + rb * 8, n0 + 64 * j, m0);
+            if (++rb == NB) { rb = 0; rph ^= 1u; }
           }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16_m128(BN);
-    const uint64_t desc_hi = umma_desc_kmajor<Cfg::kRowBytes>(0);  // everything but the start address
-    int kbc = 0, tc = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
-      const int acc = tc & 1;
-      const uint32_t aph = (tc >> 1) & 1;
-      mbar_wait(&tmem_empty_bar[acc], aph ^ 1);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < p.num_kb; ++kb, ++kbc) {
-        const int s = kbc % STAGES;
-        const uint32_t ph = (kbc / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+    // One elected thread, software pipelined: the wait for stage g+1 sits between the MMAs of stage g, so the
+    // barrier round trip is covered by tensor work that is already queued.
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(BN);
+      constexpr int MMAS_PER_KB = BK / kUmmaK;
+      const uint64_t desc_hi = umma_desc_kmajor<Cfg::kRowBytes>(0);  // everything but the start address
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
+      const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
+      uint32_t s = 0, ph = 0;
+      int tc = 0;
+      mbar_wait_a(full0, 0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+        const uint32_t acc = (uint32_t)tc & 1u;
+        mbar_wait_a(tempty0 + acc * 8, (((uint32_t)tc >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_lo = smem_u32(stage_base + s * Cfg::kStageBytes) >> 4;
-        const uint64_t adesc = desc_hi | a_lo;
-        const uint64_t bdesc = desc_hi | (a_lo + (Cfg::kABytes >> 4));
-        if (elect_one_sync()) {
-          // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
-          if (kb) umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
-          else    umma_f16_c<false>(d_tmem, adesc, bdesc, idesc);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const bool last_tile = tile + (int)gridDim.x >= p.num_tiles;
+        for (int kb = 0; kb < p.num_kb; kb += KPS) {
+          const int nk = (KPS == 1 || kb + KPS <= p.num_kb) ? KPS : p.num_kb - kb;
+          const bool last_stage = kb + KPS >= p.num_kb;
+          uint32_t ns = s + 1, nph = ph;
+          if (ns == STAGES) { ns = 0; nph ^= 1u; }
+          const uint32_t a_lo = (stage0 + s * Cfg::kStageBytes) >> 4;
+          const uint32_t b_lo = a_lo + ((KPS * Cfg::kABytes) >> 4);
+          const bool do_wait = !(last_stage && last_tile);  // false: this CTA's very last stage
+          bool ready = !do_wait;
+          // NK k-blocks, fully unrolled; the wait for the next stage follows MMA number 3/4 * (NK * MMAS_PER_KB).
+          // On a tile's last stage it is only a probe: the accumulator must be handed to the epilogue even if
+          // the next tile's operands are late (their producer may itself be waiting for that epilogue).
+          auto issue = [&](auto nk_c) {
+            constexpr int NK = decltype(nk_c)::value;
+            constexpr int WAIT_IDX = (NK * MMAS_PER_KB * 3) / 4 - 1;
 #pragma unroll
-          for (int k = 1; k < BK / kUmmaK; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
-          umma_commit(&empty_bar[s]);                                 // frees the smem stage once these MMAs have read it
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+            for (int j = 0; j < NK; ++j) {
+              const uint64_t adesc = desc_hi | (a_lo + j * (Cfg::kABytes >> 4));
+              const uint64_t bdesc = desc_hi | (b_lo + j * (Cfg::kBBytes >> 4));
+#pragma unroll
+              for (int k = 0; k < MMAS_PER_KB; ++k) {
+                // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
+                if (j == 0 && k == 0) umma_f16(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+                else                  umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
+                if (j * MMAS_PER_KB + k == WAIT_IDX && do_wait) {
+                  if (last_stage) {
+                    ready = mbar_try_wait_a(full0 + ns * 8, nph);
+                  } else {
+                    mbar_wait_a(full0 + ns * 8, nph);
+                    ready = true;
+                  }
+                  tc_fence_after();
+                }
+              }
+            }
+          };
+          if (KPS == 1 || nk == KPS) issue(std::integral_constant<int, KPS>{});
+          else                       issue(std::integral_constant<int, 1>{});
+          umma_commit_a(empty0 + s * 8);                       // frees the smem stage once these MMAs have read it
+          if (last_stage) umma_commit_a(tfull0 + acc * 8);     // accumulator complete
+          if (!ready) {
+            mbar_wait_a(full0 + ns * 8, nph);
+            tc_fence_after();
+          }
+          s = ns; ph = nph;
         }
-        __syncwarp();
       }
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ epilogue warps 2..5
-    const int t = threadIdx.x - 64;  // 0..127
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    __syncwarp();
+  } else if (warp < 2 + Cfg::kEpiWarps) {
+    // ------------------------------------------------------------------ epilogue warps
+    constexpr int CPW = Cfg::kColsPerWarp;
+    const int t = threadIdx.x - 64;   // 0 .. kEpiThreads-1
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int col0 = ((warp - 2) >> 2) * CPW;  // first tile column of this warp
+    const bool has_res = p.res != nullptr;
     int tc = 0, cached_n0 = -1;
+    uint32_t eb = 0, eph = 0;  // epilogue buffer of this tile and its phase (EPI)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
       const int n0 = (tile % p.n_tiles) * BN;
       const int m0 = (tile / p.n_tiles) * kBlockM;
       const int acc = tc & 1;
       const uint32_t aph = (tc >> 1) & 1;
-      if (n0 != cached_n0) {  // uniform across the 128 epilogue threads
-        named_bar_sync(1, 128);
-        for (int i = t; i < BN; i += 128) {
+      if (n0 != cached_n0) {  // uniform across the epilogue threads
+        named_bar_sync(1, Cfg::kEpiThreads);
+        for (int i = t; i < BN; i += Cfg::kEpiThreads) {
           const int n = n0 + i;
           s_scale[i] = (n < p.N) ? p.scale[n] : 0.f;
           s_shift[i] = (n < p.N) ? p.shift[n] : 0.f;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, Cfg::kEpiThreads);
         cached_n0 = n0;
       }
       const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      __nv_bfloat16* out_row = p.out + (long long)row * p.ldo + n0;
-      const __nv_bfloat16* res_row = p.res ? p.res + (long long)row * p.ldr + n0 : nullptr;
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0);
       if (EPI) {
-        // residual (TMA-prefetched) is read from, and the bf16 result written back to, the same swizzled
-        // shared-memory tile; each warp then TMA-stores its 32 rows (full 128-byte lines, clipped at M / N)
-        mbar_wait(&res_full_bar[acc], aph);
+        // The residual (TMA-prefetched) is read from, and the bf16 result written back to, the same swizzled
+        // shared-memory tile; each warp then TMA-stores its 32 rows x CPW columns (full 128-byte lines,
+        // clipped at M / N by the tensor map).  Without a residual the buffer only stages the store.
+        if (has_res) mbar_wait(&res_full_bar[eb], eph);
         const int lrow = q * 32 + lane;
-        const uint32_t buf = smem_u32(epi_base + acc * Cfg::kEpiBufBytes) + (uint32_t)lrow * 128u;
+        const uint32_t buf = smem_u32(epi_base + eb * Cfg::kEpiBufBytes) + (uint32_t)lrow * 128u;
         const uint32_t xr = (uint32_t)(lrow & 7);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-          tmem_ld_wait();
+        auto chunk = [&](const uint32_t (&v)[32], int c, auto res_c) {
+          constexpr bool RES = decltype(res_c)::value;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int col = c * 32 + g * 8;
+            const int col = col0 + c * 32 + g * 8;
             const uint32_t addr = buf + (uint32_t)(col >> 6) * Cfg::kEpiSubBytes + ((((uint32_t)(col & 63) >> 3) ^ xr) << 4);
-            uint4 r;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col + j], s_shift[col + j]);
-            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-            f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-            f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+            if (RES) {
+              uint4 r;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+              f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+              f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+              f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+              f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+            }
             if (p.relu) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -302,38 +368,57 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t o2 = pack_bf16x2(f[4], f[5]), o3 = pack_bf16x2(f[6], f[7]);
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
           }
+        };
+#pragma unroll 1
+        for (int c = 0; c < CPW / 32; c += 2) {
+          // two TMEM loads in flight per wait
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32), v0);
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32 + 32), v1);
+          tmem_ld_wait();
+          if (has_res) {
+            chunk(v0, c, std::true_type{});
+            chunk(v1, c + 1, std::true_type{});
+          } else {
+            chunk(v0, c, std::false_type{});
+            chunk(v1, c + 1, std::false_type{});
+          }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may start tile i+2
-        fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA store
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0) {
-          int nsub = (p.N - n0 + 63) / 64;
-          nsub = nsub > BN / 64 ? BN / 64 : nsub;
-          for (int j = 0; j < nsub; ++j)
-            tma_store_2d(&tmO, epi_base + acc * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes + q * 32 * 128, n0 + 64 * j,
-                         m0 + q * 32);
+          mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may start tile i+2
+#pragma unroll
+          for (int j = col0 / 64; j < (col0 + CPW) / 64; ++j)
+            if (n0 + 64 * j < p.N)
+              tma_store_2d(&tmO, epi_base + eb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes + q * 32 * 128, n0 + 64 * j,
+                           m0 + q * 32);
           tma_store_commit();
-          tma_store_wait_read<0>();          // smem may be overwritten once the store engine has read it
-          mbar_arrive(&res_empty_bar[acc]);  // 4 arrivals (one per epilogue warp) free the buffer
+          tma_store_wait_read<0>();                      // smem may be overwritten once the store engine has read it
+          if (has_res) mbar_arrive(&res_empty_bar[eb]);  // one arrival per epilogue warp frees the buffer
         }
         __syncwarp();
+        if (++eb == NB) { eb = 0; eph ^= 1u; }
         continue;
       }
+      const bool row_ok = row < p.M;
+      __nv_bfloat16* out_row = p.out + (long long)row * p.ldo + n0 + col0;
+      const __nv_bfloat16* res_row = p.res ? p.res + (long long)row * p.ldr + n0 + col0 : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CPW / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int col = c * 32 + g * 8;
-            if (n0 + col < p.N) {
+            const int col = c * 32 + g * 8;  // relative to col0
+            if (n0 + col0 + col < p.N) {
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col + j], s_shift[col + j]);
+                f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col0 + col + j], s_shift[col0 + col + j]);
               if (res_row) {
                 const uint4 r = *reinterpret_cast<const uint4*>(res_row + col);
                 f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
@@ -356,13 +441,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);  // 128 arrivals hand the accumulator back to the MMA warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);  // one arrival per epilogue warp hands the accumulator back
     }
   } else {
-    // ------------------------------------------------------------------ gather warps 6..9 (GATHER only)
+    // ------------------------------------------------------------------ gather warps (GATHER only)
     if (GATHER) {
       constexpr int LAG = Cfg::kGatherLag;
-      const int t = threadIdx.x - 192;  // 0..127: tile row owned by this thread
+      const int t = threadIdx.x - (64 + Cfg::kEpiThreads);  // 0..127: tile row owned by this thread
       const uint32_t sw_xor = (uint32_t)(t & 7);
       int g = 0;  // k-blocks issued so far (across tiles)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -423,7 +509,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
-  if (EPI && warp >= 2 && warp < 6 && lane == 0) tma_store_wait<0>();  // bulk stores fully complete
+  if (EPI && warp >= 2 && warp < 2 + Cfg::kEpiWarps && lane == 0) tma_store_wait<0>();  // bulk stores fully complete
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -301,75 +301,98 @@ stem_umma_v2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    // ------------------------------------------------------------------ TMA producer (one elected thread)
     if (elect_one_sync()) {
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
       mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
       for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
+      const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * pp.seg_bytes);
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int wb = r % p.tiles_w; r /= p.tiles_w;
+        const int hb = r % p.tiles_h; r /= p.tiles_h;
+        const int to = r % p.To;
+        const int n = r / p.To;
+        const int h_start = 2 * (hb * 16) - p.ph;
+        const int x_start = wb * 8 * 8;  // 8 windows x (2 px x 4 ch) elements
+        const int t0 = to * p.st - p.pt;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          mbar_wait_a(empty0 + s * 8, ph ^ 1u);
+          const uint32_t dst = stage0 + s * (uint32_t)p.stage_bytes;
+          const uint32_t fb = full0 + s * 8;
+          if (p.dbg & 4) {
+            mbar_arrive_a(fb);
+          } else {
+            mbar_arrive_expect_tx_a(fb, tx);
+            tma_load_4d_a(dst, &tmE, fb, x_start, h_start, t0 + dt, n);
+            tma_load_4d_a(dst + (uint32_t)p.off_odd, &tmOdd, fb, x_start, h_start + 1, t0 + dt, n);
+          }
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+        }
+      }
     }
     __syncwarp();
-    const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * pp.seg_bytes);
-    int kc = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int r = tile;
-      const int wb = r % p.tiles_w; r /= p.tiles_w;
-      const int hb = r % p.tiles_h; r /= p.tiles_h;
-      const int to = r % p.To;
-      const int n = r / p.To;
-      const int h_start = 2 * (hb * 16) - p.ph;
-      const int x_start = wb * 8 * 8;  // 8 windows x (2 px x 4 ch) elements
-      for (int dt = 0; dt < p.kt; ++dt, ++kc) {
-        const int s = kc % S;
-        mbar_wait(&empty_bar[s], ((kc / S) & 1) ^ 1);
-        uint8_t* dst = stage_base + s * p.stage_bytes;
-        const int ti = to * p.st - p.pt + dt;
-        if (elect_one_sync()) {
-          if (p.dbg & 4) {
-            mbar_arrive(&full_bar[s]);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], tx);
-            tma_load_4d(dst, &tmE, &full_bar[s], x_start, h_start, ti, n);
-            tma_load_4d(dst + p.off_odd, &tmOdd, &full_bar[s], x_start, h_start + 1, ti, n);
-          }
-        }
-        __syncwarp();
-      }
-    }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
-    constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
-    mbar_wait(w_bar, 0);
-    int kc = 0, tc = 0;
-    const uint32_t seg = (uint32_t)pp.seg_bytes;
-    const uint32_t w_addr = smem_u32(w_smem);
-    // descriptor high words are loop invariant; only the 14-bit start-address field moves
-    const uint64_t a_hi = umma_desc_kmajor_noswizzle(0, 16u, seg);
-    const uint64_t b_hi = umma_desc_kmajor<64>(0);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
-      const int acc = tc & 1;
-      mbar_wait(&tmem_empty_bar[acc], ((tc >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
-      for (int dt = 0; dt < p.kt; ++dt, ++kc) {
-        const int s = kc % S;
-        mbar_wait(&full_bar[s], (kc / S) & 1);
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    // Software pipelined like the generic kernel: the wait for the next dt stage sits inside the 2 * kh MMAs
+    // of the current one (tools/umma_bench.cu: N = 64 reaches its 48-cycle floor this way).
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
+      const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
+      mbar_wait(w_bar, 0);
+      const uint32_t seg = (uint32_t)pp.seg_bytes;
+      const uint32_t w_addr = smem_u32(w_smem);
+      // descriptor high words are loop invariant; only the 14-bit start-address field moves
+      const uint64_t a_hi = umma_desc_kmajor_noswizzle(0, 16u, seg);
+      const uint64_t b_hi = umma_desc_kmajor<64>(0);
+      const int kh = (p.dbg & 2) ? 0 : p.kh;
+      const int wait_dh = (kh * 3) / 4;  // wait for the next stage after this many taps
+      uint32_t s = 0, ph = 0;
+      int tc = 0;
+      mbar_wait_a(full0, 0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+        const uint32_t acc = (uint32_t)tc & 1u;
+        mbar_wait_a(tempty0 + acc * 8, (((uint32_t)tc >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t st_addr = smem_u32(stage_base + s * p.stage_bytes);
-        if (elect_one_sync()) {
+        const uint32_t d_tmem = tmem_base + acc * 64u;
+        const bool last_tile = tile + (int)gridDim.x >= p.num_tiles;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          uint32_t ns = s + 1, nph = ph;
+          if (ns == (uint32_t)S) { ns = 0; nph ^= 1u; }
+          const bool do_wait = !(last_tile && dt == p.kt - 1);
+          const uint32_t st_addr = stage0 + s * (uint32_t)p.stage_bytes;
           uint32_t b_lo = (w_addr + (uint32_t)(dt * p.kh) * kStemTapBytes) >> 4;
-          for (int dh = 0; dh < ((p.dbg & 2) ? 0 : p.kh); ++dh, b_lo += kStemTapBytes >> 4) {
-            const uint32_t a_lo = (st_addr + ((dh & 1) ? (uint32_t)p.off_odd : 0u) + (uint32_t)(dh >> 1) * seg) >> 4;
+          const uint32_t a_even = st_addr >> 4, a_odd = (st_addr + (uint32_t)p.off_odd) >> 4, seg16 = seg >> 4;
+          auto tap = [&](int dh) {
+            const uint32_t a_lo = ((dh & 1) ? a_odd : a_even) + (uint32_t)(dh >> 1) * seg16;
             const uint64_t adesc = a_hi | a_lo;
             const uint64_t bdesc = b_hi | b_lo;
-            if (dt | dh) umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
-            else         umma_f16_c<false>(d_tmem, adesc, bdesc, idesc);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (dt | dh) ? 1u : 0u);
             umma_f16_c<true>(d_tmem, adesc + 2, bdesc + 2, idesc);
+            b_lo += kStemTapBytes >> 4;
+          };
+          if (kh == 7) {
+#pragma unroll
+            for (int dh = 0; dh < 7; ++dh) {
+              tap(dh);
+              if (dh == 4 && do_wait) { mbar_wait_a(full0 + ns * 8, nph); tc_fence_after(); }
+            }
+          } else {
+            for (int dh = 0; dh < kh; ++dh) {
+              tap(dh);
+              if (dh == wait_dh && do_wait) { mbar_wait_a(full0 + ns * 8, nph); tc_fence_after(); }
+            }
+            if (kh <= wait_dh && do_wait) { mbar_wait_a(full0 + ns * 8, nph); tc_fence_after(); }
           }
-          umma_commit(&empty_bar[s]);
-          if (dt == p.kt - 1) umma_commit(&tmem_full_bar[acc]);
+          umma_commit_a(empty0 + s * 8);
+          if (dt == p.kt - 1) umma_commit_a(tfull0 + acc * 8);
+          s = ns; ph = nph;
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int lrow = q * 32 + lane;  // tile row = TMEM lane: (h_i, w_i) = (lrow / 8, lrow % 8)

@@ -89,6 +89,7 @@ struct OpRuntime {
   int res_c = 0, dst_c = 0;
   int bn = 0;
   int bk = 64;
+  int kps = 1;        // k-blocks per pipeline stage (2: eight MMAs per barrier round trip for BN <= 128)
   int grid = 0;
   bool fold = false;
   bool stem = false;  // dedicated stem kernel (spatial tiles, resident weights)
@@ -116,6 +117,8 @@ struct vad_plan {
   bool stem_v1 = false;      // VAD_STEM_V1=1: im2col-box stem kernel instead of the raw-segment (v2) one
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
+  bool epi_all = false;      // VAD_EPI_ALL=1: staged TMA-store epilogue for every layer (tuning only)
+  int kps_override = 0;      // VAD_KPS=1|2: force k-blocks per stage (tuning only)
   bool stem_gather = false;  // VAD_STEM_GATHER=1: feed the stem through the cp.async gather producer
   int batch = 0, T = 0, H = 0, W = 0;
   bool configured = false;
@@ -199,6 +202,8 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   p->stem_v1 = sv1 && sv1[0] == '1';
   const char* sgen = getenv("VAD_STEM_GENERIC");
   p->stem_generic = sgen && sgen[0] == '1';
+  { const char* k = getenv("VAD_KPS"); p->kps_override = k ? atoi(k) : 0; }
+  { const char* k = getenv("VAD_EPI_ALL"); p->epi_all = k && k[0] == '1'; }
   const char* ne = getenv("VAD_NO_EPI");
   p->no_epi = ne && ne[0] == '1';
   *plan = p;
@@ -280,8 +285,13 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         r.a_mode = A_TMA_IM2COL;
       c.a_mode = r.a_mode;
       c.num_kb = r.bk == 64 ? r.K_pad / 64 : (K + 31) / 32;
-      r.epi = d.res >= 0 && !p->no_epi;  // residual layers: staged epilogue (two 128 x BN tiles in smem)
+      // staged epilogue (two 128 x BN tiles in smem, TMA store; residual prefetched by TMA): residual layers, and
+      // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections), VAD_EPI_ALL=1: every layer
+      r.epi = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K) || p->epi_all);
       r.bn = (d.cout > 128 && !r.epi) ? 256 : (d.cout > 64 ? 128 : 64);
+      r.kps = (r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2 && !r.epi) ? 2 : 1;
+      if (p->kps_override == 1) r.kps = 1;
+      if (p->kps_override == 2 && r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2) r.kps = 2;
       const long long m_tiles = (M + kBlockM - 1) / kBlockM;
       const long long n_tiles = (d.cout + r.bn - 1) / r.bn;
       if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
@@ -441,14 +451,17 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
       memset(&r.tmO, 0, sizeof(r.tmO));
       if (r.epi) {
         // residual [M, res_c] -> 128-row x 64-channel boxes; output slice [M, cout] (row pitch dst_c) <- 32-row boxes
-        cuuint64_t rdim[2] = {(cuuint64_t)r.res_c, (cuuint64_t)c.M};
-        cuuint64_t rstr[1] = {(cuuint64_t)r.res_c * 2};
-        cuuint32_t rbox[2] = {64, (cuuint32_t)kBlockM};
         cuuint32_t es2[2] = {1, 1};
-        CUresult cr = p->encode_tiled(&r.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c.res, rdim, rstr, rbox, es2,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(residual) failed: %d", i, (int)cr);
+        CUresult cr;
+        if (d.res >= 0) {
+          cuuint64_t rdim[2] = {(cuuint64_t)r.res_c, (cuuint64_t)c.M};
+          cuuint64_t rstr[1] = {(cuuint64_t)r.res_c * 2};
+          cuuint32_t rbox[2] = {64, (cuuint32_t)kBlockM};
+          cr = p->encode_tiled(&r.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c.res, rdim, rstr, rbox, es2,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(residual) failed: %d", i, (int)cr);
+        }
         cuuint64_t odim[2] = {(cuuint64_t)d.cout, (cuuint64_t)c.M};
         cuuint64_t ostr[1] = {(cuuint64_t)r.dst_c * 2};
         cuuint32_t obox[2] = {64, 32};
@@ -574,31 +587,34 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
   return VAD_OK;
 }
 
-template <int BN, int BK, bool GATHER, bool EPI>
+template <int BN, int BK, int KPS, bool GATHER, bool EPI>
 static cudaError_t launch_conv(const OpRuntime& r, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, BK, GATHER, EPI>;
+  using Cfg = ConvCfg<BN, BK, KPS, GATHER, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, GATHER, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, KPS, GATHER, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_umma_kernel<BN, BK, GATHER, EPI><<<r.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
+  conv_umma_kernel<BN, BK, KPS, GATHER, EPI><<<r.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
   return cudaGetLastError();
 }
 
+template <int BN, bool EPI>
+static cudaError_t launch_conv_bn(const OpRuntime& r, cudaStream_t st) {
+  if (r.a_mode == A_GATHER) return launch_conv<BN, 64, 1, true, EPI>(r, st);
+  if (r.kps == 2) return launch_conv<BN, 64, 2, false, EPI>(r, st);
+  return launch_conv<BN, 64, 1, false, EPI>(r, st);
+}
+
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
-  const bool g = r.a_mode == A_GATHER;
-  if (r.bk == 32) return launch_conv<64, 32, false, false>(r, st);  // folded stem, TMA window view
-  if (r.epi) {
-    if (r.bn == 128) return g ? launch_conv<128, 64, true, true>(r, st) : launch_conv<128, 64, false, true>(r, st);
-    return g ? launch_conv<64, 64, true, true>(r, st) : launch_conv<64, 64, false, true>(r, st);
-  }
+  if (r.bk == 32) return launch_conv<64, 32, 1, false, false>(r, st);  // folded stem, TMA window view
+  if (r.epi) return r.bn == 128 ? launch_conv_bn<128, true>(r, st) : launch_conv_bn<64, true>(r, st);
   switch (r.bn) {
-    case 256: return g ? launch_conv<256, 64, true, false>(r, st) : launch_conv<256, 64, false, false>(r, st);
-    case 128: return g ? launch_conv<128, 64, true, false>(r, st) : launch_conv<128, 64, false, false>(r, st);
-    default:  return g ? launch_conv<64, 64, true, false>(r, st) : launch_conv<64, 64, false, false>(r, st);
+    case 256: return r.a_mode == A_GATHER ? launch_conv<256, 64, 1, true, false>(r, st) : launch_conv<256, 64, 1, false, false>(r, st);
+    case 128: return launch_conv_bn<128, false>(r, st);
+    default:  return launch_conv_bn<64, false>(r, st);
   }
 }
 
