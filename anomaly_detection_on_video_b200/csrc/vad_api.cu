@@ -94,10 +94,8 @@ struct OpRuntime {
   bool fold = false;
   bool stem = false;  // dedicated stem kernel (spatial tiles, resident weights)
   StemParams sp;
-  CUtensorMap tmE, tmOdd, tmW;
+  CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
-  bool stem_v2 = false;
-  int stem_seg = 0;
   int a_mode = 0;
   int avg_P = 0, avg_C = 0;
   // for tensor-map encoding
@@ -114,7 +112,6 @@ struct vad_plan {
   int in_channels = 0;
   int device = 0;
   int sm_count = 148;
-  bool stem_v1 = false;      // VAD_STEM_V1=1: im2col-box stem kernel instead of the raw-segment (v2) one
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool epi_all = false;      // VAD_EPI_ALL=1: staged TMA-store epilogue for every layer (tuning only)
@@ -173,6 +170,8 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: parameter offsets must be aligned (weights 128 B, scale/shift 16 B)", i);
       if (d.kt < 1 || d.kh < 1 || d.kw < 1 || d.st < 1 || d.sh < 1 || d.sw < 1 || d.pt < 0 || d.ph < 0 || d.pw < 0)
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad kernel/stride/pad", i);
+      if ((d.flags & VAD_FLAG_POOL_T2) && !fold)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: POOL_T2 is fused into the stem kernel only (needs STEM_FOLD_W)", i);
       if (fold && in_channels != 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs the stem input layout (in_channels == 0)", i);
       if (fold && (d.kw > 8 || d.src != 0 || in_pad_left < d.pw || ((in_pad_left - d.pw) & 1) || (d.sw & 1)))
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs src=0, kw<=8, even sw, in_pad_left-pw even and >=0", i);
@@ -198,8 +197,6 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   if (p->sm_count <= 0) p->sm_count = 148;
   const char* sg = getenv("VAD_STEM_GATHER");
   p->stem_gather = sg && sg[0] == '1';
-  const char* sv1 = getenv("VAD_STEM_V1");
-  p->stem_v1 = sv1 && sv1[0] == '1';
   const char* sgen = getenv("VAD_STEM_GENERIC");
   p->stem_generic = sgen && sgen[0] == '1';
   { const char* k = getenv("VAD_KPS"); p->kps_override = k ? atoi(k) : 0; }
@@ -300,35 +297,42 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
       r.stem = false;
+      const bool pool_t2 = (d.flags & VAD_FLAG_POOL_T2) != 0;
       if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0) {
         StemParams& q = r.sp;
         memset(&q, 0, sizeof(q));
         q.B = batch; q.To = To; q.Ho = Ho; q.Wo = Wo;
+        q.pool_t = pool_t2 ? 2 : 1;
+        q.To_out = To / q.pool_t;
         q.kt = d.kt; q.kh = d.kh; q.st = d.st; q.pt = d.pt; q.ph = d.ph;
-        const bool v2 = !p->stem_v1;
-        const int th = v2 ? 16 : 8, tw = v2 ? 8 : 16;  // output tile: v2 8 (w) x 16 (h), v1 16 (w) x 8 (h)
+        const int th = 16, tw = 8;  // output tile: 8 (w) x 16 (h)
         q.tiles_w = (Wo + tw - 1) / tw; q.tiles_h = (Ho + th - 1) / th;
-        const long long nt = (long long)batch * To * q.tiles_h * q.tiles_w;
+        const long long nu = (long long)batch * q.To_out * q.tiles_h * q.tiles_w;
         q.rows_even = th + (d.kh + 1) / 2 - 1;
         q.rows_odd = th + d.kh / 2 - 1;
-        const int seg = v2 ? ((8 - 1) * d.sw * 4 + 32) * 2 : 1024;  // bytes per input-row segment in smem
-        q.off_odd = (int)align_up((uint64_t)q.rows_even * seg, 128);
-        q.stage_bytes = (int)align_up((uint64_t)q.off_odd + (uint64_t)q.rows_odd * seg, v2 ? 128 : 1024);
+        q.seg_bytes = ((tw - 1) * d.sw * 4 + 32) * 2;  // bytes per raw input-row segment in smem (176)
+        q.off_odd = (int)align_up((uint64_t)q.rows_even * q.seg_bytes, 128);
+        q.stage_bytes = (int)align_up((uint64_t)q.off_odd + (uint64_t)q.rows_odd * q.seg_bytes, 128);
         const int w_bytes = d.kt * d.kh * kStemTapBytes;
-        int ns = (220 * 1024 - w_bytes) / q.stage_bytes;
-        const int max_ns = v2 ? kStemV2MaxStages : 4;
-        if (ns > max_ns) ns = max_ns;
-        if (ns >= 2 && nt <= 0x7fffffffLL && d.kh > 1) {
+        const int fixed = w_bytes + 2 * kStemStagingBytes + 2 * 64 * 4 + (2 * kStemMaxStages + 5) * 8 + 16 + 1024;
+        int ns = (227 * 1024 - fixed) / q.stage_bytes;
+        if (ns > kStemMaxStages) ns = kStemMaxStages;
+        if (ns >= 2 && nu > 0 && nu <= 0x7fffffffLL && d.kh > 1) {
           q.n_stages = ns;
-          q.num_tiles = (int)nt;
-          q.relu = c.relu; q.ldo = Cdst;
+          q.num_units = (int)nu;
+          q.relu = c.relu;
           { const char* sd = getenv("VAD_STEM_DEBUG"); q.dbg = sd ? atoi(sd) : 0; }
-          r.stem_smem = w_bytes + ns * q.stage_bytes + 2 * 64 * 4 + (8 + 8 + 2 + 2 + 1) * 8 + 16 + 1024;
+          r.stem_smem = fixed + ns * q.stage_bytes;
           r.stem = true;
-          r.stem_v2 = v2;
-          r.stem_seg = seg;
-          r.grid = q.num_tiles < p->sm_count ? q.num_tiles : p->sm_count;
+          r.grid = q.num_units < p->sm_count ? q.num_units : p->sm_count;
         }
+      }
+      if (pool_t2) {
+        if (!r.stem)
+          return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: POOL_T2 needs the dedicated stem kernel (stride 2, cout 64, TMA input, "
+                      "no residual)", i);
+        if (To < 2) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: POOL_T2 needs at least two output frames", i);
+        To = To / 2;  // shape of the dst slot
       }
       const uint64_t need_w = d.w_off + (uint64_t)d.cout * r.K_pad * 2;
       if (need_w > p->params_bytes || d.scale_off + 4ull * d.cout > p->params_bytes || d.shift_off + 4ull * d.cout > p->params_bytes)
@@ -342,11 +346,11 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         r.res_c = rs.C;
       }
       const int cin_real = fold ? 3 : d.cin;
-      p->op_flops[i] = 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;
+      p->op_flops[i] = 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;  // frames the reference conv produces
       p->flops += p->op_flops[i];
       // activations read once, weights once, output written once (+ residual read)
       p->op_bytes[i] = 2.0 * ((double)batch * src.T * src.H * src.W * src.C + (double)d.cout * r.K_pad +
-                              (double)M * d.cout * (d.res >= 0 ? 2 : 1));
+                              (double)M * d.cout * (d.res >= 0 ? 2.0 : (pool_t2 ? 0.5 : 1.0)));
     } else if (d.kind == VAD_OP_MAXPOOL) {
       PoolParams& q = r.pp;
       memset(&q, 0, sizeof(q));
@@ -471,45 +475,23 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(output) failed: %d", i, (int)cr);
       }
       if (r.stem) {
-        // rank-5 tiled maps over the overlapping window view (C' = 32, W' = Wo, H, T, N); even / odd input
-        // rows of one dt are two boxes of 16 windows x rows (row stride 2)
+        // raw padded rows viewed as (x = Wp * 4 elements, H, T, N): a box is 88 contiguous elements (the union of
+        // 8 overlapping windows) x rows with stride 2, no swizzle; even / odd input rows are two boxes
         StemParams& q = r.sp;
-        q.scale = c.scale; q.shift = c.shift; q.out = c.out;
+        q.scale = c.scale; q.shift = c.shift;
         const uint64_t wp = (uint64_t)p->slots[0].W;
-        cuuint64_t gdim[5] = {32, (cuuint64_t)c.Wo, (cuuint64_t)r.Hi, (cuuint64_t)r.Ti, (cuuint64_t)p->batch};
-        cuuint64_t gstr[4];
-        gstr[0] = (cuuint64_t)d.sw * 4 * 2;
-        gstr[1] = wp * 4 * 2;
-        gstr[2] = gstr[1] * r.Hi;
-        gstr[3] = gstr[2] * r.Ti;
-        CUresult cr;
-        if (r.stem_v2) {
-          // raw padded rows: (x = Wp * 4 elements, H, T, N); a box is 88 contiguous elements (the union of 8
-          // overlapping windows) x rows with stride 2, no swizzle
-          cuuint64_t rdim[4] = {(cuuint64_t)wp * 4, (cuuint64_t)r.Hi, (cuuint64_t)r.Ti, (cuuint64_t)p->batch};
-          cuuint64_t rstr[3] = {gstr[1], gstr[2], gstr[3]};
-          cuuint32_t res4[4] = {1, 2, 1, 1};
-          cuuint32_t bE[4] = {(cuuint32_t)(r.stem_seg / 2), (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
-          cuuint32_t bO[4] = {(cuuint32_t)(r.stem_seg / 2), (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
-          cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.in, rdim, rstr, bE, res4,
+        cuuint64_t rdim[4] = {(cuuint64_t)wp * 4, (cuuint64_t)r.Hi, (cuuint64_t)r.Ti, (cuuint64_t)p->batch};
+        cuuint64_t rstr[3] = {wp * 4 * 2, wp * 4 * 2 * r.Hi, wp * 4 * 2 * r.Hi * r.Ti};
+        cuuint32_t res4[4] = {1, 2, 1, 1};
+        cuuint32_t bE[4] = {(cuuint32_t)(q.seg_bytes / 2), (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
+        cuuint32_t bO[4] = {(cuuint32_t)(q.seg_bytes / 2), (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
+        CUresult cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.in, rdim, rstr, bE, res4,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS)
+          cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.in, rdim, rstr, bO, res4,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-          if (cr == CUDA_SUCCESS)
-            cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.in, rdim, rstr, bO, res4,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        } else {
-          cuuint32_t es[5] = {1, 1, 2, 1, 1};
-          cuuint32_t boxE[5] = {32, 16, (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
-          cuuint32_t boxO[5] = {32, 16, (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
-          cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxE, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-          if (cr == CUDA_SUCCESS)
-            cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, boxO, es,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        }
         if (cr == CUDA_SUCCESS) {
           cuuint64_t wdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
           cuuint64_t wstr[1] = {(cuuint64_t)r.K_pad * 2};
@@ -518,6 +500,18 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
           cr = p->encode_tiled(&r.tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), wdim, wstr, wbox,
                                wes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (cr == CUDA_SUCCESS) {
+          // output [N, To_out, Ho, Wo, Cdst] (channel slice at c.out): one store per epilogue warp = 64 channels x
+          // 8 columns x 4 rows out of the 128B-swizzled staging tile
+          const uint64_t cb = (uint64_t)r.dst_c * 2;
+          cuuint64_t odim[5] = {(cuuint64_t)d.cout, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.To_out, (cuuint64_t)p->batch};
+          cuuint64_t ostr[4] = {cb, cb * q.Wo, cb * q.Wo * q.Ho, cb * q.Wo * q.Ho * q.To_out};
+          cuuint32_t obox[5] = {64, 8, 4, 1, 1};
+          cuuint32_t oes[5] = {1, 1, 1, 1, 1};
+          cr = p->encode_tiled(&r.tmSO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.out, odim, ostr, obox, oes,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
         if (cr != CUDA_SUCCESS)
           return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(stem) failed: %d; set VAD_STEM_GENERIC=1", i, (int)cr);
@@ -660,20 +654,8 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
           stem_attr = (e == cudaSuccess);
         }
         if (e == cudaSuccess) {
-          if (r.stem_v2) {
-            static bool v2_attr = false;
-            if (!v2_attr) {
-              e = cudaFuncSetAttribute(stem_umma_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-              v2_attr = (e == cudaSuccess);
-            }
-            StemV2Params sp2;
-            sp2.s = r.sp;
-            sp2.seg_bytes = r.stem_seg;
-            if (e == cudaSuccess) stem_umma_v2_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, sp2);
-          } else {
-            stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.sp);
-          }
-          if (e == cudaSuccess) e = cudaGetLastError();
+          stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, r.sp);
+          e = cudaGetLastError();
         }
       } else {
         e = launch_conv_any(r, st);
@@ -686,6 +668,8 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
       const int g = grid_for(total, 256, 148 * 64);
       if (inb && q.kt == 2 && q.kh == 3 && q.kw == 3)
         maxpool3d_fixed_kernel<2, 3, 3><<<g, 256, 0, st>>>(q);   // I3Res50 maxpool1
+      else if (inb && q.kt == 1 && q.kh == 3 && q.kw == 3)
+        maxpool3d_fixed_kernel<1, 3, 3><<<g, 256, 0, st>>>(q);   // I3Res50 maxpool1 after the stem's fused temporal max
       else if (inb && q.kt == 2 && q.kh == 1 && q.kw == 1)
         maxpool3d_fixed_kernel<2, 1, 1><<<g, 256, 0, st>>>(q);   // I3Res50 maxpool2
       else if (inb && q.kt == 1 && q.kh == 1 && q.kw == 1)

@@ -65,6 +65,7 @@ class _NativeBackbone(nn.Module):
         self._plan: Optional[BackbonePlan] = None
         self._plan_key = None
         self.force_gather = False  # debug: feed every conv through the cp.async gather producer
+        self.fuse_stem_pool = True  # temporal half of maxpool1 in the stem epilogue (VAD_FLAG_POOL_T2)
 
     # subclasses return (ops, packer, n_slots)
     def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
@@ -89,7 +90,7 @@ class _NativeBackbone(nn.Module):
         return tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers()))
 
     def plan(self, device: torch.device) -> BackbonePlan:
-        key = (self._param_key(), str(device), self.force_gather)
+        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool)
         if self._plan is None or self._plan_key != key:
             ops, packer, n_slots = self._build_table()
             self._plan = BackbonePlan(ops, packer.blob(), n_slots, STEM_PAD_LEFT, device)
@@ -147,8 +148,17 @@ class I3Res50(_NativeBackbone):
         pk = ParamPacker()
         ops: List[Op] = []
         T1, T2, DS = 3, 4, 5  # bottleneck temporaries; slots 1/2 ping-pong the block input/output
-        ops.append(self._conv_op(pk, self.conv1, self.bn1, src=0, dst=1, relu=True, fold_w=True, name="conv1"))
-        ops.append(Op(kind=_lib.VAD_OP_MAXPOOL, src=1, dst=2, kernel=(2, 3, 3), stride=(2, 2, 2), name="maxpool1"))
+        stem = self._conv_op(pk, self.conv1, self.bn1, src=0, dst=1, relu=True, fold_w=True, name="conv1")
+        if self.fuse_stem_pool and not self.force_gather:
+            # maxpool1 = max over (2,3,3) / stride (2,2,2), pad 0 (reference src/i3d.py:212-214) separates exactly into
+            # a max over frame pairs -- done in the stem kernel's epilogue, so the full-rate stem output never
+            # reaches HBM -- followed by a spatial (1,3,3) / (1,2,2) max-pool.
+            stem.flags |= _lib.VAD_FLAG_POOL_T2
+            ops.append(stem)
+            ops.append(Op(kind=_lib.VAD_OP_MAXPOOL, src=1, dst=2, kernel=(1, 3, 3), stride=(1, 2, 2), name="maxpool1"))
+        else:
+            ops.append(stem)
+            ops.append(Op(kind=_lib.VAD_OP_MAXPOOL, src=1, dst=2, kernel=(2, 3, 3), stride=(2, 2, 2), name="maxpool1"))
         cur = 2
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self, f"layer{li}")):

@@ -297,27 +297,43 @@ def main():
         conv_flops = sum(p["flops"] for p in conv)
         all_ms = sum(p["ms"] for p in prof) or 1.0
         roofline = None
+        family = None
         if conv_ms > 0:
             achieved = conv_flops / (conv_ms / 1e3) / 1e12
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "conv_dram_traffic.json")
-            if os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             top = sorted(conv, key=lambda p: -p["ms"])[:6]
-            roofline = {
-                "bound": "tensor", "kernel": "conv_umma_kernel (53 launches per forward, aggregated)",
+            family = {
+                "bound": "tensor", "kernel": "stem_umma_kernel + conv_umma_kernel (53 launches per forward, aggregated)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
-                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step); burst {peaks['bf16_burst']}",
-                "frac_of_burst": achieved / peaks["bf16_burst"],
+                "frac": achieved / peaks["bf16_sustained"], "frac_of_burst": achieved / peaks["bf16_burst"],
                 "conv_share_of_backbone_time": conv_ms / all_ms,
                 "launches_timed": int(sum(p["calls"] for p in conv)),
-                "avg_launch_ms": conv_ms / max(1, sum(p["calls"] for p in conv)),
-                "flops_per_launch_avg": conv_flops / max(1, sum(p["calls"] for p in conv)),
                 "top_layers": [{"name": p["name"], "ms_per_launch": p["ms"] / p["calls"],
                                 "tflops": p["flops"] / (p["ms"] / 1e3) / 1e12} for p in top],
                 "whole_step_frac_of_sustained": value * FLOP_PER_CLIP / 1e12 / peaks["bf16_sustained"] / world,
             }
+            # the dominant single kernel: the stem (conv1), ~22% of the step.  Algorithmic FLOPs per launch =
+            # 9.443 GFLOP per clip-crop (4.721 GMAC) x the clip-crops of the launch; duration =
+            # CUDA events around every launch of it inside the timed region.
+            stem = [p for p in conv if p["name"] == "conv1"]
+            if stem:
+                st = stem[0]
+                s_ach = st["flops"] / (st["ms"] / 1e3) / 1e12
+                traffic = None
+                tpath = os.path.join(ROOT, "profiles", "stem_dram_traffic.json")
+                if os.path.exists(tpath):
+                    traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                roofline = {
+                    "bound": "tensor", "kernel": "stem_umma_kernel (conv1 5x7x7/2 + BN + ReLU + temporal max-pool)",
+                    "achieved": s_ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": s_ach / peaks["bf16_sustained"], "frac_of_burst": s_ach / peaks["bf16_burst"],
+                    "traffic": traffic,
+                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step); burst {peaks['bf16_burst']}",
+                    "avg_launch_ms": st["ms"] / st["calls"], "launches_timed": int(st["calls"]),
+                    "flops_per_launch_avg": st["flops"] / st["calls"],
+                    "share_of_backbone_time": st["ms"] / all_ms,
+                    "note": "useful FLOPs (K = 735); the tensor core executes K = 1120 (8 px x 4 ch windows), and N = 64 "
+                            "MMAs are bound by shared-memory operand bandwidth at 2/3 of the pipe's peak",
+                }
         cpu_baseline = None
         if not args.no_cpu_baseline:
             v, d = cpu_reference_run(steps=4, warmup=1, clips_per_step=2)
@@ -337,6 +353,7 @@ def main():
             "gpu_launches": int(launches["n"]),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_conv_family": family,
             "cpu_baseline": cpu_baseline,
             "tflops_whole_step": value * FLOP_PER_CLIP / 1e12,
         }

@@ -67,8 +67,11 @@ enum {
   VAD_FLAG_STEM_FOLD_W = 2, /* conv reads slot 0 in stem layout; the kw taps of one row are folded
                                into the contraction dim (window of 8 px x 4 ch, 64-byte aligned)    */
   VAD_FLAG_POOL_SAME = 4,   /* TF "SAME" padding for max-pool (MaxPool3dSamePadding); pad value 0   */
-  VAD_FLAG_FORCE_GATHER = 8 /* conv: feed the A operand with the cp.async gather producer instead
+  VAD_FLAG_FORCE_GATHER = 8,/* conv: feed the A operand with the cp.async gather producer instead
                                of TMA (debug / comparison; results are identical)                   */
+  VAD_FLAG_POOL_T2 = 16     /* stem conv (STEM_FOLD_W): max over output frames (2k, 2k+1) fused into
+                               the epilogue, i.e. the temporal half of a following MaxPool3d with
+                               kt = st = 2, pt = 0 (reference src/i3d.py:212-214); dst has To / 2    */
 };
 
 typedef struct vad_op_desc {

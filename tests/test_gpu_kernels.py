@@ -91,6 +91,43 @@ def test_stem_conv_folded_window(cuda_device, shape):
     assert_bf16_close(out, ref)
 
 
+@pytest.mark.parametrize("shape,slice_", [((1, 16, 224, 224), (0, 0)), ((2, 10, 64, 48), (0, 0)), ((1, 8, 50, 38), (64, 192))])
+def test_stem_fused_temporal_pool_is_exact(cuda_device, shape, slice_):
+    """VAD_FLAG_POOL_T2 (max over output frame pairs in the stem epilogue) == unfused stem followed by a
+    (2,1,1)/(2,1,1) max-pool, bit for bit; an odd trailing frame is dropped like MaxPool3d's floor mode."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+
+    B, T, H, W = shape
+    c_off, c_total = slice_
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 3, T, H, W, generator=g).clamp(-2, 2.44)
+    w = (torch.randn(64, 3, 5, 7, 7, generator=g) * 0.045).to(torch.bfloat16).float()
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    scale[::7] *= -1.0  # negative BN scales: the max must come after scale/shift, not before
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, scale, shift, fold_w=True)
+    xs = eng.ingest_ncthw(x.to(cuda_device), 3)
+
+    def run(fused):
+        flags = lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W | (lib.VAD_FLAG_POOL_T2 if fused else 0)
+        ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=4, cout=64, kernel=(5, 7, 7), stride=(2, 2, 2), pad=(2, 3, 3),
+                      flags=flags, w_off=w_off, scale_off=s_off, shift_off=b_off, dst_c_off=c_off, dst_c_total=c_total)]
+        plan = eng.BackbonePlan(ops, pk.blob(), 2, 3, cuda_device)
+        plan.configure(B, T, H, W)
+        plan.slot_tensor(1).fill_(-7.0)
+        plan.forward(xs)
+        torch.cuda.synchronize()
+        return plan.slot_tensor(1).float().cpu()
+
+    full, fused = run(False), run(True)
+    To = full.shape[1]
+    want = torch.maximum(full[:, 0:2 * (To // 2):2], full[:, 1:2 * (To // 2):2])
+    assert fused.shape == want.shape
+    assert torch.equal(fused, want)
+    if c_total:
+        assert (fused[..., :c_off] == -7.0).all() and (fused[..., c_off + 64:] == -7.0).all()
+
+
 @pytest.mark.parametrize("name,C,k,s,T,H,W", [("maxpool1", 64, (2, 3, 3), (2, 2, 2), 8, 30, 30),
                                               ("maxpool1 odd", 64, (2, 3, 3), (2, 2, 2), 8, 112, 112),
                                               ("maxpool2", 256, (2, 1, 1), (2, 1, 1), 4, 11, 11)])

@@ -8,4 +8,4 @@ for _ in range(2): m.forward_stem_layout(xs)
 plan = m.plan(dev); plan.profile_begin()
 for _ in range(3): m.forward_stem_layout(xs)
 prof = plan.profile_end()
-print(os.environ.get("VAD_STEM_DEBUG", "0"), "conv1 ms", round(prof[0]["ms"] / prof[0]["calls"], 3))
+print(os.environ.get("VAD_STEM_DEBUG", "0"), "conv1 ms", round(prof[0]["ms"] / prof[0]["calls"], 3), "maxpool1", round(prof[1]["ms"] / prof[1]["calls"], 3))
