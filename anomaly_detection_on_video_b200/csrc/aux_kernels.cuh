@@ -51,6 +51,9 @@ struct PreprocParams {
   int tops[10], lefts[10], flips[10];
   int clip_start, fpc;
   int out_mode, pad_left;
+  int rows_per_block;     // resized rows one block produces
+  int max_src_rows;       // source rows the vertical filter of rows_per_block consecutive rows can touch
+  int off_px, off_h, off_src;  // shared-memory byte offsets (16-byte aligned) of s_px / s_h / s_src
   void* out;
 };
 
@@ -59,26 +62,30 @@ __device__ __forceinline__ int clip8_q22(int acc) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// grid = (resized rows, frame slots); one block resamples one output row of one frame into shared
-// memory (horizontal pass rounded to u8, then vertical pass, exactly Pillow's order) and then
-// writes that row into every crop that contains it.
-//   phase 0  the ksize_v source rows the vertical filter needs are staged in shared memory with
-//            coalesced 128-bit loads (the 3-byte pixels make per-tap global loads byte-sized otherwise)
-//   phase 1  every (x, channel) of the resized row: sum_r kv[r] * clip8(sum_j kh[j] * src[r][xmin + j])
-//   phase 2  (crop, pixel-pair) work items are flattened over the block so all 256 threads store
+// grid = (ceil(resized rows / R), frame slots); one block resamples R consecutive output rows of one frame
+// (Pillow's order: horizontal pass rounded to u8, then the vertical pass) and writes them into every crop that
+// contains them.
+//   phase 0  the source rows the R vertical filters need are staged in shared memory with coalesced 128-bit loads
+//            (the 3-byte pixels make per-tap global loads byte-sized otherwise)
+//   phase 1a horizontal pass of every staged source row, once (consecutive output rows share source rows)
+//   phase 1b vertical pass -> u8 resized rows; for the stem layout also the standardised bf16 pixel (r, g, b, 0)
+//            through the 256-entry LUT, so the ten crops below are plain 8-byte copies
+//   phase 2  crops: two crops at a time, 128 threads each, one 16-byte store (two pixels) per work item
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) {
   extern __shared__ __align__(16) uint8_t s_mem[];
+  const int R = p.rows_per_block;
   const int row_bytes = (p.rw * 3 + 15) & ~15;
   const int src_row_bytes = p.W * 3;
   const int src_pitch = (src_row_bytes + 15) & ~15;
-  uint8_t* s_row = s_mem;                                         // resized row, rw*3 bytes
-  float* lut_f = reinterpret_cast<float*>(s_mem + row_bytes);     // 256 fp32
-  __nv_bfloat16* lut_h = reinterpret_cast<__nv_bfloat16*>(lut_f + 256);
-  uint8_t* s_src = reinterpret_cast<uint8_t*>(lut_h + 256);       // ksize_v source rows, pitch src_pitch
-  __shared__ int s_active[10];
-  __shared__ int s_nactive;
+  float* lut_f = reinterpret_cast<float*>(s_mem);                          // 256 fp32
+  __nv_bfloat16* lut_h = reinterpret_cast<__nv_bfloat16*>(lut_f + 256);    // 256 bf16
+  uint8_t* s_row = reinterpret_cast<uint8_t*>(lut_h + 256);                // R resized rows, u8, pitch row_bytes
+  uint2* s_px = reinterpret_cast<uint2*>(s_mem + p.off_px);                // R x rw standardised bf16 pixels (stem mode)
+  uint8_t* s_h = s_mem + p.off_h;                                          // horizontally resampled source rows
+  uint8_t* s_src = s_mem + p.off_src;                                      // staged source rows, pitch src_pitch
 
-  const int y = blockIdx.x;
+  const int y0 = blockIdx.x * R;
+  const int ny = (p.rh - y0) < R ? (p.rh - y0) : R;
   const int slot = blockIdx.y;
   const int clip_local = slot / p.fpc;
   const int t = slot - clip_local * p.fpc;
@@ -94,29 +101,20 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) 
     lut_f[threadIdx.x] = v;
     lut_h[threadIdx.x] = __float2bfloat16_rn(v);
   }
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int k = 0; k < p.ncrops; ++k) {
-      const int yo = y - p.tops[k];
-      if (yo >= 0 && yo < p.crop) s_active[n++] = k;
-    }
-    s_nactive = n;
-  }
 
-  const int ymin = p.bounds_v[2 * y];
-  const int ycnt = p.bounds_v[2 * y + 1];
-  const int* kv = p.coef_v + y * p.ksize_v;
+  const int ymin0 = p.bounds_v[2 * y0];
+  const int nsrc = p.bounds_v[2 * (y0 + ny - 1)] + p.bounds_v[2 * (y0 + ny - 1) + 1] - ymin0;
   {
-    const uint8_t* g0 = frame + (long long)ymin * src_row_bytes;
+    const uint8_t* g0 = frame + (long long)ymin0 * src_row_bytes;
     const bool vec = ((src_row_bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(g0) & 15) == 0);
     if (vec) {
       const int per_row = src_row_bytes >> 4;
-      for (int i = threadIdx.x; i < ycnt * per_row; i += blockDim.x) {
+      for (int i = threadIdx.x; i < nsrc * per_row; i += blockDim.x) {
         const int r = i / per_row, c = i - r * per_row;
         reinterpret_cast<uint4*>(s_src + r * src_pitch)[c] = reinterpret_cast<const uint4*>(g0 + (long long)r * src_row_bytes)[c];
       }
     } else {
-      for (int i = threadIdx.x; i < ycnt * src_row_bytes; i += blockDim.x) {
+      for (int i = threadIdx.x; i < nsrc * src_row_bytes; i += blockDim.x) {
         const int r = i / src_row_bytes, c = i - r * src_row_bytes;
         s_src[r * src_pitch + c] = g0[(long long)r * src_row_bytes + c];
       }
@@ -124,71 +122,103 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) 
   }
   __syncthreads();
 
-  for (int i = threadIdx.x; i < p.rw * 3; i += blockDim.x) {
-    const int x = i / 3;
-    const int c = i - x * 3;
+  // phase 1a: one work item = one pixel (3 channels) of one staged source row
+  for (int i = threadIdx.x; i < nsrc * p.rw; i += blockDim.x) {
+    const int r = i / p.rw;
+    const int x = i - r * p.rw;
     const int xmin = p.bounds_h[2 * x];
     const int xcnt = p.bounds_h[2 * x + 1];
     const int* kh = p.coef_h + x * p.ksize_h;
-    int acc_v = 1 << 21;
-    for (int r = 0; r < ycnt; ++r) {
-      const uint8_t* src = s_src + r * src_pitch + xmin * 3 + c;
-      int acc_h = 1 << 21;
-      for (int j = 0; j < xcnt; ++j) acc_h += (int)src[j * 3] * kh[j];
-      acc_v += clip8_q22(acc_h) * kv[r];
+    const uint8_t* src = s_src + r * src_pitch + xmin * 3;
+    int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+    for (int j = 0; j < xcnt; ++j) {
+      const int k = kh[j];
+      a0 += (int)src[3 * j] * k;
+      a1 += (int)src[3 * j + 1] * k;
+      a2 += (int)src[3 * j + 2] * k;
     }
-    s_row[i] = (uint8_t)clip8_q22(acc_v);
+    uint8_t* dst = s_h + r * row_bytes + x * 3;
+    dst[0] = (uint8_t)clip8_q22(a0);
+    dst[1] = (uint8_t)clip8_q22(a1);
+    dst[2] = (uint8_t)clip8_q22(a2);
+  }
+  __syncthreads();
+
+  // phase 1b: one work item = one pixel of one output row
+  const bool stem = p.out_mode == 1;
+  for (int i = threadIdx.x; i < ny * p.rw; i += blockDim.x) {
+    const int yy = i / p.rw;
+    const int x = i - yy * p.rw;
+    const int y = y0 + yy;
+    const int r0 = p.bounds_v[2 * y] - ymin0;
+    const int ycnt = p.bounds_v[2 * y + 1];
+    const int* kv = p.coef_v + y * p.ksize_v;
+    const uint8_t* src = s_h + r0 * row_bytes + x * 3;
+    int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+    for (int r = 0; r < ycnt; ++r) {
+      const int k = kv[r];
+      a0 += (int)src[r * row_bytes] * k;
+      a1 += (int)src[r * row_bytes + 1] * k;
+      a2 += (int)src[r * row_bytes + 2] * k;
+    }
+    const int v0 = clip8_q22(a0), v1 = clip8_q22(a1), v2 = clip8_q22(a2);
+    if (stem) {
+      const uint32_t cr = __bfloat16_as_ushort(lut_h[v0]);
+      const uint32_t cg = __bfloat16_as_ushort(lut_h[v1]);
+      const uint32_t cb = __bfloat16_as_ushort(lut_h[v2]);
+      s_px[yy * p.rw + x] = make_uint2(cr | (cg << 16), cb);
+    } else {
+      uint8_t* dst = s_row + yy * row_bytes + x * 3;
+      dst[0] = (uint8_t)v0; dst[1] = (uint8_t)v1; dst[2] = (uint8_t)v2;
+    }
   }
   __syncthreads();
 
   const int crop = p.crop;
-  const int nact = s_nactive;
-  if (p.out_mode == 1) {
+  if (stem) {
     // stem layout [clipcrop, t, crop, crop + 8, 4] bf16 ; one work item = two pixels (16 B)
     const int Wp = crop + 8;
     const int per_crop = Wp / 2;
-    for (int idx = threadIdx.x; idx < nact * per_crop; idx += blockDim.x) {
-      const int a = idx / per_crop;
-      const int i = idx - a * per_crop;
-      const int k = s_active[a];
-      const int yo = y - p.tops[k];
-      const int left = p.lefts[k];
-      const int flip = p.flips[k];
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                            ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * crop + yo) *
-                                                Wp * 4);
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int xo = 2 * i + h - p.pad_left;
-        if (xo >= 0 && xo < crop) {
-          const int xs = flip ? left + crop - 1 - xo : left + xo;
-          const uint8_t* px = s_row + xs * 3;
-          const uint32_t r = __bfloat16_as_ushort(lut_h[px[0]]);
-          const uint32_t g = __bfloat16_as_ushort(lut_h[px[1]]);
-          const uint32_t b = __bfloat16_as_ushort(lut_h[px[2]]);
-          w[2 * h] = r | (g << 16);
-          w[2 * h + 1] = b;
+    const int half = threadIdx.x >> 7;   // two crops in flight
+    const int i0 = threadIdx.x & 127;
+    for (int yy = 0; yy < ny; ++yy) {
+      const int y = y0 + yy;
+      const uint2* row = s_px + yy * p.rw;
+      for (int k = half; k < p.ncrops; k += 2) {
+        const int yo = y - p.tops[k];
+        if (yo < 0 || yo >= crop) continue;
+        const int left = p.lefts[k];
+        const int flip = p.flips[k];
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                              ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * crop + yo) * Wp * 4);
+        for (int i = i0; i < per_crop; i += 128) {
+          const int xa = 2 * i - p.pad_left, xb = xa + 1;
+          uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+          if (xa >= 0 && xa < crop) a = row[flip ? left + crop - 1 - xa : left + xa];
+          if (xb >= 0 && xb < crop) b = row[flip ? left + crop - 1 - xb : left + xb];
+          dst[i] = make_uint4(a.x, a.y, b.x, b.y);
         }
       }
-      dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
   } else {
     // dataset layout [clip, crop_idx, t, 3, crop, crop] fp32
-    const int per_crop = 3 * crop;
-    for (int idx = threadIdx.x; idx < nact * per_crop; idx += blockDim.x) {
-      const int a = idx / per_crop;
-      const int i = idx - a * per_crop;
-      const int k = s_active[a];
-      const int yo = y - p.tops[k];
-      const int left = p.lefts[k];
-      const int flip = p.flips[k];
-      const int c = i / crop;
-      const int xo = i - c * crop;
-      const int xs = flip ? left + crop - 1 - xo : left + xo;
-      float* dst = reinterpret_cast<float*>(p.out) +
-                   ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * 3) * crop * crop + (long long)yo * crop;
-      dst[(long long)c * crop * crop + xo] = lut_f[s_row[xs * 3 + c]];
+    for (int yy = 0; yy < ny; ++yy) {
+      const int y = y0 + yy;
+      const uint8_t* row = s_row + yy * row_bytes;
+      for (int k = 0; k < p.ncrops; ++k) {
+        const int yo = y - p.tops[k];
+        if (yo < 0 || yo >= crop) continue;
+        const int left = p.lefts[k];
+        const int flip = p.flips[k];
+        float* dst = reinterpret_cast<float*>(p.out) +
+                     ((((long long)clip_local * p.ncrops + k) * p.fpc + t) * 3) * crop * crop + (long long)yo * crop;
+        for (int i = threadIdx.x; i < 3 * crop; i += blockDim.x) {
+          const int c = i / crop;
+          const int xo = i - c * crop;
+          const int xs = flip ? left + crop - 1 - xo : left + xo;
+          dst[(long long)c * crop * crop + xo] = lut_f[row[xs * 3 + c]];
+        }
+      }
     }
   }
 }

@@ -749,6 +749,7 @@ struct vad_preproc {
   int tops[10] = {0}, lefts[10] = {0}, flips[10] = {0};
   int* tables_dev = nullptr;  // bounds_h | coef_h | bounds_v | coef_v
   size_t off_bh = 0, off_ch = 0, off_bv = 0, off_cv = 0;
+  std::vector<int> bounds_v_host;  // (ymin, count) per resized row: sizes the kernel's source-row staging
 };
 
 // Pillow's precompute_coeffs + normalize_coeffs_8bpc for the BILINEAR filter (support 1.0):
@@ -815,6 +816,7 @@ extern "C" int32_t vad_preproc_create(vad_preproc_t** out, int32_t src_h, int32_
   std::vector<int> bh, ch, bv, cv;
   resample_tables(src_w, pp->rw, bh, ch, pp->ksize_h);
   resample_tables(src_h, pp->rh, bv, cv, pp->ksize_v);
+  pp->bounds_v_host = bv;
   std::vector<int> all;
   pp->off_bh = 0;               all.insert(all.end(), bh.begin(), bh.end());
   pp->off_ch = all.size();      all.insert(all.end(), ch.begin(), ch.end());
@@ -863,12 +865,35 @@ extern "C" int32_t vad_preproc_run(vad_preproc_t* pp, const uint8_t* frames_dev,
   q.crop = pp->crop; q.ncrops = pp->ncrops;
   for (int k = 0; k < 10; ++k) { q.tops[k] = pp->tops[k]; q.lefts[k] = pp->lefts[k]; q.flips[k] = pp->flips[k]; }
   q.clip_start = clip_start; q.fpc = frames_per_clip; q.out_mode = out_mode; q.pad_left = pad_left; q.out = out_dev;
-  // resized row + fp32/bf16 LUTs + the ksize_v staged source rows
-  const size_t smem = ((size_t)pp->rw * 3 + 15) / 16 * 16 + 256 * 4 + 256 * 2 +
-                      (size_t)pp->ksize_v * (((size_t)pp->src_w * 3 + 15) / 16 * 16);
+  // shared memory: LUTs | R resized u8 rows | R rows of bf16 pixels (stem mode) | horizontally resampled source rows |
+  // staged source rows.  R (resized rows per block) is the largest of 8, 4, 2, 1 that fits.
+  const size_t row_bytes = ((size_t)pp->rw * 3 + 15) / 16 * 16;
+  const size_t src_pitch = ((size_t)pp->src_w * 3 + 15) / 16 * 16;
+  size_t smem = 0;
+  int R = 8;
+  for (;; R >>= 1) {
+    int max_src = 0;
+    for (int y0 = 0; y0 < pp->rh; y0 += R) {
+      const int y1 = (y0 + R < pp->rh ? y0 + R : pp->rh) - 1;
+      const int n = pp->bounds_v_host[2 * y1] + pp->bounds_v_host[2 * y1 + 1] - pp->bounds_v_host[2 * y0];
+      if (n > max_src) max_src = n;
+    }
+    size_t off = 256 * 4 + 256 * 2 + (size_t)R * row_bytes;
+    q.off_px = (int)off;
+    if (out_mode == VAD_OUT_STEM_BF16) off += (size_t)R * pp->rw * 8;
+    off = (off + 15) / 16 * 16;
+    q.off_h = (int)off;
+    off += (size_t)max_src * row_bytes;
+    q.off_src = (int)off;
+    off += (size_t)max_src * src_pitch;
+    smem = off;
+    q.rows_per_block = R;
+    q.max_src_rows = max_src;
+    if (smem <= 96 * 1024 || R == 1) break;
+  }
   if (smem > 200 * 1024) return fail(VAD_ERR_INVALID_ARGUMENT, "source frames too wide for the resampling kernel (%zu B of shared memory)", smem);
   if (smem > 48 * 1024) VAD_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(pp->rh, n_clips * frames_per_clip);
+  dim3 grid((pp->rh + R - 1) / R, n_clips * frames_per_clip);
   preprocess_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(q);
   VAD_CUDA_CHECK(cudaGetLastError());
   return VAD_OK;
