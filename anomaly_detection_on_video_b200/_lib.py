@@ -38,6 +38,14 @@ EXPORTED_SYMBOLS = (
     "vad_preproc_destroy",
     "vad_segment_mean",
     "vad_add_magnitude",
+    "vad_head_create",
+    "vad_head_workspace_bytes",
+    "vad_head_forward",
+    "vad_head_select",
+    "vad_head_loss",
+    "vad_head_num_launches",
+    "vad_head_flops",
+    "vad_head_destroy",
 )
 
 
@@ -68,6 +76,26 @@ class OpDesc(ctypes.Structure):
         ("shift_off", c_uint64),
     ]
 
+
+class HeadConfig(ctypes.Structure):
+    """Mirror of ``vad_head_config``."""
+
+    _fields_ = [
+        ("channels", c_int32),
+        ("n_stages", c_int32),
+        ("dims", c_int32 * 4),
+        ("depths", c_int32 * 4),
+        ("types", c_int32 * 4),
+        ("dim_head", c_int32),
+        ("ff_repe", c_int32),
+        ("local_aggr_kernel", c_int32),
+        ("k", c_int32),
+        ("mag_ratio", c_float),
+        ("ln_eps", c_float),
+    ]
+
+
+VAD_HEAD_GLANCE, VAD_HEAD_FOCUS = 0, 1
 
 _lib = None
 
@@ -118,6 +146,25 @@ def load() -> ctypes.CDLL:
     lib.vad_segment_mean.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.vad_add_magnitude.restype = c_int32
     lib.vad_add_magnitude.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    lib.vad_head_create.restype = c_int32
+    lib.vad_head_create.argtypes = [POINTER(c_void_p), POINTER(HeadConfig), c_void_p, c_uint64, c_int32]
+    lib.vad_head_workspace_bytes.restype = c_int32
+    lib.vad_head_workspace_bytes.argtypes = [c_void_p, c_int32, c_int32, POINTER(c_uint64)]
+    lib.vad_head_forward.restype = c_int32
+    lib.vad_head_forward.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_uint64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]
+    lib.vad_head_select.restype = c_int32
+    lib.vad_head_select.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.vad_head_loss.restype = c_int32
+    lib.vad_head_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                  c_void_p, c_void_p, c_void_p]
+    lib.vad_head_num_launches.restype = c_int32
+    lib.vad_head_num_launches.argtypes = [c_void_p]
+    lib.vad_head_flops.restype = c_double
+    lib.vad_head_flops.argtypes = [c_void_p, c_int32, c_int32]
+    lib.vad_head_destroy.restype = None
+    lib.vad_head_destroy.argtypes = [c_void_p]
     if lib.vad_abi_version() != 1:
         raise RuntimeError(f"{LIB_PATH}: ABI version {lib.vad_abi_version()} != 1; rebuild the library")
     _lib = lib
@@ -131,6 +178,6 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"libvad_b200 {what} failed (status {rc}): {msg}")
 
 
-__all__ = ["OpDesc", "load", "check", "LIB_PATH", "EXPORTED_SYMBOLS"]
+__all__ = ["OpDesc", "HeadConfig", "load", "check", "LIB_PATH", "EXPORTED_SYMBOLS"]
 # keep the ctypes scalar types importable from here for the thin wrappers
 _ = (c_float, c_uint8)

@@ -924,3 +924,6 @@ extern "C" int32_t vad_add_magnitude(const float* feats_dev, int64_t rows, int32
   VAD_CUDA_CHECK(cudaGetLastError());
   return VAD_OK;
 }
+
+// ------------------------------------------------------------------------------------ MGFN scoring head
+#include "head_api.cuh"

@@ -185,6 +185,71 @@ int32_t vad_segment_mean(const float* feats_dev, int32_t n_clips, int32_t ncrops
  * L2 norm of each row appended. */
 int32_t vad_add_magnitude(const float* feats_dev, int64_t rows, int32_t c, float* out_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MGFN scoring head.  Replaces MGFNForVideoAnomalyDetection.forward in eval mode
+ * (src/models/mgfn/modeling_mgfn.py:36-427: feature amplifier, Glance / Focus blocks, final LayerNorm +
+ * fc + sigmoid, magnitude selection and score prediction) and the losses of src/loss/base.py:7-48 and
+ * src/loss/mgfn.py:7-47.  fp32 activations; every Conv1d is a tcgen05 kind::tf32 GEMM.  Training
+ * (backward, dropout on the selection mask, the optimizer step of src/runner.py:29-59) is not built.
+ * ---------------------------------------------------------------------------------------------- */
+enum { VAD_HEAD_GLANCE = 0, VAD_HEAD_FOCUS = 1 };
+
+typedef struct vad_head_config {
+  int32_t channels;          /* feature width without the magnitude column (2048)                  */
+  int32_t n_stages;          /* <= 4                                                               */
+  int32_t dims[4];           /* stage widths (64, 128, 1024); multiples of 64                      */
+  int32_t depths[4];         /* blocks per stage (3, 3, 2)                                         */
+  int32_t types[4];          /* VAD_HEAD_GLANCE / VAD_HEAD_FOCUS per stage                         */
+  int32_t dim_head;          /* 64 (the attention kernel is specialised for it)                    */
+  int32_t ff_repe;           /* FFN expansion (4)                                                  */
+  int32_t local_aggr_kernel; /* Focus relation kernel (5)                                          */
+  int32_t k;                 /* top-k snippets (3)                                                 */
+  float mag_ratio;           /* 0.1                                                                */
+  float ln_eps;              /* 1e-5 for MGFNLayerNorm and nn.LayerNorm                            */
+} vad_head_config;
+
+typedef struct vad_head vad_head_t;
+
+/* params_dev: fp32 blob, tensors in module order, each starting on a 64-float boundary:
+ *   amplifier   to_tokens W[d0][3][channels] (tap-major contraction), b[d0]; to_mag w[d0][3], b[d0]
+ *   per block   scc W[d][3][d], b[d]
+ *     glance    norm g[d], b[d]; to_qkv W[3*inner][d]; to_out W[d][inner], b[d]
+ *     focus     to_v W[inner][d], b[inner] (BatchNorm1d folded in); rel_pos w[heads][k], b[heads];
+ *               to_out W[d][inner], b[d]
+ *     ffn       layer_norm g[d], b[d]; in_conv W[r*d][d], b[r*d]; out_conv W[d][r*d], b[d]
+ *   after every stage but the last: layer_norm g[d], b[d]; conv W[d_next][d], b[d_next]
+ *   final       layer_norm w[d], b[d]; fc w[d], b[1]
+ * vad_head_create fails unless params_bytes equals the size this layout implies. */
+int32_t vad_head_create(vad_head_t** head, const vad_head_config* cfg, const float* params_dev,
+                        uint64_t params_bytes, int32_t device);
+/* workspace for n_seq = videos * ncrops sequences of t snippets */
+int32_t vad_head_workspace_bytes(const vad_head_t* head, int32_t n_seq, int32_t t, uint64_t* bytes);
+/* video_dev [n_videos, ncrops, t, channels + 1] fp32 ->
+ *   xln_dev   [n_videos * ncrops, t, d_last]  layer-normed snippet features
+ *   score_dev [n_videos * ncrops, t]          per-crop snippet scores (sigmoid)
+ *   fmag_dev  [n_videos * ncrops, t]          L2 norms of xln                                      */
+int32_t vad_head_forward(vad_head_t* head, const float* video_dev, int32_t n_videos, int32_t ncrops,
+                         int32_t t, void* workspace_dev, uint64_t workspace_bytes, float* xln_dev,
+                         float* score_dev, float* fmag_dev, void* stream);
+/* magnitude selection + score prediction (eval: no dropout on the mask) for videos
+ * [video_off, video_off + n_sel) of an n_videos batch:
+ *   scores_dev [n_videos, t] crop-mean snippet scores (rows of the selected videos are written)
+ *   vid_score_dev [n_videos], idx_dev [n_videos, k]
+ *   sel_dev [ncrops, n_sel, k, d_last] gathered features, crop-major like the reference's torch.cat loop */
+int32_t vad_head_select(const vad_head_t* head, const float* xln_dev, const float* score_dev,
+                        const float* fmag_dev, int32_t n_videos, int32_t ncrops, int32_t t,
+                        int32_t video_off, int32_t n_sel, float* scores_dev, float* vid_score_dev,
+                        int32_t* idx_dev, float* sel_dev, void* stream);
+/* loss = MGFNLoss + TemporalSmoothnessLoss + SparsityLoss for a batch whose first n_half videos are normal and
+ * last n_half abnormal.  labels_dev [2 * n_half] (normal labels then abnormal labels); scratch_dev holds
+ * 2 * ncrops * n_half * k floats; out_dev[7] = {total, smooth, sparsity, bce, con, con_n, con_a}. */
+int32_t vad_head_loss(const vad_head_t* head, const float* scores_dev, const float* vid_score_dev,
+                      const float* labels_dev, const float* sel_normal_dev, const float* sel_abnormal_dev,
+                      int32_t n_half, int32_t ncrops, int32_t t, float* scratch_dev, float* out_dev, void* stream);
+int32_t vad_head_num_launches(const vad_head_t* head);
+double vad_head_flops(const vad_head_t* head, int32_t n_seq, int32_t t);
+void vad_head_destroy(vad_head_t* head);
+
 #ifdef __cplusplus
 }
 #endif

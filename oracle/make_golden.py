@@ -10,6 +10,10 @@ The reference ships no tests, fixtures or golden vectors, so these files are the
   segment.npz            segment() (extract_features.py:159-185) for several clip counts
   extract.npz            extract() (extract_features.py:55-156) driven end to end with a fake decoder
                          and a cheap deterministic model: file names, shapes, stacking, chunk cache
+  mgfn.npz               MGFNForVideoAnomalyDetection.forward in eval mode (modeling_mgfn.py:376-427) with
+                         oracle.mgfn.seeded_state_dict(0): a split training-shaped batch with labels (scores,
+                         selection, every loss term) and an unsplit validation-shaped video (T = 47)
+                         (`python -m oracle.make_golden mgfn` regenerates only this file)
 """
 from __future__ import annotations
 
@@ -24,6 +28,7 @@ from PIL import Image
 
 from . import _refload
 from . import i3res50 as O
+from . import mgfn as MG
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -60,9 +65,50 @@ class FakeModel(torch.nn.Module):
         return (q @ self.proj.t()).reshape(b, -1, 1, 1, 1)
 
 
+def golden_mgfn(ref) -> None:
+    """P5: the scoring head in eval() mode (dropout on the selection mask inactive -> deterministic)."""
+    import importlib
+
+    modeling = importlib.import_module("src.models.mgfn.modeling_mgfn")
+    configuration = importlib.import_module("src.models.mgfn.configuration_mgfn")
+    sd = MG.seeded_state_dict(0)
+    model = modeling.MGFNForVideoAnomalyDetection(configuration.MGFNConfig())
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    out = {"weights_sum": np.array(sum(float(v.double().sum()) for v in sd.values()))}
+
+    def record(tag, r, video):
+        out[f"{tag}/video_sha"] = np.array(sha(video.numpy()))
+        out[f"{tag}/scores"] = r.scores.numpy()
+        out[f"{tag}/abnormal_scores"] = r.abnormal_scores.numpy()
+        out[f"{tag}/normal_scores"] = r.normal_scores.numpy()
+        out[f"{tag}/a_feat_l1"] = r.a_feat_magnitude.norm(p=1, dim=2).numpy()
+        out[f"{tag}/n_feat_l1"] = r.n_feat_magnitude.norm(p=1, dim=2).numpy()
+        out[f"{tag}/a_feat_sample"] = r.a_feat_magnitude[:, :, ::16].numpy()
+        out[f"{tag}/n_feat_sample"] = r.n_feat_magnitude[:, :, ::16].numpy()
+
+    video = MG.synthetic_video(1, 4, 10, 32)
+    model.force_split = True
+    with torch.no_grad():
+        r = model(video, abnormal_labels=torch.ones(2), normal_labels=torch.zeros(2))
+    record("split", r, video)
+    out["split/loss"] = r.loss.numpy()
+    video = MG.synthetic_video(2, 1, 10, 47)
+    model.force_split = False
+    with torch.no_grad():
+        r = model(video)
+    record("valid", r, video)
+    np.savez_compressed(os.path.join(GOLDEN, "mgfn.npz"), **out)
+
+
 def main() -> None:
     ref = _refload.load()
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "mgfn":
+        golden_mgfn(ref)
+        print("mgfn.npz", os.path.getsize(os.path.join(GOLDEN, "mgfn.npz")))
+        return
+    golden_mgfn(ref)
 
     # ---------------------------------------------------------------- P1 preprocessing
     frames = synth_frames(0, 5, 60, 80)
