@@ -96,6 +96,8 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
+  bool stem_mf = false;  // multi-frame (input-frame stationary) stem kernel
+  int stem_ti = 0, stem_ti_max = 0;
   int a_mode = 0;
   int avg_P = 0, avg_C = 0;
   // for tensor-map encoding
@@ -112,6 +114,7 @@ struct vad_plan {
   int in_channels = 0;
   int device = 0;
   int sm_count = 148;
+  bool stem_v3 = false;      // VAD_STEM_V3=1: one-output-frame-per-tile stem kernel instead of the multi-frame one
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool epi_all = false;      // VAD_EPI_ALL=1: staged TMA-store epilogue for every layer (tuning only)
@@ -197,6 +200,7 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   if (p->sm_count <= 0) p->sm_count = 148;
   const char* sg = getenv("VAD_STEM_GATHER");
   p->stem_gather = sg && sg[0] == '1';
+  { const char* k = getenv("VAD_STEM_V3"); p->stem_v3 = k && k[0] == '1'; }
   const char* sgen = getenv("VAD_STEM_GENERIC");
   p->stem_generic = sgen && sgen[0] == '1';
   { const char* k = getenv("VAD_KPS"); p->kps_override = k ? atoi(k) : 0; }
@@ -301,22 +305,31 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0) {
         StemParams& q = r.sp;
         memset(&q, 0, sizeof(q));
+        q.clk_out = nullptr;
         q.B = batch; q.To = To; q.Ho = Ho; q.Wo = Wo;
         q.pool_t = pool_t2 ? 2 : 1;
         q.To_out = To / q.pool_t;
         q.kt = d.kt; q.kh = d.kh; q.st = d.st; q.pt = d.pt; q.ph = d.ph;
         const int th = 16, tw = 8;  // output tile: 8 (w) x 16 (h)
         q.tiles_w = (Wo + tw - 1) / tw; q.tiles_h = (Ho + th - 1) / th;
-        const long long nu = (long long)batch * q.To_out * q.tiles_h * q.tiles_w;
+        long long nu = (long long)batch * q.To_out * q.tiles_h * q.tiles_w;
         q.rows_even = th + (d.kh + 1) / 2 - 1;
         q.rows_odd = th + d.kh / 2 - 1;
         q.seg_bytes = ((tw - 1) * d.sw * 4 + 32) * 2;  // bytes per raw input-row segment in smem (176)
         q.off_odd = (int)align_up((uint64_t)q.rows_even * q.seg_bytes, 128);
         q.stage_bytes = (int)align_up((uint64_t)q.off_odd + (uint64_t)q.rows_odd * q.seg_bytes, 128);
         const int w_bytes = d.kt * d.kh * kStemTapBytes;
-        const int fixed = w_bytes + 2 * kStemStagingBytes + 2 * 64 * 4 + (2 * kStemMaxStages + 5) * 8 + 16 + 1024;
+        const int fixed = w_bytes + 2 * kStemStagingBytes + 2 * 64 * 4 + (2 * kStemMaxStages + 17) * 8 + 16 + 32 * 32 + 1024;
         int ns = (227 * 1024 - fixed) / q.stage_bytes;
         if (ns > kStemMaxStages) ns = kStemMaxStages;
+        // multi-frame variant: all output frames of a spatial tile live in TMEM (8 x 64 columns), input frames are
+        // walked once; needs the I3D temporal geometry (kt 5, stride 2, pad 2) and at most 8 output frames
+        r.stem_mf = !p->stem_v3 && d.kt == 5 && d.st == 2 && d.pt == 2 && To <= 8 && To >= 1 && d.kh <= 7;
+        if (r.stem_mf) {
+          nu = (long long)batch * q.tiles_h * q.tiles_w;
+          r.stem_ti = src.T;
+          r.stem_ti_max = src.T - 1 < 2 * (To - 1) + 2 ? src.T - 1 : 2 * (To - 1) + 2;
+        }
         if (ns >= 2 && nu > 0 && nu <= 0x7fffffffLL && d.kh > 1) {
           q.n_stages = ns;
           q.num_units = (int)nu;
@@ -653,7 +666,32 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
           e = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
           stem_attr = (e == cudaSuccess);
         }
-        if (e == cudaSuccess) {
+        if (e == cudaSuccess && r.stem_mf) {
+          static bool mf_attr = false;
+          if (!mf_attr) {
+            e = cudaFuncSetAttribute(stem_umma_mf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            mf_attr = (e == cudaSuccess);
+          }
+          if (e == cudaSuccess) {
+            StemMfParams mp;
+            mp.s = r.sp;
+            static long long* clk_dev = nullptr;
+            static const bool want_clk = getenv("VAD_STEM_CLOCKS") != nullptr;
+            if (want_clk && !clk_dev) cudaMalloc(&clk_dev, 32);
+            mp.s.clk_out = want_clk ? clk_dev : nullptr;
+            mp.Ti = r.stem_ti;
+            mp.ti_max = r.stem_ti_max;
+            stem_umma_mf_kernel<<<r.grid, kStemMfThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, mp);
+            e = cudaGetLastError();
+            if (want_clk && e == cudaSuccess) {  // debug only: synchronises
+              long long hclk[3] = {0, 0, 0};
+              cudaStreamSynchronize(st);
+              cudaMemcpy(hclk, clk_dev, 24, cudaMemcpyDeviceToHost);
+              fprintf(stderr, "stem mf: CTA 0 MMA thread %lld cycles in %lld ns = %.0f MHz, %lld units, %.0f cycles/unit\n", hclk[0], hclk[1],
+                      hclk[1] ? 1e3 * (double)hclk[0] / (double)hclk[1] : 0.0, hclk[2], hclk[2] ? (double)hclk[0] / (double)hclk[2] : 0.0);
+            }
+          }
+        } else if (e == cudaSuccess) {
           stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, r.sp);
           e = cudaGetLastError();
         }

@@ -418,6 +418,68 @@ void run_swp() {
   cudaFree(d);
 }
 
+
+// Stem-like operands: A through the SWIZZLE_NONE descriptor (LBO 16 B, SBO 176 B), B with BROW-byte swizzled rows,
+// N in {64, 128, 192}; PER_COMMIT MMAs per group, no waits in the loop (pure issue/execute rate).
+template <int N, int PER_COMMIT, int BROW, bool ANOSW>
+__global__ void __launch_bounds__(128, 1) bench_stemlike_kernel(int groups, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (threadIdx.x < 32) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(N);
+      const uint64_t hiB = umma_desc_kmajor<BROW>(0);
+      const uint64_t hiA = ANOSW ? umma_desc_kmajor_noswizzle(0, 16u, 176u) : umma_desc_kmajor<64>(0);
+      const uint32_t a0 = smem_u32(smem) >> 4;
+      const uint32_t b0 = (smem_u32(smem) + 65536) >> 4;
+      long long t0 = clock64();
+      for (int g = 0; g < groups; ++g) {
+#pragma unroll
+        for (int j = 0; j < PER_COMMIT; ++j) {
+          const uint32_t aoff = ANOSW ? (uint32_t)(((j >> 1) & 3) * 176 + ((j >> 1) & 4 ? 3456 : 0)) >> 4 : (uint32_t)((j >> 1) * 1024) >> 4;
+          const uint32_t boff = (uint32_t)((j >> 1) * (N * BROW)) >> 4;
+          umma_f16_c<true>(tmem, hiA | (a0 + aoff + 2 * (j & 1)), hiB | (b0 + (boff & 4095) + 2 * (j & 1)), idesc);
+        }
+      }
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      long long t1 = clock64();
+      if (blockIdx.x == 0) *out_cycles = t1 - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int N, int PC, int BROW, bool ANOSW>
+void run_stemlike() {
+  long long* d;
+  cudaMalloc(&d, 8);
+  const int groups = 2000;
+  cudaFuncSetAttribute(bench_stemlike_kernel<N, PC, BROW, ANOSW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
+  bench_stemlike_kernel<N, PC, BROW, ANOSW><<<148, 128, 164 * 1024>>>(16, d);
+  bench_stemlike_kernel<N, PC, BROW, ANOSW><<<148, 128, 164 * 1024>>>(groups, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long c = 0;
+  cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+  printf("stemlike N=%3d B rows %3d B, A %s : %7.1f cycles/MMA (%s)\n", N, BROW, ANOSW ? "noswizzle(16,176)" : "SW64", (double)c / ((double)groups * PC),
+         cudaGetErrorString(e));
+  cudaFree(d);
+}
+
 template <int N>
 void run_ring(int per_commit, int lag, int extra_polls, int flags = 0) {
   long long* d;
@@ -452,6 +514,8 @@ void run(const char* name, int per_commit, int a_step) {
 
 int main() {
   setvbuf(stdout, nullptr, _IONBF, 0);
+  run_stemlike<64,14,64,true>(); run_stemlike<128,14,64,true>(); run_stemlike<192,14,64,true>(); run_stemlike<64,14,128,true>(); run_stemlike<128,14,128,true>(); run_stemlike<192,14,128,true>(); run_stemlike<128,14,64,false>(); run_stemlike<192,14,64,false>(); run_stemlike<256,14,64,true>();
+  return 0;
   run_swp<64,4,4,1>(); run_swp<64,4,4,2>(); run_swp<64,4,4,3>(); run_swp<64,4,4,4>(); run_swp<64,8,4,2>(); run_swp<64,8,4,4>(); run_swp<64,8,4,6>(); run_swp<128,4,4,1>(); run_swp<128,4,4,2>(); run_swp<128,4,4,3>(); run_swp<128,8,4,4>(); run_swp<256,4,4,2>(); run_swp<64,14,4,7>(); run_swp<64,2,4,1>();
   run_pipe<64,4,4>(); run_pipe<64,4,8>(); run_pipe<64,2,8>(); run_pipe<64,8,4>(); run_pipe<64,14,4>(); run_pipe<128,4,4>(); run_pipe<128,4,8>(); run_pipe<128,8,4>(); run_pipe<256,4,4>(); run_pipe<256,2,4>(); run_pipe<64,4,2>(); run_pipe<64,4,3>();
   return 0;
