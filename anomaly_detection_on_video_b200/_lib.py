@@ -15,7 +15,7 @@ LIB_NAME = "libvad_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 VAD_OP_CONV, VAD_OP_MAXPOOL, VAD_OP_AVGPOOL = 0, 1, 2
-VAD_FLAG_RELU, VAD_FLAG_STEM_FOLD_W, VAD_FLAG_POOL_SAME, VAD_FLAG_FORCE_GATHER, VAD_FLAG_POOL_T2 = 1, 2, 4, 8, 16
+VAD_FLAG_RELU, VAD_FLAG_STEM_FOLD_W, VAD_FLAG_POOL_SAME, VAD_FLAG_FORCE_GATHER, VAD_FLAG_POOL_T2, VAD_FLAG_CONV_SAME = 1, 2, 4, 8, 16, 32
 VAD_OUT_DATASET_F32, VAD_OUT_STEM_BF16 = 0, 1
 
 # every symbol include/vad_b200.h declares (tests check the .so exports exactly these)

@@ -88,6 +88,8 @@ struct OpRuntime {
   bool epi = false;   // residual prefetched / output stored by TMA through shared memory
   int res_c = 0, dst_c = 0;
   int bn = 0;
+  int pf[3] = {0, 0, 0};  // front padding (t, h, w) after resolving VAD_FLAG_CONV_SAME
+  int pb[3] = {0, 0, 0};  // back padding
   int bk = 64;
   int kps = 1;        // k-blocks per pipeline stage (2: eight MMAs per barrier round trip for BN <= 128)
   int grid = 0;
@@ -176,8 +178,10 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
       if ((d.flags & VAD_FLAG_POOL_T2) && !fold)
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: POOL_T2 is fused into the stem kernel only (needs STEM_FOLD_W)", i);
       if (fold && in_channels != 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs the stem input layout (in_channels == 0)", i);
-      if (fold && (d.kw > 8 || d.src != 0 || in_pad_left < d.pw || ((in_pad_left - d.pw) & 1) || (d.sw & 1)))
-        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs src=0, kw<=8, even sw, in_pad_left-pw even and >=0", i);
+      if (fold && (d.kw > 8 || d.src != 0 || (d.sw & 1)))
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs src=0, kw<=8, even sw", i);
+      if (fold && !(d.flags & VAD_FLAG_CONV_SAME) && (in_pad_left < d.pw || ((in_pad_left - d.pw) & 1)))
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs in_pad_left - pw even and >= 0", i);
     }
   }
   vad_plan* p = new vad_plan();
@@ -241,28 +245,48 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       const bool fold = d.flags & VAD_FLAG_STEM_FOLD_W;
       const int Wi = fold ? src.W - 8 : src.W;
       if (src.C != d.cin) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: cin=%d but slot %d has C=%d", i, d.cin, d.src, src.C);
-      To = (src.T + 2 * d.pt - d.kt) / d.st + 1;
-      Ho = (src.H + 2 * d.ph - d.kh) / d.sh + 1;
-      Wo = (Wi + 2 * d.pw - d.kw) / d.sw + 1;
+      if (d.flags & VAD_FLAG_CONV_SAME) {
+        // TF "SAME" (Unit3D.compute_pad of the public I3D port): out = ceil(in / stride), the padding that needs is
+        // split front = total / 2, back = total - front (asymmetric for the 7x7x7 / 2 stem: 2 in front, 3 behind)
+        const int in3[3] = {src.T, src.H, Wi}, k3[3] = {d.kt, d.kh, d.kw}, s3[3] = {d.st, d.sh, d.sw};
+        int out3[3];
+        for (int a = 0; a < 3; ++a) {
+          out3[a] = (in3[a] + s3[a] - 1) / s3[a];
+          int tot = (out3[a] - 1) * s3[a] + k3[a] - in3[a];
+          if (tot < 0) tot = 0;
+          r.pf[a] = tot / 2;
+          r.pb[a] = tot - tot / 2;
+        }
+        To = out3[0]; Ho = out3[1]; Wo = out3[2];
+        if (fold && (p->in_pad_left < r.pf[2] || ((p->in_pad_left - r.pf[2]) & 1)))
+          return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: STEM_FOLD_W needs in_pad_left - (SAME front pad %d) even and >= 0", i, r.pf[2]);
+      } else {
+        r.pf[0] = r.pb[0] = d.pt; r.pf[1] = r.pb[1] = d.ph; r.pf[2] = r.pb[2] = d.pw;
+        To = (src.T + 2 * d.pt - d.kt) / d.st + 1;
+        Ho = (src.H + 2 * d.ph - d.kh) / d.sh + 1;
+        Wo = (Wi + 2 * d.pw - d.kw) / d.sw + 1;
+      }
+      const int pt = r.pf[0], ph = r.pf[1], pw = r.pf[2];
+      const bool sym_pad = r.pf[0] == r.pb[0] && r.pf[1] == r.pb[1] && r.pf[2] == r.pb[2];
       if (To <= 0 || Ho <= 0 || Wo <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: empty output", i);
       Cdst = d.dst_c_total ? d.dst_c_total : d.cout;
       if (d.dst_c_off + d.cout > Cdst) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: channel slice exceeds dst_c_total", i);
       const long long M = (long long)batch * To * Ho * Wo;
       if (M > 0x7fffffffLL - 256) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: too many output pixels (%lld)", i, M);
-      if (fold && d.sw * (Wo - 1) - d.pw + p->in_pad_left + 7 > src.W - 1)
+      if (fold && d.sw * (Wo - 1) - pw + p->in_pad_left + 7 > src.W - 1)
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: folded stem window overruns the padded row", i);
       ConvParams& c = r.cp;
       memset(&c, 0, sizeof(c));
       c.M = (int)M; c.N = d.cout;
       c.To = To; c.Ho = Ho; c.Wo = Wo;
       c.Ti = src.T; c.Hi = src.H;
-      c.kt = d.kt; c.kh = d.kh; c.st = d.st; c.sh = d.sh; c.pt = d.pt; c.ph = d.ph;
+      c.kt = d.kt; c.kh = d.kh; c.st = d.st; c.sh = d.sh; c.pt = pt; c.ph = ph;
       if (fold) {
         c.Wi = Wo; c.kw = 1; c.sw = 1; c.pw = 0;
         c.cin_eff = 32; c.ntaps = d.kt * d.kh;
         c.sW = d.sw * 4; c.sH = (long long)src.W * 4; c.sT = c.sH * src.H; c.sN = c.sT * src.T;
       } else {
-        c.Wi = Wi; c.kw = d.kw; c.sw = d.sw; c.pw = d.pw;
+        c.Wi = Wi; c.kw = d.kw; c.sw = d.sw; c.pw = pw;
         c.cin_eff = d.cin; c.ntaps = d.kt * d.kh * d.kw;
         c.sW = d.cin; c.sH = (long long)Wi * d.cin; c.sT = c.sH * src.H; c.sN = c.sT * src.T;
       }
@@ -271,8 +295,8 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       c.relu = (d.flags & VAD_FLAG_RELU) ? 1 : 0;
       c.ldo = Cdst;
       r.dst_c = Cdst;
-      const bool unit = d.kt == 1 && d.kh == 1 && d.kw == 1 && d.st == 1 && d.sh == 1 && d.sw == 1 && !d.pt && !d.ph && !d.pw;
-      const bool tma_geom_ok = d.pt <= 15 && d.ph <= 15 && d.pw <= 15 && d.kt <= 16 && d.kh <= 16 && d.kw <= 16 &&
+      const bool unit = d.kt == 1 && d.kh == 1 && d.kw == 1 && d.st == 1 && d.sh == 1 && d.sw == 1 && !pt && !ph && !pw;
+      const bool tma_geom_ok = r.pb[0] <= 15 && r.pb[1] <= 15 && r.pb[2] <= 15 && d.kt <= 16 && d.kh <= 16 && d.kw <= 16 &&
                                d.st <= 8 && d.sh <= 8 && d.sw <= 8;
       r.bk = 64;
       if ((d.flags & VAD_FLAG_FORCE_GATHER) || !tma_geom_ok || (!fold && (d.cin % 64)) || (fold && p->stem_gather))
@@ -302,14 +326,15 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
       r.stem = false;
       const bool pool_t2 = (d.flags & VAD_FLAG_POOL_T2) != 0;
-      if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0) {
+      if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0 && sym_pad &&
+          d.kt * d.kh * kStemTapBytes <= 150 * 1024) {
         StemParams& q = r.sp;
         memset(&q, 0, sizeof(q));
         q.clk_out = nullptr;
         q.B = batch; q.To = To; q.Ho = Ho; q.Wo = Wo;
         q.pool_t = pool_t2 ? 2 : 1;
         q.To_out = To / q.pool_t;
-        q.kt = d.kt; q.kh = d.kh; q.st = d.st; q.pt = d.pt; q.ph = d.ph;
+        q.kt = d.kt; q.kh = d.kh; q.st = d.st; q.pt = pt; q.ph = ph;
         const int th = 16, tw = 8;  // output tile: 8 (w) x 16 (h)
         q.tiles_w = (Wo + tw - 1) / tw; q.tiles_h = (Ho + th - 1) / th;
         long long nu = (long long)batch * q.To_out * q.tiles_h * q.tiles_w;
@@ -324,7 +349,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         if (ns > kStemMaxStages) ns = kStemMaxStages;
         // multi-frame variant: all output frames of a spatial tile live in TMEM (8 x 64 columns), input frames are
         // walked once; needs the I3D temporal geometry (kt 5, stride 2, pad 2) and at most 8 output frames
-        r.stem_mf = !p->stem_v3 && d.kt == 5 && d.st == 2 && d.pt == 2 && To <= 8 && To >= 1 && d.kh <= 7;
+        r.stem_mf = !p->stem_v3 && d.kt == 5 && d.st == 2 && pt == 2 && To <= 8 && To >= 1 && d.kh <= 7;
         if (r.stem_mf) {
           nu = (long long)batch * q.tiles_h * q.tiles_w;
           r.stem_ti = src.T;
@@ -446,7 +471,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
     if (d.kind == VAD_OP_CONV) {
       ConvParams& c = r.cp;
       const bool fold = d.flags & VAD_FLAG_STEM_FOLD_W;
-      c.in = reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.src)) + (fold ? (p->in_pad_left - d.pw) * 4 : 0);
+      c.in = reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.src)) + (fold ? (p->in_pad_left - r.pf[2]) * 4 : 0);
       c.out = reinterpret_cast<__nv_bfloat16*>(slot_ptr(d.dst)) + d.dst_c_off;
       c.res = d.res >= 0 ? reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.res)) : nullptr;
       c.scale = reinterpret_cast<const float*>(p->params + d.scale_off);
@@ -549,8 +574,8 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         gstr[1] = wp * 4 * 2;
         gstr[2] = gstr[1] * r.Hi;
         gstr[3] = gstr[2] * r.Ti;
-        int lower[3] = {0, -d.ph, -d.pt};
-        int upper[3] = {0, d.ph - (d.kh - 1), d.pt - (d.kt - 1)};
+        int lower[3] = {0, -r.pf[1], -r.pf[0]};
+        int upper[3] = {0, r.pb[1] - (d.kh - 1), r.pb[0] - (d.kt - 1)};
         cuuint32_t es[5] = {1, 1, (cuuint32_t)d.sh, (cuuint32_t)d.st, 1};
         CUresult cr = p->encode_im2col(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)c.in, gdim, gstr, lower, upper,
                                        32, (cuuint32_t)kBlockM, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -570,8 +595,8 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         gstr[1] = gstr[0] * r.Wi;
         gstr[2] = gstr[1] * r.Hi;
         gstr[3] = gstr[2] * r.Ti;
-        int lower[3] = {-d.pw, -d.ph, -d.pt};
-        int upper[3] = {d.pw - (d.kw - 1), d.ph - (d.kh - 1), d.pt - (d.kt - 1)};
+        int lower[3] = {-r.pf[2], -r.pf[1], -r.pf[0]};
+        int upper[3] = {r.pb[2] - (d.kw - 1), r.pb[1] - (d.kh - 1), r.pb[0] - (d.kt - 1)};
         cuuint32_t es[5] = {1, (cuuint32_t)d.sw, (cuuint32_t)d.sh, (cuuint32_t)d.st, 1};
         CUresult cr = p->encode_im2col(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)slot_ptr(d.src), gdim, gstr,
                                        lower, upper, 64, (cuuint32_t)kBlockM, es,

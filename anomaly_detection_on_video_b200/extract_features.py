@@ -86,9 +86,9 @@ def extract_clip_features(video_dataset: TenCropVideoFrameDataset, model: torch.
             n = min(clips_per_batch, n_clips - start)
             if stem_buf is None or stem_buf.shape[0] != n * k:
                 stem_buf = None
-                stem_buf = video_dataset.clips_stem(start, n)
+                stem_buf = video_dataset.clips_stem(start, n, pad_left=model.pad_left)
             else:
-                video_dataset.clips_stem(start, n, out=stem_buf)
+                video_dataset.clips_stem(start, n, pad_left=model.pad_left, out=stem_buf)
             f = model.forward_stem_layout(stem_buf)  # (n * k, C), clip-major then crop
             if feats is None:
                 feats = torch.empty(n_clips, k, f.shape[1], dtype=torch.float32, device=f.device)

@@ -59,6 +59,7 @@ class _NativeBackbone(nn.Module):
     """Shared machinery: build the op table from the module tree, run it through the C ABI."""
 
     feature_dim = 0
+    pad_left = STEM_PAD_LEFT  # zero pixels left of every row in the stem layout this backbone reads
 
     def __init__(self) -> None:
         super().__init__()
@@ -93,7 +94,7 @@ class _NativeBackbone(nn.Module):
         key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool)
         if self._plan is None or self._plan_key != key:
             ops, packer, n_slots = self._build_table()
-            self._plan = BackbonePlan(ops, packer.blob(), n_slots, STEM_PAD_LEFT, device)
+            self._plan = BackbonePlan(ops, packer.blob(), n_slots, self.pad_left, device)
             self._plan_key = key
         return self._plan
 
@@ -111,7 +112,7 @@ class _NativeBackbone(nn.Module):
         if not batch.is_cuda:
             raise RuntimeError("I3D features are computed by sm_100a kernels only; move the input (and the model) "
                                "to a CUDA device. There is no CPU fallback.")
-        feats = self.forward_stem_layout(ingest_ncthw(batch.float(), STEM_PAD_LEFT))
+        feats = self.forward_stem_layout(ingest_ncthw(batch.float(), self.pad_left))
         return feats.view(feats.shape[0], feats.shape[1], 1, 1, 1)
 
 

@@ -1,0 +1,165 @@
+"""InceptionV1-3D ("I3D", Carreira & Zisserman 2017) feature extractor on the same native kernels.
+
+`north_star` names this backbone (``InceptionI3d`` / ``Unit3D`` / ``MaxPool3dSamePadding``, 1024-d features); the
+reference repository does NOT contain it (it ships I3D-ResNet50), so there is no reference
+code to be a drop-in for.  The module tree and parameter names follow the widely used public PyTorch port of the
+Kinetics I3D checkpoint (``Conv3d_1a_7x7.conv3d.weight``, ``Conv3d_1a_7x7.bn.*``, ``Mixed_3b.b1a.conv3d.weight`` ...),
+so those checkpoints load with ``load_state_dict``; the layer table is SURVEY.md Appendix B.  PARITY UNPINNED BY THE
+REFERENCE: the oracle (``oracle/inception.py``) is our own fp32 restatement of the public architecture.
+
+What maps onto which kernel:
+  Unit3D (conv3d, TF-"SAME" padding, no bias + BatchNorm3d(eps 1e-3) + ReLU)  -> K2 with ``VAD_FLAG_CONV_SAME``;
+      16/24/32/48-channel and 480/528-channel inputs (Cin % 64 != 0) take the cp.async gather producer
+  MaxPool3dSamePadding                                                        -> K3 with ``VAD_FLAG_POOL_SAME``
+  Inception branch concat                                                     -> every branch conv writes its
+      channel slice of the concatenated tensor directly (``dst_c_off`` / ``dst_c_total``): no copy kernel
+  AvgPool3d([2, 7, 7]) on the final 2 x 7 x 7 map                             -> K4 (global mean)
+The 7x7x7 / 2 stem runs through the generic implicit-GEMM kernel (its 49 taps x 4 KB of weights do not fit the
+resident-weight stem kernel), which is L2-bound there: this backbone is functionally complete, not yet tuned.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .engine import Op, ParamPacker, fold_bn
+from .i3d import _NativeBackbone
+
+INCEPTION_PAD_LEFT = 2  # == the SAME front pad of the 7-wide stride-2 stem, so the folded window starts on a 16 B boundary
+
+# (name, in_channels, [b0, b1a, b1b, b2a, b2b, b3b]) -- SURVEY.md Appendix B
+MIXED: Tuple[Tuple[str, int, Tuple[int, int, int, int, int, int]], ...] = (
+    ("Mixed_3b", 192, (64, 96, 128, 16, 32, 32)),
+    ("Mixed_3c", 256, (128, 128, 192, 32, 96, 64)),
+    ("Mixed_4b", 480, (192, 96, 208, 16, 48, 64)),
+    ("Mixed_4c", 512, (160, 112, 224, 24, 64, 64)),
+    ("Mixed_4d", 512, (128, 128, 256, 24, 64, 64)),
+    ("Mixed_4e", 512, (112, 144, 288, 32, 64, 64)),
+    ("Mixed_4f", 528, (256, 160, 320, 32, 128, 128)),
+    ("Mixed_5b", 832, (256, 160, 320, 32, 128, 128)),
+    ("Mixed_5c", 832, (384, 192, 384, 48, 128, 128)),
+)
+# max-pools that sit in front of a Mixed block: name -> (kernel, stride)
+POOL_BEFORE = {"Mixed_4b": ("MaxPool3d_4a_3x3", (3, 3, 3), (2, 2, 2)), "Mixed_5b": ("MaxPool3d_5a_2x2", (2, 2, 2), (2, 2, 2))}
+
+
+class Unit3D(nn.Module):
+    """Parameter container: Conv3d (no bias) + BatchNorm3d(eps=1e-3) + ReLU with TF-SAME padding."""
+
+    def __init__(self, in_channels: int, output_channels: int, kernel_shape=(1, 1, 1), stride=(1, 1, 1)) -> None:
+        super().__init__()
+        self.conv3d = nn.Conv3d(in_channels, output_channels, kernel_shape, stride=stride, padding=0, bias=False)
+        self.bn = nn.BatchNorm3d(output_channels, eps=0.001, momentum=0.01)
+
+
+class MaxPool3dSamePadding(nn.Module):
+    def __init__(self, kernel_size, stride) -> None:
+        super().__init__()
+        self.kernel_size, self.stride = tuple(kernel_size), tuple(stride)
+
+
+class InceptionModule(nn.Module):
+    def __init__(self, in_channels: int, out_channels: Sequence[int]) -> None:
+        super().__init__()
+        self.b0 = Unit3D(in_channels, out_channels[0])
+        self.b1a = Unit3D(in_channels, out_channels[1])
+        self.b1b = Unit3D(out_channels[1], out_channels[2], (3, 3, 3))
+        self.b2a = Unit3D(in_channels, out_channels[3])
+        self.b2b = Unit3D(out_channels[3], out_channels[4], (3, 3, 3))
+        self.b3a = MaxPool3dSamePadding((3, 3, 3), (1, 1, 1))
+        self.b3b = Unit3D(in_channels, out_channels[5])
+        self.out_channels = tuple(out_channels)
+
+
+class InceptionI3d(_NativeBackbone):
+    """``model(x [B,3,16,224,224] fp32 cuda) -> [B,1024,1,1,1]`` (== ``extract_features``); the logits layer of the
+    public port is kept as parameters for checkpoint compatibility and never evaluated (feature extraction stops at
+    the average pool)."""
+
+    feature_dim = 1024
+    pad_left = INCEPTION_PAD_LEFT
+
+    def __init__(self, num_classes: int = 400, in_channels: int = 3) -> None:
+        super().__init__()
+        if in_channels != 3:
+            raise NotImplementedError("only the RGB stream is built (the flow stream has 2 input channels)")
+        self.fuse_stem_pool = False
+        self.Conv3d_1a_7x7 = Unit3D(3, 64, (7, 7, 7), (2, 2, 2))
+        self.MaxPool3d_2a_3x3 = MaxPool3dSamePadding((1, 3, 3), (1, 2, 2))
+        self.Conv3d_2b_1x1 = Unit3D(64, 64)
+        self.Conv3d_2c_3x3 = Unit3D(64, 192, (3, 3, 3))
+        self.MaxPool3d_3a_3x3 = MaxPool3dSamePadding((1, 3, 3), (1, 2, 2))
+        for name, cin, outs in MIXED:
+            if name in POOL_BEFORE:
+                pname, k, s = POOL_BEFORE[name]
+                setattr(self, pname, MaxPool3dSamePadding(k, s))
+            setattr(self, name, InceptionModule(cin, outs))
+        self.logits = nn.Conv3d(1024, num_classes, 1)  # unused by extract_features; kept for state_dict compatibility
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out")
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def _unit(self, pk: ParamPacker, u: Unit3D, src: int, dst: int, name: str, fold_w: bool = False, off: int = 0,
+              total: int = 0) -> Op:
+        scale, shift = fold_bn(u.bn.weight, u.bn.bias, u.bn.running_mean, u.bn.running_var, u.bn.eps)
+        w_off, s_off, b_off = pk.add_conv(u.conv3d.weight, scale, shift, fold_w=fold_w)
+        flags = _lib.VAD_FLAG_RELU | _lib.VAD_FLAG_CONV_SAME | (_lib.VAD_FLAG_STEM_FOLD_W if fold_w else 0)
+        if self.force_gather:
+            flags |= _lib.VAD_FLAG_FORCE_GATHER
+        conv = u.conv3d
+        return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, cin=4 if fold_w else conv.in_channels, cout=conv.out_channels,
+                  kernel=tuple(conv.kernel_size), stride=tuple(conv.stride), pad=(0, 0, 0), flags=flags, dst_c_off=off,
+                  dst_c_total=total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
+
+    @staticmethod
+    def _pool(p: MaxPool3dSamePadding, src: int, dst: int, name: str) -> Op:
+        return Op(kind=_lib.VAD_OP_MAXPOOL, src=src, dst=dst, kernel=p.kernel_size, stride=p.stride, flags=_lib.VAD_FLAG_POOL_SAME,
+                  name=name)
+
+    def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
+        pk = ParamPacker()
+        ops: List[Op] = []
+        T1, T2, T3 = 3, 4, 5  # branch temporaries; slots 1 / 2 ping-pong the block input / output
+        ops.append(self._unit(pk, self.Conv3d_1a_7x7, 0, 1, "Conv3d_1a_7x7", fold_w=True))
+        ops.append(self._pool(self.MaxPool3d_2a_3x3, 1, 2, "MaxPool3d_2a_3x3"))
+        ops.append(self._unit(pk, self.Conv3d_2b_1x1, 2, 1, "Conv3d_2b_1x1"))
+        ops.append(self._unit(pk, self.Conv3d_2c_3x3, 1, 2, "Conv3d_2c_3x3"))
+        ops.append(self._pool(self.MaxPool3d_3a_3x3, 2, 1, "MaxPool3d_3a_3x3"))
+        cur = 1
+        for name, _, outs in MIXED:
+            if name in POOL_BEFORE:
+                nxt = 2 if cur == 1 else 1
+                ops.append(self._pool(getattr(self, POOL_BEFORE[name][0]), cur, nxt, POOL_BEFORE[name][0]))
+                cur = nxt
+            m: InceptionModule = getattr(self, name)
+            nxt = 2 if cur == 1 else 1
+            total = outs[0] + outs[2] + outs[4] + outs[5]
+            # torch.cat([b0, b1, b2, b3], dim=1): every branch writes its channel slice of the output in place
+            ops.append(self._unit(pk, m.b0, cur, nxt, name + ".b0", off=0, total=total))
+            ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a"))
+            ops.append(self._unit(pk, m.b1b, T1, nxt, name + ".b1b", off=outs[0], total=total))
+            ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a"))
+            ops.append(self._unit(pk, m.b2b, T2, nxt, name + ".b2b", off=outs[0] + outs[2], total=total))
+            ops.append(self._pool(m.b3a, cur, T3, name + ".b3a"))
+            ops.append(self._unit(pk, m.b3b, T3, nxt, name + ".b3b", off=outs[0] + outs[2] + outs[4], total=total))
+            cur = nxt
+        ops.append(Op(kind=_lib.VAD_OP_AVGPOOL, src=cur, name="avg_pool"))
+        return ops, pk, 6
+
+    def extract_features(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward(x)
+
+    def forward(self, batch: torch.Tensor) -> torch.Tensor:
+        if batch.dim() == 5 and (batch.shape[2] // 8 != 2 or (batch.shape[3] + 31) // 32 != 7 or (batch.shape[4] + 31) // 32 != 7):
+            raise ValueError("InceptionI3d.extract_features ends in AvgPool3d([2, 7, 7]); it is built for inputs whose final "
+                             "feature map is exactly 2 x 7 x 7 (16 frames of 193..224 pixels)")
+        return super().forward(batch)
+
+
+__all__ = ["InceptionI3d", "InceptionModule", "Unit3D", "MaxPool3dSamePadding", "MIXED"]

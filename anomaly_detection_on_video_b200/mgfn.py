@@ -278,13 +278,14 @@ class MGFNForVideoAnomalyDetection(nn.Module):
         n_seq, dl, k = bs * ncrops, self.config.dims[-1], self.config.k
         need = ctypes.c_uint64()
         check(lib.vad_head_workspace_bytes(h, n_seq, T, ctypes.byref(need)), "vad_head_workspace_bytes")
-        if self._ws is None or self._ws.numel() < need.value or self._ws.device != dev:
-            self._ws = torch.empty(max(int(need.value), 1024), dtype=torch.uint8, device=dev)
+        if self._ws is None or self._ws.numel() < need.value + 1024 or self._ws.device != dev:
+            self._ws = torch.empty(int(need.value) + 1024, dtype=torch.uint8, device=dev)
+        ws_ptr = (self._ws.data_ptr() + 1023) // 1024 * 1024  # the C ABI wants a 1024-byte aligned workspace
         stream = torch.cuda.current_stream(dev).cuda_stream
         xln = torch.empty(n_seq, T, dl, dtype=torch.float32, device=dev)
         score_tok = torch.empty(n_seq, T, dtype=torch.float32, device=dev)
         fmag_tok = torch.empty(n_seq, T, dtype=torch.float32, device=dev)
-        check(lib.vad_head_forward(h, video.data_ptr(), bs, ncrops, T, self._ws.data_ptr(), self._ws.numel(), xln.data_ptr(),
+        check(lib.vad_head_forward(h, video.data_ptr(), bs, ncrops, T, ws_ptr, int(need.value), xln.data_ptr(),
                                    score_tok.data_ptr(), fmag_tok.data_ptr(), stream), "vad_head_forward")
         scores = torch.empty(bs, T, dtype=torch.float32, device=dev)
         vid_score = torch.empty(bs, dtype=torch.float32, device=dev)

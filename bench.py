@@ -154,7 +154,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--clips-per-batch", type=int, default=16)
+    ap.add_argument("--clips-per-batch", type=int, default=16,
+                    help="clips per backbone forward (x10 crops); 16 is the reference's DataLoader batch (extract_features.py:79)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -282,6 +283,53 @@ def main():
     ms_e2e = t0.elapsed_time(t1)  # device-timed; the D2H copies make every step host-synchronous anyway
     wall_e2e = (time.perf_counter() - wall0) * 1e3
 
+    # ---- scoring head (BASELINE config 5, inference side): gather the per-rank segment features over NCCL, append
+    # the magnitudes, score a training-shaped batch of 32 bags (16 normal + 16 abnormal) with the MGFN head and
+    # evaluate the loss.  Reported beside the extraction numbers, never mixed into `value`.
+    head_info = None
+    try:
+        from anomaly_detection_on_video_b200.dataset import add_magnitude
+        from anomaly_detection_on_video_b200.mgfn import MGFNConfig, MGFNForVideoAnomalyDetection
+        from oracle import mgfn as OM  # seeded synthetic weights only
+
+        head = MGFNForVideoAnomalyDetection(MGFNConfig())
+        head.load_state_dict(OM.seeded_state_dict(0), strict=True)
+        head.eval().to(dev)
+        head.force_split = True
+        seg_local = s_host.to(dev).contiguous()                       # (10, 32, 2048) of this rank's video
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        if world > 1:
+            gathered = torch.empty(world, *seg_local.shape, dtype=seg_local.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, seg_local)
+        else:
+            gathered = seg_local.unsqueeze(0)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gather_ms = g0.elapsed_time(g1)
+        bags = 32
+        video = add_magnitude(gathered.repeat((bags + gathered.shape[0] - 1) // gathered.shape[0], 1, 1, 1)[:bags].contiguous())
+        nl, al = torch.zeros(bags // 2, device=dev), torch.ones(bags // 2, device=dev)
+        for _ in range(2):
+            out = head(video, abnormal_labels=al, normal_labels=nl)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        h0.record()
+        for _ in range(K):
+            out = head(video, abnormal_labels=al, normal_labels=nl)
+        h1.record()
+        torch.cuda.synchronize(dev)
+        head_ms = h0.elapsed_time(h1) / K
+        flops = head.flops(bags * CROPS, 32)
+        head_info = {"bags": bags, "crops": CROPS, "segments": 32, "ms": head_ms, "bags_per_s": bags / (head_ms / 1e3),
+                     "tflops_tf32": flops / (head_ms / 1e3) / 1e12, "launches": head.num_launches + 3,
+                     "loss": float(out.loss), "nccl_gather_ms": gather_ms,
+                     "gather_bytes": int(seg_local.numel() * 4 * world),
+                     "note": "eval-mode forward + selection + loss (no backward kernels: training is not built)"}
+    except Exception as exc:  # the head is reported beside the metric; it must never take the bench line down
+        head_info = {"error": f"{type(exc).__name__}: {exc}"}
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,6 +403,7 @@ def main():
             "roofline": roofline,
             "roofline_conv_family": family,
             "cpu_baseline": cpu_baseline,
+            "head": head_info,
             "tflops_whole_step": value * FLOP_PER_CLIP / 1e12,
         }
         print(json.dumps(line), flush=True)

@@ -69,9 +69,11 @@ enum {
   VAD_FLAG_POOL_SAME = 4,   /* TF "SAME" padding for max-pool (MaxPool3dSamePadding); pad value 0   */
   VAD_FLAG_FORCE_GATHER = 8,/* conv: feed the A operand with the cp.async gather producer instead
                                of TMA (debug / comparison; results are identical)                   */
-  VAD_FLAG_POOL_T2 = 16     /* stem conv (STEM_FOLD_W): max over output frames (2k, 2k+1) fused into
+  VAD_FLAG_POOL_T2 = 16,    /* stem conv (STEM_FOLD_W): max over output frames (2k, 2k+1) fused into
                                the epilogue, i.e. the temporal half of a following MaxPool3d with
                                kt = st = 2, pt = 0 (reference src/i3d.py:212-214); dst has To / 2    */
+  VAD_FLAG_CONV_SAME = 32   /* conv: TF "SAME" padding (InceptionI3d's Unit3D): out = ceil(in / stride),
+                               front pad = total / 2, back pad = total - front; pt/ph/pw are ignored */
 };
 
 typedef struct vad_op_desc {

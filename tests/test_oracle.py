@@ -178,3 +178,23 @@ def test_oracle_equals_live_reference():
         want = m(x)
     got, _ = O.forward(x, sd)
     assert torch.equal(got, want)
+
+
+# ----------------------------------------------------------------------------- InceptionV1-3D (parity unpinned by the reference)
+def test_inception_oracle_layer_table_matches_survey_appendix_b():
+    from oracle import inception as OI
+
+    assert OI.conv_macs() == 27_787_569_152
+    sd = OI.seeded_state_dict(0)
+    from anomaly_detection_on_video_b200.inception import InceptionI3d
+
+    m = InceptionI3d()
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    ops = m.op_table()
+    convs = [o for o in ops if o.kind == 1 or o.cout]
+    assert len(ops) == 71 and sum(1 for o in ops if o.cout) == 57
+    # every Inception branch writes a channel slice of the concatenated tensor: slices tile [0, total) exactly
+    for name in ("Mixed_3b", "Mixed_4f", "Mixed_5c"):
+        sl = sorted((o.dst_c_off, o.cout, o.dst_c_total) for o in ops if o.name.startswith(name) and o.dst_c_total)
+        assert sl[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(sl, sl[1:])) and sl[-1][0] + sl[-1][1] == sl[-1][2]
