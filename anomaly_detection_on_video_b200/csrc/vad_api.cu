@@ -14,6 +14,7 @@
 #include "aux_kernels.cuh"
 #include "conv_umma.cuh"
 #include "stem_umma.cuh"
+#include "conv_thalo.cuh"
 
 using namespace vad;
 
@@ -98,6 +99,8 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
+  bool thalo = false;    // temporal-halo kernel for (3,1,1) convs (conv_thalo.cuh)
+  ThaloParams tp;
   bool stem_mf = false;  // multi-frame (input-frame stationary) stem kernel
   int stem_ti = 0, stem_ti_max = 0;
   int a_mode = 0;
@@ -120,6 +123,9 @@ struct vad_plan {
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool epi_all = false;      // VAD_EPI_ALL=1: staged TMA-store epilogue for every layer (tuning only)
+  bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
+  bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
+  int bn_model = 0;          // VAD_BN_MODEL=<pct>: prefer BN=128 over 256 when its modelled time is below pct % (tuning)
   int kps_override = 0;      // VAD_KPS=1|2: force k-blocks per stage (tuning only)
   bool stem_gather = false;  // VAD_STEM_GATHER=1: feed the stem through the cp.async gather producer
   int batch = 0, T = 0, H = 0, W = 0;
@@ -207,6 +213,9 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_STEM_V3"); p->stem_v3 = k && k[0] == '1'; }
   const char* sgen = getenv("VAD_STEM_GENERIC");
   p->stem_generic = sgen && sgen[0] == '1';
+  { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_BN_MODEL"); p->bn_model = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_KPS"); p->kps_override = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_EPI_ALL"); p->epi_all = k && k[0] == '1'; }
   const char* ne = getenv("VAD_NO_EPI");
@@ -314,15 +323,46 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections), VAD_EPI_ALL=1: every layer
       r.epi = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K) || p->epi_all);
       r.bn = (d.cout > 128 && !r.epi) ? 256 : (d.cout > 64 ? 128 : 64);
+      if (r.bn == 256 && d.cout % 128 == 0 && p->bn_model) {
+        // wave quantisation: a persistent grid of sm_count CTAs runs ceil(tiles / sm_count) rounds of tiles whose time
+        // is ~ BN; 128-wide tiles (two k-blocks per stage keep their MMAs at the floor) win when they cut the rounds
+        const long long mt = (M + kBlockM - 1) / kBlockM;
+        const long long t256 = mt * ((d.cout + 255) / 256), t128 = mt * (d.cout / 128);
+        const long long c256 = (t256 + p->sm_count - 1) / p->sm_count * 256, c128 = (t128 + p->sm_count - 1) / p->sm_count * 128;
+        if (c128 * 100 < c256 * p->bn_model) r.bn = 128;
+      }
       r.kps = (r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2 && !r.epi) ? 2 : 1;
       if (p->kps_override == 1) r.kps = 1;
       if (p->kps_override == 2 && r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2) r.kps = 2;
-      const long long m_tiles = (M + kBlockM - 1) / kBlockM;
+      long long m_tiles = (M + kBlockM - 1) / kBlockM;
+      r.thalo = !p->no_thalo && r.a_mode == A_TMA_IM2COL && !fold && !r.epi && d.res < 0 && r.bn <= (p->thalo_bn128 ? 128 : 64) && d.kt == 3 && d.kh == 1 &&
+                d.kw == 1 && d.st == 1 && d.sh == 1 && d.sw == 1 && pt == 1 && sym_pad && ph == 0 && pw == 0 &&
+                (src.T == 2 || src.T == 4) && d.cin % 64 == 0;
+      if (r.thalo) {
+        ThaloParams& q = r.tp;
+        memset(&q, 0, sizeof(q));
+        q.B = batch; q.T = src.T; q.HW = src.H * src.W;
+        q.P = 128 / src.T; q.logP = src.T == 2 ? 6 : 5;
+        q.tiles_per_clip = (q.HW + q.P - 1) / q.P;
+        q.N = d.cout; q.Cin = d.cin;
+        q.relu = c.relu; q.ldo = Cdst;
+        m_tiles = (long long)batch * q.tiles_per_clip;
+        // weights resident in shared memory when one n tile covers cout and they leave room for >= 3 A-only stages
+        const int kb_bytes = r.bn * 128, w_all = 3 * (d.cin / 64) * kb_bytes;
+        const int budget = r.bn == 128 ? ThaloCfg<128>::kBudget : ThaloCfg<64>::kBudget;
+        q.a_region = 16384 + 256 * q.P;
+        q.resident = (d.cout <= r.bn && w_all + 3 * q.a_region <= budget) ? 1 : 0;
+        q.stage_bytes = q.a_region + (q.resident ? 0 : 3 * kb_bytes);
+        q.n_stages = (budget - (q.resident ? w_all : 0)) / q.stage_bytes;
+        if (q.n_stages > ThaloCfg<64>::kMaxStages) q.n_stages = ThaloCfg<64>::kMaxStages;
+        if (q.n_stages < 2) r.thalo = false;
+      }
       const long long n_tiles = (d.cout + r.bn - 1) / r.bn;
       if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
       c.n_tiles = (int)n_tiles;
       c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
+      if (r.thalo) { r.tp.n_tiles = c.n_tiles; r.tp.num_tiles = c.num_tiles; }
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
       r.stem = false;
       const bool pool_t2 = (d.flags & VAD_FLAG_POOL_T2) != 0;
@@ -553,6 +593,18 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         }
         if (cr != CUDA_SUCCESS)
           return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(stem) failed: %d; set VAD_STEM_GENERIC=1", i, (int)cr);
+      } else if (r.thalo) {
+        // (C, HW, T, N): one box = 64 channels x P pixels x all T frames of one clip
+        ThaloParams& q = r.tp;
+        q.scale = c.scale; q.shift = c.shift; q.out = c.out;
+        cuuint64_t gdim[4] = {(cuuint64_t)r.Ci, (cuuint64_t)q.HW, (cuuint64_t)q.T, (cuuint64_t)p->batch};
+        cuuint64_t gstr[3] = {(cuuint64_t)r.Ci * 2, (cuuint64_t)r.Ci * 2 * q.HW, (cuuint64_t)r.Ci * 2 * q.HW * q.T};
+        cuuint32_t box[4] = {64, (cuuint32_t)q.P, (cuuint32_t)q.T, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(d.src), gdim, gstr, box, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(temporal halo A) failed: %d", i, (int)cr);
       } else if (r.a_mode == A_TMA_2D) {
         cuuint64_t gdim[2] = {(cuuint64_t)r.Ci, (cuuint64_t)c.M};
         cuuint64_t gstr[1] = {(cuuint64_t)r.Ci * 2};
@@ -720,6 +772,20 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
           stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, r.sp);
           e = cudaGetLastError();
         }
+      } else if (r.thalo) {
+        const int w_all = r.tp.resident ? 3 * (r.tp.Cin / 64) * r.bn * 128 : 0;
+        if (r.bn == 128) {
+          const int smem = w_all + r.tp.n_stages * r.tp.stage_bytes + ThaloCfg<128>::kFixedBytes;
+          static bool attr = false;
+          if (!attr) { e = cudaFuncSetAttribute(conv_thalo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = (e == cudaSuccess); }
+          if (e == cudaSuccess) conv_thalo_kernel<128><<<r.grid, ThaloCfg<128>::kThreads, smem, st>>>(r.tmA, r.tmB, r.tp);
+        } else {
+          const int smem = w_all + r.tp.n_stages * r.tp.stage_bytes + ThaloCfg<64>::kFixedBytes;
+          static bool attr = false;
+          if (!attr) { e = cudaFuncSetAttribute(conv_thalo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = (e == cudaSuccess); }
+          if (e == cudaSuccess) conv_thalo_kernel<64><<<r.grid, ThaloCfg<64>::kThreads, smem, st>>>(r.tmA, r.tmB, r.tp);
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
       } else {
         e = launch_conv_any(r, st);
       }

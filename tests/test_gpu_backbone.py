@@ -66,7 +66,11 @@ def test_features_track_the_bf16_emulating_oracle(model, cuda_device):
     assert ((y - y32).abs().max() / scale).item() < MAX_NORM_TOL
 
 
-def test_gather_and_tma_paths_agree_bitwise(model, cuda_device):
+def test_gather_and_tma_paths_agree(model, cuda_device):
+    """Every conv through the cp.async gather producer vs the TMA producers.  Layer by layer the operand tiles are
+    identical (tests/test_gpu_kernels.py asserts bit-equality per layer); end to end the (3,1,1) layers run through the
+    temporal-halo kernel, whose (channel block, tap) contraction order differs from the gather path's (tap, channel
+    block) in fp32 summation order, so the features agree to bf16 resolution rather than bit for bit."""
     x = torch.randn(2, 3, 8, 64, 64, generator=torch.Generator().manual_seed(7)).clamp(-2.0, 2.4444).to(cuda_device)
     a = model(x).clone()
     model.force_gather = True
@@ -74,7 +78,8 @@ def test_gather_and_tma_paths_agree_bitwise(model, cuda_device):
         b = model(x).clone()
     finally:
         model.force_gather = False
-    assert torch.equal(a, b)
+    assert float((a - b).abs().max()) <= 5e-3 * float(b.abs().max())
+    assert float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)) >= 0.99999
 
 
 def test_batch_invariance_and_determinism(model, cuda_device):

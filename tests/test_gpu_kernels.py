@@ -29,6 +29,9 @@ CONV_CASES = [
     ("1x1 stride 2 downsample", 256, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), 2, 2, 15, 15, False, False),
     ("3x3x3 64->192 (Inception)", 64, 192, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 4, 10, 10, False, True),
     ("t3 T=1 all-padding edges", 64, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 3, 1, 5, 5, False, True),
+    ("t3 T=2 256->128 (layer2.0.conv1)", 256, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 2, 9, 11, False, True),
+    ("t3 T=4 64->64 row 55 ragged tile", 64, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, 4, 55, 3, False, True),
+    ("t3 T=2 512->128 two stages deep", 512, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, 2, 28, 28, False, False),
 ]
 GATHER_ONLY = [
     ("cin 24 3x3x3", 24, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 4, 10, 10, False, True),
@@ -51,9 +54,17 @@ def test_tma_im2col_and_gather_producers_agree_bitwise(cuda_device, case):
     """Both A-operand producers must deliver the same tile, so the outputs are bit-identical."""
     from gpu_util import run_conv_case
 
-    a, _ = run_conv_case(*case[1:], force_gather=False)
+    a, ref = run_conv_case(*case[1:], force_gather=False)
     b, _ = run_conv_case(*case[1:], force_gather=True)
-    assert torch.equal(a, b)
+    if case[3] == (3, 1, 1) and not case[10]:
+        # (3,1,1) convs without a residual run through the temporal-halo kernel, which contracts in (channel block, tap)
+        # order instead of (tap, channel block): same products, different fp32 summation order
+        from gpu_util import assert_bf16_close
+
+        assert_bf16_close(a, ref)
+        assert (a - b).abs().max() <= 2.0 ** -7 * ref.abs().max()
+    else:
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("case", GATHER_ONLY, ids=[c[0] for c in GATHER_ONLY])
