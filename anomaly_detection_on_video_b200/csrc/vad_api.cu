@@ -15,6 +15,7 @@
 #include "conv_umma.cuh"
 #include "stem_umma.cuh"
 #include "conv_thalo.cuh"
+#include "conv_s3x3.cuh"
 
 using namespace vad;
 
@@ -99,6 +100,8 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
+  bool s3 = false;       // spatial (1,3,3) 64 -> 64 kernel (conv_s3x3.cuh)
+  S3x3Params s3p;
   bool thalo = false;    // temporal-halo kernel for (3,1,1) convs (conv_thalo.cuh)
   ThaloParams tp;
   bool stem_mf = false;  // multi-frame (input-frame stationary) stem kernel
@@ -123,6 +126,7 @@ struct vad_plan {
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool epi_all = false;      // VAD_EPI_ALL=1: staged TMA-store epilogue for every layer (tuning only)
+  bool no_s3 = false;        // VAD_NO_S3X3=1: layer1's (1,3,3) convs through the generic im2col kernel
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
   int bn_model = 0;          // VAD_BN_MODEL=<pct>: prefer BN=128 over 256 when its modelled time is below pct % (tuning)
@@ -213,6 +217,7 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_STEM_V3"); p->stem_v3 = k && k[0] == '1'; }
   const char* sgen = getenv("VAD_STEM_GENERIC");
   p->stem_generic = sgen && sgen[0] == '1';
+  { const char* k = getenv("VAD_NO_S3X3"); p->no_s3 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
   { const char* k = getenv("VAD_BN_MODEL"); p->bn_model = k ? atoi(k) : 0; }
@@ -357,12 +362,23 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         if (q.n_stages > ThaloCfg<64>::kMaxStages) q.n_stages = ThaloCfg<64>::kMaxStages;
         if (q.n_stages < 2) r.thalo = false;
       }
+      r.s3 = !p->no_s3 && r.a_mode == A_TMA_IM2COL && !fold && !r.epi && d.res < 0 && d.cin == 64 && d.cout == 64 && d.kt == 1 &&
+             d.kh == 3 && d.kw == 3 && d.st == 1 && d.sh == 1 && d.sw == 1 && pt == 0 && ph == 1 && pw == 1 && sym_pad;
+      if (r.s3) {
+        S3x3Params& q = r.s3p;
+        memset(&q, 0, sizeof(q));
+        q.F = batch * src.T; q.H = src.H; q.W = Wi;
+        q.tiles_w = (Wi + 7) / 8; q.tiles_h = (src.H + 15) / 16;
+        q.relu = c.relu;
+        m_tiles = (long long)q.F * q.tiles_w * q.tiles_h;
+      }
       const long long n_tiles = (d.cout + r.bn - 1) / r.bn;
       if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
       c.n_tiles = (int)n_tiles;
       c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
       if (r.thalo) { r.tp.n_tiles = c.n_tiles; r.tp.num_tiles = c.num_tiles; }
+      if (r.s3) r.s3p.num_tiles = c.num_tiles;
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
       r.stem = false;
       const bool pool_t2 = (d.flags & VAD_FLAG_POOL_T2) != 0;
@@ -593,6 +609,27 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         }
         if (cr != CUDA_SUCCESS)
           return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(stem) failed: %d; set VAD_STEM_GENERIC=1", i, (int)cr);
+      } else if (r.s3) {
+        // input (C, W, H, F): one box = 64 channels x 8 columns x 18 rows; output slice (cout, W, H, F): 8 x 4 per store
+        S3x3Params& q = r.s3p;
+        q.scale = c.scale; q.shift = c.shift;
+        cuuint64_t gdim[4] = {64, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.F};
+        cuuint64_t gstr[3] = {128, (cuuint64_t)128 * q.W, (cuuint64_t)128 * q.W * q.H};
+        cuuint32_t box[4] = {64, 8, 18, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(d.src), gdim, gstr, box, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS) {
+          const uint64_t cb = (uint64_t)r.dst_c * 2;
+          cuuint64_t odim[4] = {64, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.F};
+          cuuint64_t ostr[3] = {cb, cb * q.W, cb * q.W * q.H};
+          cuuint32_t obox[4] = {64, 8, 4, 1};
+          cr = p->encode_tiled(&r.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.out, odim, ostr, obox, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(3x3 halo tile) failed: %d", i, (int)cr);
       } else if (r.thalo) {
         // (C, HW, T, N): one box = 64 channels x P pixels x all T frames of one clip
         ThaloParams& q = r.tp;
@@ -770,6 +807,13 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
           }
         } else if (e == cudaSuccess) {
           stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, r.sp);
+          e = cudaGetLastError();
+        }
+      } else if (r.s3) {
+        static bool attr = false;
+        if (!attr) { e = cudaFuncSetAttribute(conv_s3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes); attr = (e == cudaSuccess); }
+        if (e == cudaSuccess) {
+          conv_s3x3_kernel<<<r.grid, kS3Threads, kS3SmemBytes, st>>>(r.tmA, r.tmB, r.tmO, r.s3p);
           e = cudaGetLastError();
         }
       } else if (r.thalo) {
