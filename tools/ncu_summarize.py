@@ -80,7 +80,7 @@ if os.path.exists(path):
         v, u = float(d[key]), units[hdr.index(key)].lower()
         return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}[u]
     traffic = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-    json.dump({"kernel": "stem_umma_kernel", "capture": f"{tag}_stem (ncu --set full, tools/ncu_target.py, 160 clip-crops)",
+    json.dump({"kernel": "stem_umma_mf_kernel", "capture": f"{tag}_stem (ncu --set full, tools/ncu_target.py, 160 clip-crops)",
                "dram_bytes_per_launch": traffic, "dram_read_bytes": gb("dram__bytes_read.sum"),
                "dram_write_bytes": gb("dram__bytes_write.sum"), "clip_crops_per_launch": 160},
               open("profiles/stem_dram_traffic.json", "w"), indent=1)
