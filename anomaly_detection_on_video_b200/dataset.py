@@ -8,6 +8,7 @@ produced on the GPU; ``clips_stem`` hands the native backbone its bf16 input lay
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
@@ -196,5 +197,79 @@ def add_magnitude(feature: Union[np.ndarray, torch.Tensor]) -> Union[np.ndarray,
     return _add_magnitude(feature)
 
 
-__all__ = ["TenCropVideoFrameDataset", "FrameSource", "add_magnitude", "BILINEAR"]
+class FeatureDataset(Dataset):
+    """Drop-in for the reference ``FeatureDataset`` (src/dataset.py:96-142): one item per ``<video>_i3d.npy`` feature
+    file, ``{"feature": (crops, T, C + 1) fp32 with the L2 magnitude appended, "anomaly": 0.0 / 1.0 from the file name,
+    ["label": per-frame ground truth]}``.  ``values`` maps a file name to an array or, with ``open_func``, to whatever
+    ``np.load(open_func(value))`` can read (the reference's lazily opened zip members).  The magnitude column is
+    computed by ``vad_add_magnitude`` on ``device`` (the reference uses ``np.linalg.norm``; they agree to fp32
+    rounding, see tests/test_gpu_kernels.py)."""
+
+    def __init__(self, filenames, values, labels=None, open_func=None, device: Optional[torch.device] = None) -> None:
+        self.filenames = list(filenames)
+        self.values = values
+        self.labels = labels
+        self.open_func = open_func
+        self.device = torch.device(device if device is not None else "cuda")
+
+    def __len__(self) -> int:
+        return len(self.values)
+
+    def open(self, value):
+        if self.open_func is None:
+            return value
+        return np.load(self.open_func(value))  # dynamic loading (src/dataset.py:115-119)
+
+    def add_magnitude(self, feature: np.ndarray) -> np.ndarray:
+        if self.device.type != "cuda":
+            raise RuntimeError("FeatureDataset.add_magnitude runs on the GPU only (no CPU fallback)")
+        t = torch.from_numpy(np.ascontiguousarray(feature, dtype=np.float32)).to(self.device)
+        return _add_magnitude(t).cpu().numpy()
+
+    def get_filename(self, idx: int) -> str:
+        return self.filenames[idx]
+
+    def __getitem__(self, idx: int):
+        fname = self.get_filename(idx)
+        feature = self.open(self.values[fname])
+        outputs = {"feature": self.add_magnitude(feature),
+                   "anomaly": np.array(0.0 if "Normal" in fname else 1.0, dtype=np.float32)}
+        if self.labels is not None:
+            outputs["label"] = np.array(self.labels[fname], dtype=np.float32)
+        return outputs
+
+
+def build_feature_dataset(mode: str = "train", local_path: Optional[str] = None, filename: Optional[str] = None,
+                          ground_truth: Optional[str] = None, dynamic_load: bool = True,
+                          device: Optional[torch.device] = None):
+    """``build_feature_dataset`` (src/dataset.py:20-93) for a LOCAL ``train.zip`` / ``test.zip`` of ``*_i3d.npy``
+    feature files (the reference downloads them from the HF hub; there is no network here): ``train`` returns
+    ``{"normal": FeatureDataset, "abnormal": FeatureDataset}`` split on "Normal" in the file name, ``test`` one dataset
+    with the per-frame labels of ``ground_truth`` (a json: file name -> list)."""
+    import json
+    import zipfile
+
+    assert mode in ("train", "test")
+    if local_path is None or filename is None:
+        raise RuntimeError("no network: pass local_path and filename of the feature archive "
+                           "(the reference's default downloads jinmang2/ucf_crime_tencrop_i3d_seg32)")
+    zipf = zipfile.ZipFile(os.path.join(local_path, filename))
+    names, values = [], {}
+    for member in zipf.infolist():
+        if member.is_dir():
+            continue
+        name = member.filename.split("/")[-1]
+        names.append(name)
+        values[name] = member if dynamic_load else np.load(zipf.open(member))
+    open_func = zipf.open if dynamic_load else None
+    if mode == "test":
+        labels = json.load(open(ground_truth)) if ground_truth is not None else None
+        return FeatureDataset(names, values, labels=labels, open_func=open_func, device=device)
+    normal = [n for n in names if "Normal" in n]
+    abnormal = [n for n in names if "Normal" not in n]
+    return {"normal": FeatureDataset(normal, {n: values[n] for n in normal}, open_func=open_func, device=device),
+            "abnormal": FeatureDataset(abnormal, {n: values[n] for n in abnormal}, open_func=open_func, device=device)}
+
+
+__all__ = ["TenCropVideoFrameDataset", "FrameSource", "FeatureDataset", "build_feature_dataset", "add_magnitude", "BILINEAR"]
 _ = List

@@ -94,3 +94,43 @@ def test_head_rejects_bad_inputs(head, cuda_device):
     with pytest.raises(ValueError):
         head(torch.zeros(3, 10, 32, 2049, device=cuda_device))
     head.force_split = False
+
+
+def test_validation_loop_over_a_feature_archive(head, cuda_device, tmp_path):
+    """FeatureDataset (local zip, GPU magnitude) -> runner.validate == the reference's validation_step +
+    on_validation_epoch_end formulas evaluated on the oracle's scores (src/runner.py:42-79)."""
+    import json
+    import zipfile
+
+    from anomaly_detection_on_video_b200.dataset import build_feature_dataset
+    from anomaly_detection_on_video_b200.runner import frame_level_metrics, validate, validation_step
+    from oracle import mgfn as M
+
+    rng = np.random.default_rng(3)
+    gt, feats = {}, {}
+    with zipfile.ZipFile(tmp_path / "test.zip", "w") as zf:
+        for name, t in (("Abuse028_x264_i3d.npy", 7), ("Normal_Videos_050_x264_i3d.npy", 12)):
+            f = np.abs(rng.standard_normal((t, 10, 2048))).astype(np.float32) * 0.5
+            np.save(tmp_path / name, f)
+            zf.write(tmp_path / name, arcname="test/" + name)
+            feats[name] = f
+            gt[name] = (rng.random(t * 16) > 0.5).astype(float).tolist()
+    json.dump(gt, open(tmp_path / "gt.json", "w"))
+    ds = build_feature_dataset("test", local_path=str(tmp_path), filename="test.zip", ground_truth=str(tmp_path / "gt.json"),
+                               device=cuda_device)
+    item = ds[0]
+    want = np.concatenate([feats[ds.get_filename(0)], np.linalg.norm(feats[ds.get_filename(0)], axis=2)[:, :, None]], axis=2)
+    np.testing.assert_allclose(item["feature"], want, rtol=1e-6, atol=1e-6)
+    assert item["anomaly"] == 1.0 and item["label"].shape == (7 * 16,)
+    head.force_split = False
+    got = validate(head, ds, frames_per_clip=16, device=cuda_device)
+    sd = M.seeded_state_dict(0)
+    ref_outs = []
+    for i in range(len(ds)):
+        it = ds[i]
+        video = torch.from_numpy(it["feature"]).unsqueeze(0).permute(0, 2, 1, 3)
+        ref_outs.append({"preds": M.forward(video, sd, split=False)["scores"].squeeze(0).squeeze(-1).numpy(), "labels": it["label"]})
+        step = validation_step(head, it, cuda_device)
+        assert np.abs(step["preds"] - ref_outs[-1]["preds"]).max() <= SCORE_ATOL
+    ref = frame_level_metrics(ref_outs, 16)
+    assert abs(got["valid/rec_auc"] - ref["valid/rec_auc"]) < 0.02 and abs(got["valid/pr_auc"] - ref["valid/pr_auc"]) < 0.02

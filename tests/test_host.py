@@ -143,3 +143,46 @@ def test_workqueue_single_process_is_identity():
 
     assert list(WorkQueue().claim(7)) == list(range(7))
     assert WorkQueue.from_env() is None or int(os.environ.get("WORLD_SIZE", "1")) > 1
+
+
+def test_frame_level_metrics_match_the_reference_formula():
+    """src/runner.py:62-73: np.repeat(preds, 16) against per-frame labels, ROC-AUC / PR-AUC via sklearn."""
+    from sklearn.metrics import auc, roc_curve
+
+    from anomaly_detection_on_video_b200.runner import frame_level_metrics
+
+    rng = np.random.default_rng(0)
+    outs = []
+    for t in (5, 9):
+        preds = rng.random(t).astype(np.float32)
+        labels = (np.repeat(preds, 16) + 0.3 * rng.standard_normal(t * 16) > 0.6).astype(np.float32)
+        outs.append({"preds": preds, "labels": labels})
+    m = frame_level_metrics(outs, 16)
+    p = np.repeat(np.concatenate([o["preds"] for o in outs]), 16)
+    l = np.concatenate([o["labels"] for o in outs])
+    fpr, tpr, _ = roc_curve(l.tolist(), p)
+    assert abs(m["valid/rec_auc"] - auc(fpr, tpr)) < 1e-12 and 0.5 < m["valid/rec_auc"] <= 1.0
+    with pytest.raises(ValueError):
+        frame_level_metrics([{"preds": np.zeros(3, np.float32), "labels": np.zeros(40, np.float32)}], 16)
+
+
+def test_feature_dataset_archive_layout(tmp_path):
+    """build_feature_dataset on a local zip: normal / abnormal split by file name, lazily opened members."""
+    import zipfile
+
+    from anomaly_detection_on_video_b200.dataset import build_feature_dataset
+
+    rng = np.random.default_rng(1)
+    z = tmp_path / "train.zip"
+    with zipfile.ZipFile(z, "w") as zf:
+        for name in ("Abuse001_x264_i3d.npy", "Normal_Videos_003_x264_i3d.npy", "Normal_Videos_010_x264_i3d.npy"):
+            path = tmp_path / name
+            np.save(path, rng.standard_normal((10, 32, 8)).astype(np.float32))
+            zf.write(path, arcname="train/" + name)
+    ds = build_feature_dataset("train", local_path=str(tmp_path), filename="train.zip", device="cpu")
+    assert len(ds["normal"]) == 2 and len(ds["abnormal"]) == 1
+    assert ds["abnormal"].get_filename(0).startswith("Abuse") and ds["normal"].open(ds["normal"].values[ds["normal"].get_filename(0)]).shape == (10, 32, 8)
+    with pytest.raises(RuntimeError, match="GPU only|no CPU fallback"):
+        ds["normal"][0]
+    with pytest.raises(RuntimeError, match="no network"):
+        build_feature_dataset("train")
