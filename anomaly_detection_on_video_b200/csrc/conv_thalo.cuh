@@ -43,14 +43,6 @@ struct ThaloCfg {
   static constexpr int kFixedBytes = 2 * BN * 4 + (2 * kMaxStages + 5) * 8 + 16 + 1024;
 };
 
-__device__ __forceinline__ void tma_load_4d_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
 template <int BN>
 __global__ void __launch_bounds__(ThaloCfg<BN>::kThreads, 1)
 conv_thalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ThaloParams p) {

@@ -44,6 +44,8 @@ struct ConvParams {
   int ntaps;
   long long sN, sT, sH, sW;  // input strides in elements
   int a_mode;
+  int pool_tp;           // 1: M tiles are (all 4 frames x 32 pixels) and the staged epilogue max-reduces frame pairs (maxpool2 fused)
+  int tp_tiles_per_clip; // ceil(H * W / 32) when pool_tp
   int relu;
   int ldo;  // output row pitch in elements
   int ldr;  // residual row pitch in elements
@@ -111,6 +113,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;                                // descriptor version (sm_100)
   d |= static_cast<uint64_t>(ROW_BYTES == 128 ? 2 : 4) << 61;         // SWIZZLE_128B / SWIZZLE_64B
   return d;
+}
+
+__device__ __forceinline__ void tma_load_4d_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_b(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 template <int BN, int BK, int KPS, bool GATHER, bool EPI>
@@ -183,6 +199,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * BN;
         const int m0 = (tile / p.n_tiles) * kBlockM;
+        int tp_clip = 0, tp_p0 = 0;  // pool_tp: tile = (clip, 32 pixels) x all 4 frames
+        if (EPI && p.pool_tp) {
+          const int mt = tile / p.n_tiles;
+          tp_clip = mt / p.tp_tiles_per_clip;
+          tp_p0 = (mt - tp_clip * p.tp_tiles_per_clip) * 32;
+        }
         int wq = 0, hq = 0, dq = 0, nq = 0;
         if (!GATHER && p.a_mode == A_TMA_IM2COL) {
           int t = m0;
@@ -206,7 +228,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < KPS; ++j) {
             if (j < nk) {
               if (!GATHER) {
-                if (p.a_mode == A_TMA_2D) {
+                if (EPI && p.pool_tp) {
+                  tma_load_4d_b(a_dst + j * Cfg::kABytes, &tmA, fb, (kb + j) * BK, tp_p0, 0, tp_clip);
+                } else if (p.a_mode == A_TMA_2D) {
                   tma_load_2d_a(a_dst + j * Cfg::kABytes, &tmA, fb, (kb + j) * BK, m0);
                 } else {
                   tma_load_im2col_5d_a(a_dst + j * Cfg::kABytes, &tmA, fb, c0, wq, hq, dq, nq, (uint16_t)dw, (uint16_t)dh,
@@ -229,8 +253,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int nsub = (p.N - n0 + 63) / 64;
             nsub = nsub > BN / 64 ? BN / 64 : nsub;
             mbar_arrive_expect_tx_a(res_full0 + rb * 8, (uint32_t)(nsub * Cfg::kEpiSubBytes));
-            for (int j = 0; j < nsub; ++j)
-              tma_load_2d_a(epi0 + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, res_full0 + rb * 8, n0 + 64 * j, m0);
+            for (int j = 0; j < nsub; ++j) {
+              if (p.pool_tp)
+                tma_load_4d_b(epi0 + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, res_full0 + rb * 8, n0 + 64 * j, tp_p0, 0, tp_clip);
+              else
+                tma_load_2d_a(epi0 + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, res_full0 + rb * 8, n0 + 64 * j, m0);
+            }
             if (++rb == NB) { rb = 0; rph ^= 1u; }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -385,6 +413,56 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         tc_fence_before();
+        if (p.pool_tp) {
+          // maxpool2 fused: tile rows are (frame = q, pixel = lane); frames (0,1) and (2,3) are max-reduced through the
+          // staging tile and only the pooled frame is stored.  Warp pairs (q, q ^ 1) of the same column half meet on a
+          // named barrier; the even-frame warp reduces and stores.
+          if (CPW == 64) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            const int pair_bar = 2 + (q >> 1) * 2 + (col0 >> 6);
+            named_bar_sync(pair_bar, 64);
+            {
+              // both warps of the pair reduce: lane = pixel, the even-frame warp takes the first 32 columns of the
+              // 64-column sub-tile, the odd-frame warp the other 32; results land in the even frame's rows
+              const uint32_t even_row = (uint32_t)((q & ~1) * 32 + lane);
+              const uint32_t sub = smem_u32(epi_base + eb * Cfg::kEpiBufBytes) + (uint32_t)(col0 >> 6) * Cfg::kEpiSubBytes + even_row * 128u;
+              const uint32_t xe = even_row & 7u;
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {
+                const uint32_t g = (uint32_t)((q & 1) * 4 + g4);
+                const uint32_t a0 = sub + ((g ^ xe) << 4);
+                const uint32_t a1 = a0 + 32u * 128u;  // same pixel, next frame (32 rows further: same swizzle phase)
+                uint32_t x[4], y[4];
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(a0));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]) : "r"(a1));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x[j]), *reinterpret_cast<const __nv_bfloat162*>(&y[j]));
+                  x[j] = *reinterpret_cast<const uint32_t*>(&m);
+                }
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
+              }
+              fence_proxy_async_smem();
+            }
+            named_bar_sync(pair_bar, 64);
+            if (!(q & 1) && lane == 0) {
+              const int mt = tile / p.n_tiles;
+              const int clip = mt / p.tp_tiles_per_clip;
+              const int p0 = (mt - clip * p.tp_tiles_per_clip) * 32;
+              if (n0 + col0 < p.N)
+                tma_store_4d_b(&tmO, smem_u32(epi_base + eb * Cfg::kEpiBufBytes) + (uint32_t)(col0 >> 6) * Cfg::kEpiSubBytes + (uint32_t)q * 32u * 128u,
+                               n0 + col0, p0, q >> 1, clip);
+              tma_store_commit();
+              tma_store_wait_read<0>();
+            }
+            __syncwarp();
+            if (lane == 0 && has_res) mbar_arrive(&res_empty_bar[eb]);
+            __syncwarp();
+          }
+          if (++eb == NB) { eb = 0; eph ^= 1u; }
+          continue;
+        }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0) {

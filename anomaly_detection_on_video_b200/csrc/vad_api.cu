@@ -100,6 +100,7 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
+  bool pool_tp = false;  // 1x1x1 residual conv with maxpool2 (2,1,1)/(2,1,1) fused into its staged epilogue
   bool s3 = false;       // spatial (1,3,3) 64 -> 64 kernel (conv_s3x3.cuh)
   S3x3Params s3p;
   bool thalo = false;    // temporal-halo kernel for (3,1,1) convs (conv_thalo.cuh)
@@ -185,8 +186,9 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: parameter offsets must be aligned (weights 128 B, scale/shift 16 B)", i);
       if (d.kt < 1 || d.kh < 1 || d.kw < 1 || d.st < 1 || d.sh < 1 || d.sw < 1 || d.pt < 0 || d.ph < 0 || d.pw < 0)
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad kernel/stride/pad", i);
-      if ((d.flags & VAD_FLAG_POOL_T2) && !fold)
-        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: POOL_T2 is fused into the stem kernel only (needs STEM_FOLD_W)", i);
+      if ((d.flags & VAD_FLAG_POOL_T2) && !fold &&
+          !(d.kt == 1 && d.kh == 1 && d.kw == 1 && d.st == 1 && d.sh == 1 && d.sw == 1 && d.res >= 0 && d.cout % 128 == 0 && d.cin % 64 == 0))
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: POOL_T2 needs the stem (STEM_FOLD_W) or a 1x1x1 residual conv with cout %% 128 == 0", i);
       if (fold && in_channels != 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs the stem input layout (in_channels == 0)", i);
       if (fold && (d.kw > 8 || d.src != 0 || (d.sw & 1)))
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs src=0, kw<=8, even sw", i);
@@ -362,6 +364,15 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         if (q.n_stages > ThaloCfg<64>::kMaxStages) q.n_stages = ThaloCfg<64>::kMaxStages;
         if (q.n_stages < 2) r.thalo = false;
       }
+      const bool pool_t2 = (d.flags & VAD_FLAG_POOL_T2) != 0;
+      r.pool_tp = false;
+      if (pool_t2 && !fold) {
+        // maxpool2 fused into a 1x1x1 residual conv: (all 4 frames x 32 pixels) tiles through the staged epilogue
+        if (!(r.epi && r.bn == 128 && r.a_mode == A_TMA_2D && src.T == 4 && r.kps == 1))
+          return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: POOL_T2 on a 1x1x1 conv needs 4 input frames, the staged epilogue and TMA operands", i);
+        r.pool_tp = true;
+        m_tiles = (long long)batch * ((src.H * Wi + 31) / 32);
+      }
       r.s3 = !p->no_s3 && r.a_mode == A_TMA_IM2COL && !fold && !r.epi && d.res < 0 && d.cin == 64 && d.cout == 64 && d.kt == 1 &&
              d.kh == 3 && d.kw == 3 && d.st == 1 && d.sh == 1 && d.sw == 1 && pt == 0 && ph == 1 && pw == 1 && sym_pad;
       if (r.s3) {
@@ -378,10 +389,10 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
       if (r.thalo) { r.tp.n_tiles = c.n_tiles; r.tp.num_tiles = c.num_tiles; }
+      if (r.pool_tp) { c.pool_tp = 1; c.tp_tiles_per_clip = (src.H * Wi + 31) / 32; }
       if (r.s3) r.s3p.num_tiles = c.num_tiles;
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
       r.stem = false;
-      const bool pool_t2 = (d.flags & VAD_FLAG_POOL_T2) != 0;
       if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0 && sym_pad &&
           d.kt * d.kh * kStemTapBytes <= 150 * 1024) {
         StemParams& q = r.sp;
@@ -421,7 +432,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
           r.grid = q.num_units < p->sm_count ? q.num_units : p->sm_count;
         }
       }
-      if (pool_t2) {
+      if (pool_t2 && fold) {
         if (!r.stem)
           return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: POOL_T2 needs the dedicated stem kernel (stride 2, cout 64, TMA input, "
                       "no residual)", i);
@@ -439,6 +450,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         c.ldr = rs.C;
         r.res_c = rs.C;
       }
+      if (r.pool_tp) To = To / 2;  // shape of the dst slot (the residual above has the unpooled shape)
       const int cin_real = fold ? 3 : d.cin;
       p->op_flops[i] = 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;  // frames the reference conv produces
       p->flops += p->op_flops[i];
@@ -551,6 +563,34 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         // residual [M, res_c] -> 128-row x 64-channel boxes; output slice [M, cout] (row pitch dst_c) <- 32-row boxes
         cuuint32_t es2[2] = {1, 1};
         CUresult cr;
+        if (r.pool_tp) {
+          // (channels, H*W, T, clips) views: residual boxes are 64 ch x 32 px x 4 frames, the pooled output 64 x 32 x 1
+          const uint64_t hw = (uint64_t)c.Ho * c.Wo;
+          cuuint32_t es4[4] = {1, 1, 1, 1};
+          cuuint64_t rdim[4] = {(cuuint64_t)r.res_c, hw, 4, (cuuint64_t)p->batch};
+          cuuint64_t rstr[3] = {(cuuint64_t)r.res_c * 2, (cuuint64_t)r.res_c * 2 * hw, (cuuint64_t)r.res_c * 2 * hw * 4};
+          cuuint32_t rbox[4] = {64, 32, 4, 1};
+          cr = p->encode_tiled(&r.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.res, rdim, rstr, rbox, es4,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cr == CUDA_SUCCESS) {
+            cuuint64_t odim[4] = {(cuuint64_t)d.cout, hw, 2, (cuuint64_t)p->batch};
+            cuuint64_t ostr[3] = {(cuuint64_t)r.dst_c * 2, (cuuint64_t)r.dst_c * 2 * hw, (cuuint64_t)r.dst_c * 2 * hw * 2};
+            cuuint32_t obox[4] = {64, 32, 1, 1};
+            cr = p->encode_tiled(&r.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c.out, odim, ostr, obox, es4,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          }
+          if (cr == CUDA_SUCCESS) {
+            cuuint64_t adim[4] = {(cuuint64_t)r.Ci, hw, 4, (cuuint64_t)p->batch};
+            cuuint64_t astr[3] = {(cuuint64_t)r.Ci * 2, (cuuint64_t)r.Ci * 2 * hw, (cuuint64_t)r.Ci * 2 * hw * 4};
+            cuuint32_t abox[4] = {64, 32, 4, 1};
+            cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(d.src), adim, astr, abox, es4,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          }
+          if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(fused temporal pool) failed: %d", i, (int)cr);
+        } else {
         if (d.res >= 0) {
           cuuint64_t rdim[2] = {(cuuint64_t)r.res_c, (cuuint64_t)c.M};
           cuuint64_t rstr[1] = {(cuuint64_t)r.res_c * 2};
@@ -567,6 +607,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(output) failed: %d", i, (int)cr);
+        }
       }
       if (r.stem) {
         // raw padded rows viewed as (x = Wp * 4 elements, H, T, N): a box is 88 contiguous elements (the union of
@@ -642,6 +683,8 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(temporal halo A) failed: %d", i, (int)cr);
+      } else if (r.pool_tp) {
+        // operand map encoded with the epilogue maps above
       } else if (r.a_mode == A_TMA_2D) {
         cuuint64_t gdim[2] = {(cuuint64_t)r.Ci, (cuuint64_t)c.M};
         cuuint64_t gstr[1] = {(cuuint64_t)r.Ci * 2};

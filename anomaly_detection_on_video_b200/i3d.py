@@ -67,6 +67,7 @@ class _NativeBackbone(nn.Module):
         self._plan_key = None
         self.force_gather = False  # debug: feed every conv through the cp.async gather producer
         self.fuse_stem_pool = True  # temporal half of maxpool1 in the stem epilogue (VAD_FLAG_POOL_T2)
+        self.fuse_pool2 = False     # maxpool2 in layer1's last conv3 epilogue; set per forward from the clip length
 
     # subclasses return (ops, packer, n_slots)
     def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
@@ -91,7 +92,7 @@ class _NativeBackbone(nn.Module):
         return tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers()))
 
     def plan(self, device: torch.device) -> BackbonePlan:
-        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool)
+        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool, self.fuse_pool2)
         if self._plan is None or self._plan_key != key:
             ops, packer, n_slots = self._build_table()
             self._plan = BackbonePlan(ops, packer.blob(), n_slots, self.pad_left, device)
@@ -105,7 +106,11 @@ class _NativeBackbone(nn.Module):
         """bf16 stem-layout clips [B, T, H, W+8, 4] (what ``Preprocessor`` emits) -> [B, C] fp32."""
         if self.training:
             raise RuntimeError("the native backbone is inference-only: call .eval() first (extract_features.py:36)")
+        self._select_fusions(int(x_stem.shape[1]))
         return self.plan(x_stem.device).forward(x_stem)
+
+    def _select_fusions(self, clip_len: int) -> None:
+        """Hook: pick the op-table variant for this clip length (plans are cached per variant)."""
 
     def forward(self, batch: torch.Tensor) -> torch.Tensor:
         """[B, 3, T, H, W] fp32 on the GPU -> [B, C, 1, 1, 1] fp32 (reference src/i3d.py:302-318)."""
@@ -145,6 +150,14 @@ class I3Res50(_NativeBackbone):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
 
+    allow_fuse_pool2 = True
+
+    def _select_fusions(self, clip_len: int) -> None:
+        # frames entering layer1: stem (k5, s2, p2) then maxpool1's temporal half (k2, s2); the fused maxpool2 epilogue
+        # is built for exactly four of them (16-frame clips, the reference's frames_per_clip)
+        t1 = ((clip_len + 4 - 5) // 2 + 1) // 2
+        self.fuse_pool2 = bool(self.allow_fuse_pool2 and self.fuse_stem_pool and t1 == 4)
+
     def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
         pk = ParamPacker()
         ops: List[Op] = []
@@ -171,9 +184,17 @@ class I3Res50(_NativeBackbone):
                 if blk.downsample is not None:
                     ops.append(self._conv_op(pk, blk.downsample[0], blk.downsample[1], cur, DS, relu=False, name=n + ".downsample"))
                     res = DS
-                ops.append(self._conv_op(pk, blk.conv3, blk.bn3, T2, nxt, relu=True, res=res, name=n + ".conv3"))
+                conv3 = self._conv_op(pk, blk.conv3, blk.bn3, T2, nxt, relu=True, res=res, name=n + ".conv3")
+                last_of_layer1 = li == 1 and bi == len(getattr(self, "layer1")) - 1
+                if last_of_layer1 and self.fuse_pool2 and not self.force_gather:
+                    # maxpool2 = max over frame pairs (reference src/i3d.py:215-217,309) in conv3's staged epilogue: the
+                    # unpooled block output (991 MB per 160 clips) is never written and no pool kernel runs.  Needs the
+                    # 4-frame feature map of a 16-frame clip; other clip lengths take the separate pool below.
+                    conv3.flags |= _lib.VAD_FLAG_POOL_T2
+                    conv3.name = n + ".conv3+maxpool2"
+                ops.append(conv3)
                 cur = nxt
-            if li == 1:
+            if li == 1 and not (self.fuse_pool2 and not self.force_gather):
                 nxt = 1 if cur == 2 else 2
                 ops.append(Op(kind=_lib.VAD_OP_MAXPOOL, src=cur, dst=nxt, kernel=(2, 1, 1), stride=(2, 1, 1), name="maxpool2"))
                 cur = nxt

@@ -279,3 +279,39 @@ def test_add_magnitude(cuda_device):
     ref = S.add_magnitude(f)
     assert out.shape == (10, 32, 2049) and np.array_equal(out[..., :2048], f)
     np.testing.assert_allclose(out[..., 2048], ref[..., 2048], rtol=1e-6)
+
+
+@pytest.mark.parametrize("H,W,cin,cout", [(9, 7, 256, 256), (55, 55, 256, 256), (5, 6, 256, 128)])
+def test_conv3_fused_temporal_pool_is_exact(cuda_device, H, W, cin, cout):
+    """VAD_FLAG_POOL_T2 on a 1x1x1 residual conv (maxpool2 fused into layer1's last conv3): bit-identical to the unfused
+    conv followed by a (2,1,1)/(2,1,1) max-pool, including ragged 32-pixel tiles at the end of a frame.  The residual is
+    the conv input itself (copied into slot 1 by an identity 1x1x1 max-pool), so cout <= cin."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+
+    g = torch.Generator().manual_seed(21)
+    B, T = 2, 4
+    x = torch.randn(B, cin, T, H, W, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 1, 1, 1, generator=g) * (2.0 / cin) ** 0.5).to(torch.bfloat16)
+    scale, shift = 0.5 + torch.rand(cout, generator=g), 0.2 * torch.randn(cout, generator=g)
+    scale[::5] *= -1.0
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w.float(), scale, shift)
+    xg = x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device)
+    outs = []
+    for fused in (False, True):
+        ops = [eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=1, kernel=(1, 1, 1), stride=(1, 1, 1)),
+               eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=2, res=1, cin=cin, cout=cout, kernel=(1, 1, 1), stride=(1, 1, 1), pad=(0, 0, 0),
+                      flags=lib.VAD_FLAG_RELU | (lib.VAD_FLAG_POOL_T2 if fused else 0), w_off=w_off, scale_off=s_off, shift_off=b_off)]
+        if not fused:
+            ops.append(eng.Op(kind=lib.VAD_OP_MAXPOOL, src=2, dst=3, kernel=(2, 1, 1), stride=(2, 1, 1)))
+        plan = eng.BackbonePlan(ops, pk.blob(), 4, 0, cuda_device, in_channels=cin)
+        plan.forward(xg)
+        torch.cuda.synchronize()
+        outs.append(plan.slot_tensor(2 if fused else 3).float().cpu())
+    assert outs[0].shape == outs[1].shape == (B, 2, H, W, cout)
+    assert torch.equal(outs[0], outs[1])
+    ref = torch.relu(torch.nn.functional.conv3d(x.float(), w.float()) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1) + x.float()[:, :cout])
+    ref = torch.nn.functional.max_pool3d(ref, (2, 1, 1), (2, 1, 1)).permute(0, 2, 3, 4, 1)
+    from gpu_util import assert_bf16_close
+
+    assert_bf16_close(outs[1], ref)
