@@ -100,6 +100,7 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
+  bool mc = false;       // cluster-of-2 kernel with the weight tile multicast (BN = 256, TMA operands, direct epilogue)
   bool pool_tp = false;  // 1x1x1 residual conv with maxpool2 (2,1,1)/(2,1,1) fused into its staged epilogue
   bool s3 = false;       // spatial (1,3,3) 64 -> 64 kernel (conv_s3x3.cuh)
   S3x3Params s3p;
@@ -130,6 +131,9 @@ struct vad_plan {
   bool no_s3 = false;        // VAD_NO_S3X3=1: layer1's (1,3,3) convs through the generic im2col kernel
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
+  int mc_min_tiles = -1;     // VAD_MC_MIN_TILES=<n>: use the cluster-multicast kernel from n m-tiles on.  Off by default: measured
+                             // neutral (layer3/4 are not bound by weight traffic), kept as a verified building block
+  int l2_ahead = 0;          // VAD_L2_AHEAD=<n>: residual tiles prefetched into L2 n iterations ahead (staged epilogue)
   int bn_model = 0;          // VAD_BN_MODEL=<pct>: prefer BN=128 over 256 when its modelled time is below pct % (tuning)
   int kps_override = 0;      // VAD_KPS=1|2: force k-blocks per stage (tuning only)
   bool stem_gather = false;  // VAD_STEM_GATHER=1: feed the stem through the cp.async gather producer
@@ -222,6 +226,8 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_NO_S3X3"); p->no_s3 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_MC_MIN_TILES"); p->mc_min_tiles = k ? atoi(k) : -1; }
+  { const char* k = getenv("VAD_L2_AHEAD"); p->l2_ahead = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_BN_MODEL"); p->bn_model = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_KPS"); p->kps_override = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_EPI_ALL"); p->epi_all = k && k[0] == '1'; }
@@ -388,7 +394,14 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       c.n_tiles = (int)n_tiles;
       c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
+      r.mc = r.bn == 256 && !r.epi && r.a_mode != A_GATHER && r.bk == 64 && r.kps == 1 && !r.thalo && !r.s3 && !r.stem &&
+             d.cout % 256 == 0 && (p->sm_count % 2) == 0 && p->mc_min_tiles >= 0 && m_tiles >= p->mc_min_tiles;
+      if (r.mc) {
+        c.mc_items = (int)(((m_tiles + 1) / 2) * n_tiles);
+        r.grid = 2 * c.mc_items < p->sm_count ? 2 * c.mc_items : p->sm_count;  // whole clusters, each with at least one item
+      }
       if (r.thalo) { r.tp.n_tiles = c.n_tiles; r.tp.num_tiles = c.num_tiles; }
+      c.l2_ahead = (r.epi && d.res >= 0) ? p->l2_ahead : 0;
       if (r.pool_tp) { c.pool_tp = 1; c.tp_tiles_per_clip = (src.H * Wi + 31) / 32; }
       if (r.s3) r.s3p.num_tiles = c.num_tiles;
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
@@ -559,6 +572,17 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
       memset(&r.tmA, 0, sizeof(r.tmA));
       memset(&r.tmR, 0, sizeof(r.tmR));
       memset(&r.tmO, 0, sizeof(r.tmO));
+      if (r.mc) {
+        // each CTA of a pair loads half of the BN weight rows and multicasts them
+        cuuint64_t gdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)r.K_pad * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)(r.bn / 2)};
+        cuuint32_t es[2] = {1, 1};
+        CUresult cr = p->encode_tiled(&r.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), gdim, gstr, box, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(weight halves) failed: %d", i, (int)cr);
+      }
       if (r.epi) {
         // residual [M, res_c] -> 128-row x 64-channel boxes; output slice [M, cout] (row pitch dst_c) <- 32-row boxes
         cuuint32_t es2[2] = {1, 1};
@@ -772,7 +796,33 @@ static cudaError_t launch_conv_bn(const OpRuntime& r, cudaStream_t st) {
   return launch_conv<BN, 64, 1, false, EPI>(r, st);
 }
 
+static cudaError_t launch_conv_mc(const OpRuntime& r, cudaStream_t st) {
+  using Cfg = ConvCfg<256, 64, 1, false, false>;
+  auto kern = conv_umma_kernel<256, 64, 1, false, false, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(r.grid);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
+}
+
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
+  if (r.mc) return launch_conv_mc(r, st);
   if (r.bk == 32) return launch_conv<64, 32, 1, false, false>(r, st);  // folded stem, TMA window view
   if (r.epi) return r.bn == 128 ? launch_conv_bn<128, true>(r, st) : launch_conv_bn<64, true>(r, st);
   switch (r.bn) {

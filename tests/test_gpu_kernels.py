@@ -315,3 +315,27 @@ def test_conv3_fused_temporal_pool_is_exact(cuda_device, H, W, cin, cout):
     from gpu_util import assert_bf16_close
 
     assert_bf16_close(outs[1], ref)
+
+
+MC_CASES = [
+    ("1x1 512->256 odd m-tiles", 512, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 14, 14),   # M = 392: 4 m-tiles -> 2 pairs
+    ("1x1 256->512 tail pair", 256, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 13, 13),      # M = 338: 3 m-tiles -> odd CTA idles
+    ("s3x3 256->256 im2col", 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 2, 14, 14),
+    ("t3 512->256 K=1536", 512, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0), 3, 2, 10, 13),
+    ("1x1 stride 2 512->1024 ds", 512, 1024, (1, 1, 1), (1, 2, 2), (0, 0, 0), 2, 2, 28, 28),
+]
+
+
+@pytest.mark.parametrize("case", MC_CASES, ids=[c[0] for c in MC_CASES])
+def test_cluster_multicast_kernel_matches_the_plain_kernel(cuda_device, case, monkeypatch):
+    """The cluster-of-2 kernel (weight tile multicast through thread-block clusters, BN = 256) is off by default (measured
+    neutral on this network); VAD_MC_MIN_TILES=2 switches it on, incl. for an odd number of m-tiles where the second CTA
+    of the last pair has no rows.  Bit-identical to the plain kernel."""
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    monkeypatch.delenv("VAD_MC_MIN_TILES", raising=False)
+    plain, ref = run_conv_case(*case[1:], False, True)
+    monkeypatch.setenv("VAD_MC_MIN_TILES", "2")
+    mc, _ = run_conv_case(*case[1:], False, True)
+    assert_bf16_close(mc, ref)
+    assert torch.equal(mc, plain)
