@@ -83,17 +83,27 @@ class FrameSource:
         return np.stack([self._reader[i].asnumpy() for i in range(start, stop)])
 
 
+def _from_numpy_readonly(a: np.ndarray) -> torch.Tensor:
+    """``torch.from_numpy`` without the non-writable warning: memory-mapped / read-only frame arrays are only ever read
+    (they are copied to pinned memory or to the GPU next)."""
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+        return torch.from_numpy(a)
+
+
 def _frames_to_tensor(src) -> torch.Tensor:
     """Any accepted frame container -> uint8 [n, H, W, 3] tensor (CPU or already on the GPU)."""
     if isinstance(src, torch.Tensor):
         t = src
     elif isinstance(src, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(src))
+        t = _from_numpy_readonly(np.ascontiguousarray(src))
     elif isinstance(src, FrameSource):
-        t = torch.from_numpy(src.read(0, len(src)))
+        t = _from_numpy_readonly(src.read(0, len(src)))
     elif isinstance(src, str):
         fs = FrameSource(src)
-        t = torch.from_numpy(fs.read(0, len(fs)))
+        t = _from_numpy_readonly(fs.read(0, len(fs)))
     elif isinstance(src, (list, tuple)) and len(src) > 0 and Image is not None and isinstance(src[0], Image.Image):
         t = torch.from_numpy(np.stack([np.asarray(im.convert("RGB")) for im in src]))
     else:
