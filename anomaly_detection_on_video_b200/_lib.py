@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "vad_plan_num_launches",
     "vad_plan_flops",
     "vad_plan_profile_begin",
+    "vad_plan_profile_select",
     "vad_plan_profile_end",
     "vad_plan_destroy",
     "vad_ingest_ncthw_f32",
@@ -128,6 +129,8 @@ def load() -> ctypes.CDLL:
     lib.vad_plan_flops.argtypes = [c_void_p]
     lib.vad_plan_profile_begin.restype = c_int32
     lib.vad_plan_profile_begin.argtypes = [c_void_p]
+    lib.vad_plan_profile_select.restype = c_int32
+    lib.vad_plan_profile_select.argtypes = [c_void_p, c_int32, c_int32]
     lib.vad_plan_profile_end.restype = c_int32
     lib.vad_plan_profile_end.argtypes = [c_void_p, c_int32, POINTER(c_double), POINTER(c_int32), POINTER(c_double), POINTER(c_double)]
     lib.vad_plan_destroy.restype = None

@@ -90,6 +90,7 @@ conv_s3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected thread)
@@ -100,6 +101,7 @@ conv_s3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive_expect_tx_a(wb, (uint32_t)kS3WBytes);
         for (int tap = 0; tap < 9; ++tap) tma_load_2d_a(w0 + (uint32_t)tap * 8192u, &tmW, wb, tap * 64, 0);
       }
+      griddep_wait();  // weights are constants; the activations come from the preceding kernel
       uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int r = tile;
@@ -167,6 +169,7 @@ conv_s3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..9
+    griddep_wait();
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const bool issuer = half == 0;

@@ -100,6 +100,7 @@ conv_thalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected thread)
@@ -113,6 +114,7 @@ conv_thalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int dt = 0; dt < 3; ++dt)
             tma_load_2d_a(w0 + (uint32_t)(cb * 3 + dt) * Cfg::kBBytes, &tmB, wb, dt * p.Cin + cb * 64, 0);
       }
+      griddep_wait();  // weights are constants; the activations come from the preceding kernel
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * BN;
         const int mt = tile / p.n_tiles;
@@ -194,6 +196,7 @@ conv_thalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ------------------------------------------------------------------ epilogue warps
     constexpr int CPW = Cfg::kColsPerWarp;
+    griddep_wait();
     const int t = threadIdx.x - 64;
     const int q = warp & 3;
     const int col0 = ((warp - 2) >> 2) * CPW;

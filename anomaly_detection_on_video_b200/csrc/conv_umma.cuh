@@ -199,6 +199,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // the next kernel of the stream may begin its own prologue as SMs free up
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -209,6 +210,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t res_full0 = smem_u32(res_full_bar), res_empty0 = smem_u32(res_empty_bar), epi0 = smem_u32(epi_base);
       uint32_t s = 0, ph = 0;    // ring slot and its phase
       uint32_t rb = 0, rph = 0;  // epilogue buffer of this tile and its phase
+      griddep_wait();            // activations / residuals of the previous kernel are complete from here on
       for (int tile = w_first; tile < w_total; tile += w_step) {
         const int n0 = (tile % p.n_tiles) * BN;
         const int m0 = m_tile_of(tile) * kBlockM;
@@ -376,6 +378,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp < 2 + Cfg::kEpiWarps) {
     // ------------------------------------------------------------------ epilogue warps
     constexpr int CPW = Cfg::kColsPerWarp;
+    griddep_wait();  // this role reads (residual) and overwrites activation slots of earlier kernels
     const int t = threadIdx.x - 64;   // 0 .. kEpiThreads-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int col0 = ((warp - 2) >> 2) * CPW;  // first tile column of this warp
@@ -567,6 +570,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ gather warps (GATHER only)
     if (GATHER) {
       constexpr int LAG = Cfg::kGatherLag;
+      griddep_wait();
       const int t = threadIdx.x - (64 + Cfg::kEpiThreads);  // 0..127: tile row owned by this thread
       const uint32_t sw_xor = (uint32_t)(t & 7);
       int g = 0;  // k-blocks issued so far (across tiles)

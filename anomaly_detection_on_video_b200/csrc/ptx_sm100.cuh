@@ -217,6 +217,13 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
                : "memory");
 }
 
+// ---- programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// (barrier init, TMEM allocation, loads of constant weights) while its predecessor in the stream is still draining;
+// griddep_wait() blocks until the predecessor grid has completed and its writes are visible.  Both are no-ops for a
+// normally launched kernel.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------- cp.async
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)

@@ -130,6 +130,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected thread)
@@ -137,6 +138,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
       mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
       for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
+      griddep_wait();  // the weights are constants; the clips come from the preceding preprocessing kernel
       const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * p.seg_bytes);
       uint32_t s = 0, ph = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -231,6 +233,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..5
+    griddep_wait();
     const int q = warp & 3;
     const int lrow = q * 32 + lane;  // tile row = TMEM lane: (h_i, w_i) = (lrow / 8, lrow % 8)
     const uint32_t xr = (uint32_t)(lrow & 7);
@@ -403,6 +406,7 @@ stem_umma_mf_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected thread)
@@ -415,6 +419,7 @@ stem_umma_mf_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
                                   : w_smem + (uint32_t)(dh * 3 + (4 - dt) / 2) * kStemTapBytes;
           tma_load_2d(dst, &tmW, w_bar, (dt * p.kh + dh) * 32, 0);
         }
+      griddep_wait();  // weights are constants; the clips come from the preceding preprocessing kernel
       const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * p.seg_bytes);
       uint32_t s = 0, ph = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -573,6 +578,7 @@ stem_umma_mf_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_consta
     // ------------------------------------------------------------------ epilogue warps 2..9
     // two warps per TMEM lane quarter, 32 of the 64 channels each; the pair shares one 32-row x 128-byte slice of the
     // staging tile (named barrier 1 + q) and warp 2 + q issues the TMA store
+    griddep_wait();
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const bool issuer = half == 0;

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "aux_kernels.cuh"
@@ -38,6 +39,8 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
       return fail(VAD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
                   __LINE__);                                                                       \
   } while (0)
+
+static bool g_pdl = true;  // VAD_NO_PDL=1 switches programmatic dependent launch off (read at plan creation)
 
 extern "C" const char* vad_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t vad_abi_version(void) { return VAD_ABI_VERSION; }
@@ -151,6 +154,7 @@ struct vad_plan {
   int driver_version = 0;
   // optional per-op timing (vad_plan_profile_begin/end): events bracket every launch
   bool profiling = false;
+  int prof_first = 0, prof_count = -1;  // ops bracketed by events (vad_plan_profile_select); -1: all
   std::vector<cudaEvent_t> ev_pool;   // recycled events
   std::vector<cudaEvent_t> ev_used;   // (n_ops + 1) events per profiled forward, in order
   std::vector<double> op_flops;       // useful FLOPs per op at the configured size
@@ -227,6 +231,7 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
   { const char* k = getenv("VAD_MC_MIN_TILES"); p->mc_min_tiles = k ? atoi(k) : -1; }
+  { const char* k = getenv("VAD_NO_PDL"); g_pdl = !(k && k[0] == '1'); }
   { const char* k = getenv("VAD_L2_AHEAD"); p->l2_ahead = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_BN_MODEL"); p->bn_model = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_KPS"); p->kps_override = k ? atoi(k) : 0; }
@@ -775,6 +780,37 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
   return VAD_OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel may begin (barrier init, TMEM allocation,
+// loads of constant weights) while its predecessor in the stream is still draining; every kernel launched this way
+// executes griddepcontrol.wait before it touches anything a predecessor wrote.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, int cluster,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)cluster;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int BN, int BK, int KPS, bool GATHER, bool EPI>
 static cudaError_t launch_conv(const OpRuntime& r, cudaStream_t st) {
   using Cfg = ConvCfg<BN, BK, KPS, GATHER, EPI>;
@@ -785,8 +821,7 @@ static cudaError_t launch_conv(const OpRuntime& r, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_umma_kernel<BN, BK, KPS, GATHER, EPI><<<r.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
-  return cudaGetLastError();
+  return launch_k(conv_umma_kernel<BN, BK, KPS, GATHER, EPI>, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
 }
 
 template <int BN, bool EPI>
@@ -805,20 +840,7 @@ static cudaError_t launch_conv_mc(const OpRuntime& r, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(r.grid);
-  cfg.blockDim = dim3(Cfg::kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
+  return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 2, r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
 }
 
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
@@ -861,8 +883,10 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
     p->ev_used.push_back(ev);
     return cudaEventRecord(ev, st);
   };
-  if (mark() != cudaSuccess) return fail(VAD_ERR_CUDA, "profiling event failed");
+  const int pf0 = p->prof_count < 0 ? 0 : p->prof_first;
+  const int pf1 = p->prof_count < 0 ? (int)p->ops.size() : p->prof_first + p->prof_count;  // events before ops pf0..pf1-1 and after op pf1-1
   for (size_t i = 0; i < p->ops.size(); ++i) {
+    if ((int)i >= pf0 && (int)i < pf1 && mark() != cudaSuccess) return fail(VAD_ERR_CUDA, "profiling event failed");
     const vad_op_desc& d = p->ops[i];
     const OpRuntime& r = p->rt[i];
     cudaError_t e = cudaSuccess;
@@ -888,8 +912,7 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
             mp.s.clk_out = want_clk ? clk_dev : nullptr;
             mp.Ti = r.stem_ti;
             mp.ti_max = r.stem_ti_max;
-            stem_umma_mf_kernel<<<r.grid, kStemMfThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, mp);
-            e = cudaGetLastError();
+            e = launch_k(stem_umma_mf_kernel, r.grid, kStemMfThreads, (size_t)r.stem_smem, st, g_pdl, 1, r.tmE, r.tmOdd, r.tmW, r.tmSO, mp);
             if (want_clk && e == cudaSuccess) {  // debug only: synchronises
               long long hclk[3] = {0, 0, 0};
               cudaStreamSynchronize(st);
@@ -899,15 +922,13 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
             }
           }
         } else if (e == cudaSuccess) {
-          stem_umma_kernel<<<r.grid, kStemThreads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, r.sp);
-          e = cudaGetLastError();
+          e = launch_k(stem_umma_kernel, r.grid, kStemThreads, (size_t)r.stem_smem, st, g_pdl, 1, r.tmE, r.tmOdd, r.tmW, r.tmSO, r.sp);
         }
       } else if (r.s3) {
         static bool attr = false;
         if (!attr) { e = cudaFuncSetAttribute(conv_s3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes); attr = (e == cudaSuccess); }
         if (e == cudaSuccess) {
-          conv_s3x3_kernel<<<r.grid, kS3Threads, kS3SmemBytes, st>>>(r.tmA, r.tmB, r.tmO, r.s3p);
-          e = cudaGetLastError();
+          e = launch_k(conv_s3x3_kernel, r.grid, kS3Threads, (size_t)kS3SmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmO, r.s3p);
         }
       } else if (r.thalo) {
         const int w_all = r.tp.resident ? 3 * (r.tp.Cin / 64) * r.bn * 128 : 0;
@@ -915,12 +936,12 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
           const int smem = w_all + r.tp.n_stages * r.tp.stage_bytes + ThaloCfg<128>::kFixedBytes;
           static bool attr = false;
           if (!attr) { e = cudaFuncSetAttribute(conv_thalo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = (e == cudaSuccess); }
-          if (e == cudaSuccess) conv_thalo_kernel<128><<<r.grid, ThaloCfg<128>::kThreads, smem, st>>>(r.tmA, r.tmB, r.tp);
+          if (e == cudaSuccess) e = launch_k(conv_thalo_kernel<128>, r.grid, ThaloCfg<128>::kThreads, (size_t)smem, st, g_pdl, 1, r.tmA, r.tmB, r.tp);
         } else {
           const int smem = w_all + r.tp.n_stages * r.tp.stage_bytes + ThaloCfg<64>::kFixedBytes;
           static bool attr = false;
           if (!attr) { e = cudaFuncSetAttribute(conv_thalo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = (e == cudaSuccess); }
-          if (e == cudaSuccess) conv_thalo_kernel<64><<<r.grid, ThaloCfg<64>::kThreads, smem, st>>>(r.tmA, r.tmB, r.tp);
+          if (e == cudaSuccess) e = launch_k(conv_thalo_kernel<64>, r.grid, ThaloCfg<64>::kThreads, (size_t)smem, st, g_pdl, 1, r.tmA, r.tmB, r.tp);
         }
         if (e == cudaSuccess) e = cudaGetLastError();
       } else {
@@ -953,9 +974,19 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
       e = cudaGetLastError();
     }
     if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "op %zu launch failed: %s", i, cudaGetErrorString(e));
-    if (mark() != cudaSuccess) return fail(VAD_ERR_CUDA, "profiling event failed");
-    if (p->profiling) { p->prof_flops[i] += p->op_flops[i]; p->prof_bytes[i] += p->op_bytes[i]; }
+    if ((int)i == pf1 - 1 && mark() != cudaSuccess) return fail(VAD_ERR_CUDA, "profiling event failed");
+    if (p->profiling && (int)i >= pf0 && (int)i < pf1) { p->prof_flops[i] += p->op_flops[i]; p->prof_bytes[i] += p->op_bytes[i]; }
   }
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_plan_profile_select(vad_plan_t* p, int32_t first_op, int32_t n_ops) {
+  if (!p) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_profile_select: null plan");
+  if (p->profiling) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_profile_select: profiling is running");
+  if (n_ops < 0) { p->prof_first = 0; p->prof_count = -1; return VAD_OK; }
+  if (first_op < 0 || n_ops == 0 || first_op + n_ops > (int32_t)p->ops.size())
+    return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_profile_select: ops [%d, %d) out of range", first_op, first_op + n_ops);
+  p->prof_first = first_op; p->prof_count = n_ops;
   return VAD_OK;
 }
 
@@ -983,13 +1014,15 @@ extern "C" int32_t vad_plan_profile_end(vad_plan_t* p, int32_t n_ops, double* op
   }
   if (p->ev_used.empty()) return VAD_OK;
   VAD_CUDA_CHECK(cudaEventSynchronize(p->ev_used.back()));
-  const size_t per = n + 1;
+  const size_t first = p->prof_count < 0 ? 0 : (size_t)p->prof_first;
+  const size_t cnt = p->prof_count < 0 ? n : (size_t)p->prof_count;
+  const size_t per = cnt + 1;
   for (size_t f = 0; f + per <= p->ev_used.size(); f += per) {
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = 0; i < cnt; ++i) {
       float ms = 0.f;
       VAD_CUDA_CHECK(cudaEventElapsedTime(&ms, p->ev_used[f + i], p->ev_used[f + i + 1]));
-      if (op_ms_sum) op_ms_sum[i] += ms;
-      if (op_calls) op_calls[i] += 1;
+      if (op_ms_sum) op_ms_sum[first + i] += ms;
+      if (op_calls) op_calls[first + i] += 1;
     }
   }
   for (cudaEvent_t e : p->ev_used) p->ev_pool.push_back(e);

@@ -174,7 +174,9 @@ class BackbonePlan:
     def num_launches(self) -> int:
         return int(self.lib.vad_plan_num_launches(self._h))
 
-    def profile_begin(self) -> None:
+    def profile_begin(self, first_op: int = 0, n_ops: int = -1) -> None:
+        """Bracket every launch (default) or only ops [first_op, first_op + n_ops) with CUDA events."""
+        check(self.lib.vad_plan_profile_select(self._h, first_op, n_ops), "vad_plan_profile_select")
         check(self.lib.vad_plan_profile_begin(self._h), "vad_plan_profile_begin")
 
     def profile_end(self) -> List[Dict[str, object]]:

@@ -134,6 +134,10 @@ double vad_plan_flops(const vad_plan_t* plan);
  * the last event and returns, per op, totals over the timed launches: milliseconds, launch count,
  * useful FLOPs and algorithmic bytes (each input / output tensor touched once). */
 int32_t vad_plan_profile_begin(vad_plan_t* plan);
+/* Restrict the events to ops [first_op, first_op + n_ops) (n_ops < 0: all ops again).  Event records between kernels
+ * keep consecutive kernels from overlapping their prologues (programmatic dependent launch), so a timed run that only
+ * needs the dominant kernel's duration brackets just that one. */
+int32_t vad_plan_profile_select(vad_plan_t* plan, int32_t first_op, int32_t n_ops);
 int32_t vad_plan_profile_end(vad_plan_t* plan, int32_t n_ops, double* op_ms_sum, int32_t* op_calls,
                              double* op_flops, double* op_bytes);
 
