@@ -17,6 +17,7 @@
 #include "stem_umma.cuh"
 #include "conv_thalo.cuh"
 #include "conv_s3x3.cuh"
+#include "conv_pair.cuh"
 
 using namespace vad;
 
@@ -103,6 +104,7 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
+  bool pair = false;     // CTA-pair kernel (tcgen05 cta_group::2, 256 x BN tiles): BN = 256 layers with TMA operands and the direct epilogue
   bool mc = false;       // cluster-of-2 kernel with the weight tile multicast (BN = 256, TMA operands, direct epilogue)
   bool pool_tp = false;  // 1x1x1 residual conv with maxpool2 (2,1,1)/(2,1,1) fused into its staged epilogue
   bool s3 = false;       // spatial (1,3,3) 64 -> 64 kernel (conv_s3x3.cuh)
@@ -134,6 +136,8 @@ struct vad_plan {
   bool no_s3 = false;        // VAD_NO_S3X3=1: layer1's (1,3,3) convs through the generic im2col kernel
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
+  int pair_mode = 1;         // VAD_PAIR=0: never use the CTA-pair kernel; 1 (default): for the long-K layers without residual
+  int pair_min_kb = 12;      // VAD_PAIR_MIN_KB: fewest 64-wide k-blocks for which a layer goes to the CTA-pair kernel
   int mc_min_tiles = -1;     // VAD_MC_MIN_TILES=<n>: use the cluster-multicast kernel from n m-tiles on.  Off by default: measured
                              // neutral (layer3/4 are not bound by weight traffic), kept as a verified building block
   int l2_ahead = 0;          // VAD_L2_AHEAD=<n>: residual tiles prefetched into L2 n iterations ahead (staged epilogue)
@@ -230,6 +234,8 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_NO_S3X3"); p->no_s3 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_PAIR"); p->pair_mode = k ? atoi(k) : 1; }
+  { const char* k = getenv("VAD_PAIR_MIN_KB"); p->pair_min_kb = k ? atoi(k) : 12; }
   { const char* k = getenv("VAD_MC_MIN_TILES"); p->mc_min_tiles = k ? atoi(k) : -1; }
   { const char* k = getenv("VAD_NO_PDL"); g_pdl = !(k && k[0] == '1'); }
   { const char* k = getenv("VAD_L2_AHEAD"); p->l2_ahead = k ? atoi(k) : 0; }
@@ -401,7 +407,10 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
       r.mc = r.bn == 256 && !r.epi && r.a_mode != A_GATHER && r.bk == 64 && r.kps == 1 && !r.thalo && !r.s3 && !r.stem &&
              d.cout % 256 == 0 && (p->sm_count % 2) == 0 && p->mc_min_tiles >= 0 && m_tiles >= p->mc_min_tiles;
-      if (r.mc) {
+      // CTA pairs pay off where the L2 -> shared-memory path is the limit (long K); short-K layers are output bound
+      r.pair = !r.mc && p->pair_mode > 0 && (r.bn == 256 || r.bn == 128) && !r.epi && r.a_mode != A_GATHER && r.bk == 64 && !r.thalo && !r.s3 &&
+               !r.pool_tp && d.cout % r.bn == 0 && (p->sm_count % 2) == 0 && m_tiles >= 2 && c.num_kb >= p->pair_min_kb;
+      if (r.mc || r.pair) {
         c.mc_items = (int)(((m_tiles + 1) / 2) * n_tiles);
         r.grid = 2 * c.mc_items < p->sm_count ? 2 * c.mc_items : p->sm_count;  // whole clusters, each with at least one item
       }
@@ -577,8 +586,8 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
       memset(&r.tmA, 0, sizeof(r.tmA));
       memset(&r.tmR, 0, sizeof(r.tmR));
       memset(&r.tmO, 0, sizeof(r.tmO));
-      if (r.mc) {
-        // each CTA of a pair loads half of the BN weight rows and multicasts them
+      if (r.mc || r.pair) {
+        // each CTA of a pair loads half of the BN weight rows (mc: and multicasts them)
         cuuint64_t gdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
         cuuint64_t gstr[1] = {(cuuint64_t)r.K_pad * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)(r.bn / 2)};
@@ -843,7 +852,24 @@ static cudaError_t launch_conv_mc(const OpRuntime& r, cudaStream_t st) {
   return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 2, r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
 }
 
+template <int BN, int KPS>
+static cudaError_t launch_conv_pair_t(const OpRuntime& r, cudaStream_t st) {
+  using Cfg = PairCfg<BN, KPS>;
+  auto kern = conv_pair_kernel<BN, KPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 2, r.tmA, r.tmR, r.cp);
+}
+static cudaError_t launch_conv_pair(const OpRuntime& r, cudaStream_t st) {
+  return r.bn == 256 ? launch_conv_pair_t<256, 1>(r, st) : launch_conv_pair_t<128, 2>(r, st);
+}
+
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
+  if (r.pair) return launch_conv_pair(r, st);
   if (r.mc) return launch_conv_mc(r, st);
   if (r.bk == 32) return launch_conv<64, 32, 1, false, false>(r, st);  // folded stem, TMA window view
   if (r.epi) return r.bn == 128 ? launch_conv_bn<128, true>(r, st) : launch_conv_bn<64, true>(r, st);

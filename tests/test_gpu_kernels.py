@@ -334,8 +334,36 @@ def test_cluster_multicast_kernel_matches_the_plain_kernel(cuda_device, case, mo
     from gpu_util import assert_bf16_close, run_conv_case
 
     monkeypatch.delenv("VAD_MC_MIN_TILES", raising=False)
+    monkeypatch.setenv("VAD_PAIR", "0")
     plain, ref = run_conv_case(*case[1:], False, True)
     monkeypatch.setenv("VAD_MC_MIN_TILES", "2")
     mc, _ = run_conv_case(*case[1:], False, True)
     assert_bf16_close(mc, ref)
     assert torch.equal(mc, plain)
+
+
+PAIR_CASES = MC_CASES + [
+    ("1x1 1024->512 many items", 1024, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 4, 4, 28, 28),   # 98 m-tiles x 2 n-tiles: 98 items on 74 pairs
+    ("s3x3 stride 2 256->256", 256, 256, (1, 3, 3), (1, 2, 2), (0, 1, 1), 3, 4, 28, 28),
+    ("1x1 2048->512 K=2048 single pair", 2048, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 1, 7, 7),  # M = 49: the odd CTA is all padding
+    ("s3x3 128->128 (256 x 128 tiles)", 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), 4, 2, 28, 28),
+    ("1x1 1088->128 odd k-blocks", 1088, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 2, 13, 13),      # 17 k-blocks, two per stage
+    ("s3x3 stride 2 128->128", 128, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), 3, 2, 28, 28),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_cta_pair_kernel_matches_the_plain_kernel(cuda_device, case, monkeypatch):
+    """conv_pair_kernel (tcgen05 cta_group::2: two CTAs share one 256 x 256 tile, each loading half of the weight rows) is
+    the default for the 128 x 256-tile layers; VAD_PAIR=0 routes them through the single-CTA kernel.  Same operand
+    order per accumulator element, so the two are bit-identical."""
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    monkeypatch.delenv("VAD_MC_MIN_TILES", raising=False)
+    monkeypatch.setenv("VAD_PAIR", "0")
+    plain, ref = run_conv_case(*case[1:], False, True)
+    monkeypatch.setenv("VAD_PAIR", "1")
+    monkeypatch.setenv("VAD_PAIR_MIN_KB", "1")  # default: only layers with >= 12 k-blocks
+    pair, _ = run_conv_case(*case[1:], False, True)
+    assert_bf16_close(pair, ref)
+    assert torch.equal(pair, plain)
