@@ -13,6 +13,11 @@
 // barrier address mapped into CTA 0 with mapa); tcgen05.commit.cta_group::2 multicasts the slot release and the
 // accumulator-ready signal into both CTAs; the epilogue warps of both CTAs arrive remotely on the leader's
 // accumulator-empty barrier.  Operand order inside a k-block is identical to K2, so results are bit-identical.
+//
+// EPI = true is the residual form (bottleneck conv3 + BN + identity + ReLU, src/i3d.py:112-116) for layers 3 and 4: each
+// CTA's 128 x 256 result passes through three 32 KB staging tiles as 128-column halves -- an extra warp TMA-prefetches
+// the residual half-tile, the epilogue warps add it in place and TMA-store the sum -- the staged epilogue of K2 with
+// twice the weight reuse (K2 runs these layers as 128 x 128 tiles: 64 FLOP per byte pulled from L2, here 128).
 #pragma once
 
 #include "conv_umma.cuh"
@@ -79,45 +84,60 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_m256(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
 }
 
-template <int BN, int KPS>
+template <int BN, int KPS, bool EPI = false>
 struct PairCfg {
   static_assert(BN == 256 || BN == 128, "pair tile is 256 x BN");
+  static_assert(!EPI || (BN == 256 && KPS == 1), "staged residual epilogue: 256 x 256 pair tiles");
   static constexpr int kABytes = kBlockM * 128;      // this CTA's 128 rows of one k-block
   static constexpr int kBBytes = (BN / 2) * 128;     // this CTA's half of the weight rows of one k-block
   static constexpr int kKbBytes = kABytes + kBBytes;
   static constexpr int kStageBytes = KPS * kKbBytes;  // [A_0 .. A_{KPS-1}][B_0 .. B_{KPS-1}]
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  // EPI: this CTA's 128 x 256 output goes through the staging tiles as two 128 x 128 halves (residual prefetched by
+  // TMA into the tile, result written over it, TMA store), three tiles in rotation: each is two [128 rows x 64 cols]
+  // SWIZZLE_128B sub-tiles
+  static constexpr int kEpiSubBytes = kBlockM * 128;
+  static constexpr int kEpiBufBytes = EPI ? 2 * kEpiSubBytes : 0;
+  static constexpr int kEpiBufs = 3;
+  static constexpr int kPipeBudget = EPI ? 131072 : 196608;
+  static constexpr int kStages = (kPipeBudget / kStageBytes) > 8 ? 8 : (kPipeBudget / kStageBytes);
   static constexpr int kEpiWarps = 8;
-  static constexpr int kColsPerWarp = BN / 2;
+  static constexpr int kColsPerWarp = EPI ? 64 : BN / 2;
   static constexpr int kEpiThreads = kEpiWarps * 32;
-  static constexpr int kThreads = 64 + kEpiThreads;
+  static constexpr int kThreads = 64 + kEpiThreads + (EPI ? 32 : 0);  // EPI: one more warp that only prefetches residual tiles
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * BN * 4 + (2 * kStages + 4) * 8 + 16 + 1024;
+  // the dynamic shared memory of these kernels is declared 1024-byte aligned (checked at run time): no slack for
+  // manual alignment, which the EPI layout (4 x 32 KB stages + 3 x 32 KB staging tiles) could not afford
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + 2 * BN * 4 + (2 * kStages + 4 + 2 * kEpiBufs) * 8 + 16;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
 // tmB: weight map with (64 x BN/2) boxes.  Work item w -> (n tile = w % n_tiles, pair of m tiles = w / n_tiles); the
 // cluster (blockIdx.x >> 1) walks items with stride gridDim.x / 2; CTA rank r of the pair owns rows (2 * pair + r) * 128.
 // A pair whose odd CTA has no rows (odd number of m tiles) still loads: the boxes are out of bounds and arrive as zeros.
-template <int BN, int KPS>
-__global__ void __launch_bounds__(PairCfg<BN, KPS>::kThreads, 1)
-conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
-  using Cfg = PairCfg<BN, KPS>;
+template <int BN, int KPS, bool EPI>
+__global__ void __launch_bounds__(PairCfg<BN, KPS, EPI>::kThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
+  using Cfg = PairCfg<BN, KPS, EPI>;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int NB = Cfg::kEpiBufs;
   const int crank = (int)cluster_ctarank();
   const int w_first = (int)(blockIdx.x >> 1), w_step = (int)(gridDim.x >> 1), w_total = p.mc_items;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t pair_smem[];
+  uint8_t* smem = pair_smem;
+  if (smem_u32(smem) & 1023u) __trap();  // swizzled TMA boxes and UMMA descriptors need 1024-byte aligned tiles
   uint8_t* stage_base = smem;
-  float* s_scale = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* epi_base = smem + STAGES * Cfg::kStageBytes;
+  float* s_scale = reinterpret_cast<float*>(epi_base + NB * Cfg::kEpiBufBytes);
   float* s_shift = s_scale + BN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + BN);  // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2] used in the leader only: arrivals from both CTAs' epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;   // [NB] residual half-tile landed (EPI)
+  uint64_t* res_empty_bar = res_full_bar + NB;   // [NB] staging tile free again (EPI)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,6 +152,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 2 * Cfg::kEpiWarps);
+    }
+    for (int a = 0; a < NB; ++a) {
+      mbar_init(&res_full_bar[a], 1);
+      mbar_init(&res_empty_bar[a], Cfg::kEpiWarps);
+    }
+    if (EPI) {
+      tma_prefetch_desc(&tmR);
+      tma_prefetch_desc(&tmO);
     }
     fence_barrier_init();
   }
@@ -257,7 +285,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 2 + Cfg::kEpiWarps) {
     // ------------------------------------------------------------------ epilogue warps (both CTAs)
     constexpr int CPW = Cfg::kColsPerWarp;
     griddep_wait();
@@ -265,6 +293,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int col0 = ((warp - 2) >> 2) * CPW;
     const uint32_t ltempty0 = mapa_u32(smem_u32(tmem_empty_bar), 0);
+    const bool has_res = EPI && p.res != nullptr;
+    uint32_t eb = 0, eph = 0;  // staging tile of the current half and its phase (EPI)
+    int prev_eb = -1;          // staging tile whose TMA store has been issued but not yet waited for
     int tc = 0, cached_n0 = -1;
     for (int tile = w_first; tile < w_total; tile += w_step) {
       const int n0 = (tile % p.n_tiles) * BN;
@@ -286,6 +317,74 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0);
+      if (EPI) {
+        // two 128-column halves; in each, this warp owns rows [32q, 32q+32) x columns [col0, col0+64) of the staging tile
+        const int lrow = q * 32 + lane;
+        const uint32_t xr = (uint32_t)(lrow & 7);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (has_res) mbar_wait(&res_full_bar[eb], eph);
+          const uint32_t sub = smem_u32(epi_base + eb * Cfg::kEpiBufBytes) + (uint32_t)(col0 >> 6) * Cfg::kEpiSubBytes;
+          const uint32_t buf = sub + (uint32_t)lrow * 128u;
+          auto chunk = [&](const uint32_t (&v)[32], int c, auto res_c) {
+            constexpr bool RES = decltype(res_c)::value;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = c * 32 + g * 8;  // inside this warp's 64 columns
+              const uint32_t addr = buf + ((((uint32_t)col >> 3) ^ xr) << 4);
+              const int sc = h * 128 + col0 + col;
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[sc + j], s_shift[sc + j]);
+              if (RES) {
+                uint4 r;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              const uint32_t o0 = pack_bf16x2(f[0], f[1]), o1 = pack_bf16x2(f[2], f[3]);
+              const uint32_t o2 = pack_bf16x2(f[4], f[5]), o3 = pack_bf16x2(f[6], f[7]);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+            }
+          };
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr + (uint32_t)(h * 128), v0);
+          tmem_ld_32x32(taddr + (uint32_t)(h * 128 + 32), v1);
+          tmem_ld_wait();
+          if (h == 1) {
+            // both halves are in registers / shared memory: hand this CTA's accumulator back to the leader
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(ltempty0 + acc * 8);
+          }
+          if (has_res) {
+            chunk(v0, 0, std::true_type{});
+            chunk(v1, 1, std::true_type{});
+          } else {
+            chunk(v0, 0, std::false_type{});
+            chunk(v1, 1, std::false_type{});
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmO, epi_base + eb * Cfg::kEpiBufBytes + (col0 >> 6) * Cfg::kEpiSubBytes + q * 32 * 128, n0 + h * 128 + col0,
+                         m0 + q * 32);
+            tma_store_commit();
+            tma_store_wait_read<1>();  // the PREVIOUS half's store has left shared memory (this one's read-out stays off the critical path)
+            if (has_res && prev_eb >= 0) mbar_arrive(&res_empty_bar[prev_eb]);  // one arrival per epilogue warp frees that staging tile
+          }
+          __syncwarp();
+          prev_eb = (int)eb;
+          if (++eb == NB) { eb = 0; eph ^= 1u; }
+        }
+        continue;
+      }
       const bool row_ok = row < p.M;
       __nv_bfloat16* out_row = p.out + (long long)row * p.ldo + n0 + col0;
 #pragma unroll 1
@@ -320,8 +419,28 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(ltempty0 + acc * 8);  // hands this CTA's half of the accumulator back to the leader
     }
+  } else {
+    // ------------------------------------------------------------------ residual prefetch warp (EPI, both CTAs)
+    if (EPI && p.res != nullptr && elect_one_sync()) {
+      const uint32_t res_full0 = smem_u32(res_full_bar), res_empty0 = smem_u32(res_empty_bar), epi0 = smem_u32(epi_base);
+      uint32_t rb = 0, rph = 0;
+      griddep_wait();
+      for (int tile = w_first; tile < w_total; tile += w_step) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        const int m0 = (2 * (tile / p.n_tiles) + crank) * kBlockM;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait_a(res_empty0 + rb * 8, rph ^ 1u);
+          mbar_arrive_expect_tx_a(res_full0 + rb * 8, (uint32_t)Cfg::kEpiBufBytes);
+          tma_load_2d_a(epi0 + rb * Cfg::kEpiBufBytes, &tmR, res_full0 + rb * 8, n0 + h * 128, m0);
+          tma_load_2d_a(epi0 + rb * Cfg::kEpiBufBytes + Cfg::kEpiSubBytes, &tmR, res_full0 + rb * 8, n0 + h * 128 + 64, m0);
+          if (++rb == NB) { rb = 0; rph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
   }
 
+  if (EPI && warp >= 2 && warp < 2 + Cfg::kEpiWarps && lane == 0) tma_store_wait<0>();  // bulk stores fully complete
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // nobody leaves while the peer may still signal into this CTA or read its shared memory

@@ -385,6 +385,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_res = p.res != nullptr;
     int tc = 0, cached_n0 = -1;
     uint32_t eb = 0, eph = 0;  // epilogue buffer of this tile and its phase (EPI)
+    int prev_eb = -1;          // buffer whose TMA store has been issued but not yet waited for
     for (int tile = w_first; tile < w_total; tile += w_step) {
       const int n0 = (tile % p.n_tiles) * BN;
       const int m0 = m_tile_of(tile) * kBlockM;
@@ -517,10 +518,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_store_2d(&tmO, epi_base + eb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes + q * 32 * 128, n0 + 64 * j,
                            m0 + q * 32);
           tma_store_commit();
-          tma_store_wait_read<0>();                      // smem may be overwritten once the store engine has read it
-          if (has_res) mbar_arrive(&res_empty_bar[eb]);  // one arrival per epilogue warp frees the buffer
+          // The store engine needs a few hundred cycles to read the tile out of shared memory; waiting for THIS store
+          // here would put that on every tile's critical path.  Wait for the PREVIOUS tile's store instead and release
+          // its buffer (three buffers: the one this warp writes next was released one tile ago).
+          tma_store_wait_read<1>();
+          if (has_res && prev_eb >= 0) mbar_arrive(&res_empty_bar[prev_eb]);  // one arrival per epilogue warp frees the buffer
         }
         __syncwarp();
+        prev_eb = (int)eb;
         if (++eb == NB) { eb = 0; eph ^= 1u; }
         continue;
       }

@@ -104,6 +104,8 @@ struct OpRuntime {
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
+  bool pair_epi = false; // CTA-pair kernel with the staged residual epilogue (conv3 of layer 4: cout % 256 == 0, >= 8 k-blocks)
+  CUtensorMap tmBh;      // pair kernels: weight map with (64 x BN/2)-row boxes
   bool pair = false;     // CTA-pair kernel (tcgen05 cta_group::2, 256 x BN tiles): BN = 256 layers with TMA operands and the direct epilogue
   bool mc = false;       // cluster-of-2 kernel with the weight tile multicast (BN = 256, TMA operands, direct epilogue)
   bool pool_tp = false;  // 1x1x1 residual conv with maxpool2 (2,1,1)/(2,1,1) fused into its staged epilogue
@@ -137,6 +139,7 @@ struct vad_plan {
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
   int pair_mode = 1;         // VAD_PAIR=0: never use the CTA-pair kernel; 1 (default): for the long-K layers without residual
+  int pair_epi_min_kb = 8;   // VAD_PAIR_EPI_MIN_KB: same for residual layers (staged epilogue; measured: K = 512 gains, K = 256 loses); 0 = off
   int pair_min_kb = 12;      // VAD_PAIR_MIN_KB: fewest 64-wide k-blocks for which a layer goes to the CTA-pair kernel
   int mc_min_tiles = -1;     // VAD_MC_MIN_TILES=<n>: use the cluster-multicast kernel from n m-tiles on.  Off by default: measured
                              // neutral (layer3/4 are not bound by weight traffic), kept as a verified building block
@@ -236,6 +239,7 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR"); p->pair_mode = k ? atoi(k) : 1; }
   { const char* k = getenv("VAD_PAIR_MIN_KB"); p->pair_min_kb = k ? atoi(k) : 12; }
+  { const char* k = getenv("VAD_PAIR_EPI_MIN_KB"); p->pair_epi_min_kb = k ? atoi(k) : 8; }
   { const char* k = getenv("VAD_MC_MIN_TILES"); p->mc_min_tiles = k ? atoi(k) : -1; }
   { const char* k = getenv("VAD_NO_PDL"); g_pdl = !(k && k[0] == '1'); }
   { const char* k = getenv("VAD_L2_AHEAD"); p->l2_ahead = k ? atoi(k) : 0; }
@@ -347,7 +351,10 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections), VAD_EPI_ALL=1: every layer
       r.epi = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K) || p->epi_all);
       r.bn = (d.cout > 128 && !r.epi) ? 256 : (d.cout > 64 ? 128 : 64);
-      if (r.bn == 256 && d.cout % 128 == 0 && p->bn_model) {
+      r.pair_epi = r.epi && p->pair_mode > 0 && p->pair_epi_min_kb > 0 && d.res >= 0 && r.a_mode != A_GATHER && r.bk == 64 && d.cout % 256 == 0 &&
+                   !(d.flags & VAD_FLAG_POOL_T2) && (p->sm_count % 2) == 0 && c.num_kb >= p->pair_epi_min_kb && M > kBlockM;
+      if (r.pair_epi) r.bn = 256;
+      if (r.bn == 256 && d.cout % 128 == 0 && p->bn_model && !r.pair_epi) {
         // wave quantisation: a persistent grid of sm_count CTAs runs ceil(tiles / sm_count) rounds of tiles whose time
         // is ~ BN; 128-wide tiles (two k-blocks per stage keep their MMAs at the floor) win when they cut the rounds
         const long long mt = (M + kBlockM - 1) / kBlockM;
@@ -410,7 +417,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       // CTA pairs pay off where the L2 -> shared-memory path is the limit (long K); short-K layers are output bound
       r.pair = !r.mc && p->pair_mode > 0 && (r.bn == 256 || r.bn == 128) && !r.epi && r.a_mode != A_GATHER && r.bk == 64 && !r.thalo && !r.s3 &&
                !r.pool_tp && d.cout % r.bn == 0 && (p->sm_count % 2) == 0 && m_tiles >= 2 && c.num_kb >= p->pair_min_kb;
-      if (r.mc || r.pair) {
+      if (r.mc || r.pair || r.pair_epi) {
         c.mc_items = (int)(((m_tiles + 1) / 2) * n_tiles);
         r.grid = 2 * c.mc_items < p->sm_count ? 2 * c.mc_items : p->sm_count;  // whole clusters, each with at least one item
       }
@@ -586,13 +593,14 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
       memset(&r.tmA, 0, sizeof(r.tmA));
       memset(&r.tmR, 0, sizeof(r.tmR));
       memset(&r.tmO, 0, sizeof(r.tmO));
-      if (r.mc || r.pair) {
+      memset(&r.tmBh, 0, sizeof(r.tmBh));
+      if (r.mc || r.pair || r.pair_epi) {
         // each CTA of a pair loads half of the BN weight rows (mc: and multicasts them)
         cuuint64_t gdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
         cuuint64_t gstr[1] = {(cuuint64_t)r.K_pad * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)(r.bn / 2)};
         cuuint32_t es[2] = {1, 1};
-        CUresult cr = p->encode_tiled(&r.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), gdim, gstr, box, es,
+        CUresult cr = p->encode_tiled(r.mc ? &r.tmR : &r.tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), gdim, gstr, box, es,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(weight halves) failed: %d", i, (int)cr);
@@ -852,24 +860,25 @@ static cudaError_t launch_conv_mc(const OpRuntime& r, cudaStream_t st) {
   return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 2, r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
 }
 
-template <int BN, int KPS>
+template <int BN, int KPS, bool EPI>
 static cudaError_t launch_conv_pair_t(const OpRuntime& r, cudaStream_t st) {
-  using Cfg = PairCfg<BN, KPS>;
-  auto kern = conv_pair_kernel<BN, KPS>;
+  using Cfg = PairCfg<BN, KPS, EPI>;
+  auto kern = conv_pair_kernel<BN, KPS, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 2, r.tmA, r.tmR, r.cp);
+  return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 2, r.tmA, r.tmBh, r.tmR, r.tmO, r.cp);
 }
 static cudaError_t launch_conv_pair(const OpRuntime& r, cudaStream_t st) {
-  return r.bn == 256 ? launch_conv_pair_t<256, 1>(r, st) : launch_conv_pair_t<128, 2>(r, st);
+  if (r.pair_epi) return launch_conv_pair_t<256, 1, true>(r, st);
+  return r.bn == 256 ? launch_conv_pair_t<256, 1, false>(r, st) : launch_conv_pair_t<128, 2, false>(r, st);
 }
 
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
-  if (r.pair) return launch_conv_pair(r, st);
+  if (r.pair || r.pair_epi) return launch_conv_pair(r, st);
   if (r.mc) return launch_conv_mc(r, st);
   if (r.bk == 32) return launch_conv<64, 32, 1, false, false>(r, st);  // folded stem, TMA window view
   if (r.epi) return r.bn == 128 ? launch_conv_bn<128, true>(r, st) : launch_conv_bn<64, true>(r, st);

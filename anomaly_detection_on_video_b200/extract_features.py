@@ -224,6 +224,9 @@ def cli(argv: Optional[Sequence[str]] = None) -> None:
     queue = WorkQueue.from_env()
     if queue is not None:
         torch.cuda.set_device(queue.local_rank)
+    from .hostaffinity import bind_to_gpu
+
+    bind_to_gpu(queue.local_rank if queue is not None else 0)  # pinned frame buffers land on the GPU's own socket
     dataset = {"train": _rows_from_dir(args.videos)} if args.videos else None
     main(args.outdir, dataset=dataset, model_name=args.model_name, state_dict_path=args.weights, queue=queue)
 

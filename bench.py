@@ -180,6 +180,10 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from anomaly_detection_on_video_b200.hostaffinity import bind_to_gpu
+
+    cpus_at_start = os.sched_getaffinity(0)
+    host_info = bind_to_gpu(local_rank)  # before the pinned frame buffer is allocated (first touch decides its NUMA node)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     build.build()
@@ -253,8 +257,11 @@ def main():
         sampler.start()
         time.sleep(0.25)
     launches["n"] = 0
+    # Inside the timed region only the dominant kernel (op 0, the stem) is bracketed with CUDA events: its launch
+    # durations feed `roofline`.  Event records between all the other launches would keep their programmatic dependent
+    # launch from overlapping prologues, so the per-layer table comes from a separate, untimed, fully profiled pass below.
     if os.environ.get("VAD_BENCH_NO_PROFILE") != "1":
-        plan.profile_begin()
+        plan.profile_begin(0, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -263,12 +270,28 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    launches_timed_region = launches["n"]
     clocks = sampler.stop() if rank == 0 else {}
     # note: steps whose last batch has a different size re-bind the plan; profile data covers every forward
     try:
-        prof = plan.profile_end()
+        prof_stem = plan.profile_end()
     except RuntimeError:
-        prof = []
+        prof_stem = []
+    prof = []
+    if os.environ.get("VAD_BENCH_NO_PROFILE") != "1":
+        plan = model.plan(dev)
+        plan.profile_begin()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(K):
+            step_resident()
+        p1.record()
+        torch.cuda.synchronize(dev)
+        ms_profiled = p0.elapsed_time(p1)
+        try:
+            prof = plan.profile_end()
+        except RuntimeError:
+            prof = []
 
     # ---- e2e
     for _ in range(2):
@@ -363,7 +386,7 @@ def main():
             # the dominant single kernel: the stem (conv1), ~22% of the step.  Algorithmic FLOPs per launch =
             # 9.443 GFLOP per clip-crop (4.721 GMAC) x the clip-crops of the launch; duration =
             # CUDA events around every launch of it inside the timed region.
-            stem = [p for p in conv if p["name"] == "conv1"]
+            stem = [p for p in prof_stem if p["name"] == "conv1" and p["calls"]]
             if stem:
                 st = stem[0]
                 s_ach = st["flops"] / (st["ms"] / 1e3) / 1e12
@@ -385,6 +408,7 @@ def main():
                 }
         cpu_baseline = None
         if not args.no_cpu_baseline:
+            os.sched_setaffinity(0, cpus_at_start)  # the CPU baseline gets every core the box allows
             v, d = cpu_reference_run(steps=4, warmup=1, clips_per_step=2)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": d["sample"],
                             "seconds": d["seconds"]}
@@ -399,16 +423,19 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames_host.numel()),
                     "d2h_bytes_per_step": int(f_host.numel() * 4 + s_host.numel() * 4), "ms_per_step": ms_e2e / K,
                     "wall_ms_per_step": wall_e2e / K},
-            "gpu_launches": int(launches["n"]),
+            "gpu_launches": int(launches_timed_region),
             "clocks": clocks,
             "roofline": roofline,
             "roofline_conv_family": family,
             "cpu_baseline": cpu_baseline,
             "head": head_info,
+            "host": host_info,
             "tflops_whole_step": value * FLOP_PER_CLIP / 1e12,
-            "step_breakdown": {"step_ms": ms / K, "backbone_kernels_ms": (sum(p["ms"] for p in prof) / K) if prof else None,
-                               "note": "backbone_kernels_ms = CUDA-event time of the op-table launches; the rest is preprocessing, "
-                                       "feature scatter, segment mean and launch gaps"},
+            "step_breakdown": {"step_ms": ms / K, "profiled_pass_step_ms": (ms_profiled / K) if prof else None,
+                               "backbone_kernels_ms": (sum(p["ms"] for p in prof) / K) if prof else None,
+                               "note": "backbone_kernels_ms = CUDA-event time of the op-table launches in the separate fully "
+                                       "profiled pass (events between launches switch off the PDL overlap, so that pass is "
+                                       "slower than step_ms); the rest is preprocessing, feature scatter, segment mean, gaps"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -367,3 +367,28 @@ def test_cta_pair_kernel_matches_the_plain_kernel(cuda_device, case, monkeypatch
     pair, _ = run_conv_case(*case[1:], False, True)
     assert_bf16_close(pair, ref)
     assert torch.equal(pair, plain)
+
+
+PAIR_EPI_CASES = [
+    ("1x1 256->256 +res, 4 k-blocks", 256, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 2, 14, 14),
+    ("1x1 512->512 +res, odd m-tiles", 512, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 13, 13),      # 3 m-tiles: odd CTA of pair 2 is padding
+    ("1x1 512->256 +res (wider residual)", 512, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 3, 2, 14, 14),
+    ("1x1 256->512... many items", 512, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 4, 4, 28, 28),           # 98 m-tiles x 2 n-tiles on 74 pairs
+    ("1x1 256->256 +res, M = 49", 256, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 1, 7, 7),
+]
+
+
+@pytest.mark.parametrize("relu", [True, False], ids=["relu", "linear"])
+@pytest.mark.parametrize("case", PAIR_EPI_CASES, ids=[c[0] for c in PAIR_EPI_CASES])
+def test_cta_pair_residual_kernel_matches_the_plain_kernel(cuda_device, case, relu, monkeypatch):
+    """conv_pair_kernel<256, 1, true>: residual layers with cout % 256 == 0 and >= 4 k-blocks run as 256 x 256 CTA-pair
+    tiles whose halves pass through TMA-prefetched residual staging tiles; bit-identical to the single-CTA staged epilogue."""
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    monkeypatch.setenv("VAD_PAIR", "0")
+    plain, ref = run_conv_case(*case[1:], True, relu)
+    monkeypatch.setenv("VAD_PAIR", "1")
+    monkeypatch.setenv("VAD_PAIR_EPI_MIN_KB", "1")  # default: only layers with >= 8 k-blocks
+    pair, _ = run_conv_case(*case[1:], True, relu)
+    assert_bf16_close(pair, ref)
+    assert torch.equal(pair, plain)

@@ -186,3 +186,20 @@ def test_feature_dataset_archive_layout(tmp_path):
         ds["normal"][0]
     with pytest.raises(RuntimeError, match="no network"):
         build_feature_dataset("train")
+
+
+def test_bind_to_gpu_is_best_effort_without_nvml(monkeypatch):
+    """hostaffinity.bind_to_gpu never raises and never changes the cpuset when it cannot learn the GPU's local CPUs."""
+    import os
+
+    from anomaly_detection_on_video_b200.hostaffinity import bind_to_gpu
+
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu(0)
+    assert isinstance(info, dict) and "bound" in info and info["allowed_cpus"] == len(before)
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
+    monkeypatch.setenv("VAD_NO_NUMA_BIND", "1")
+    assert bind_to_gpu(0)["bound"] is False
+    assert os.sched_getaffinity(0) == before
