@@ -47,6 +47,14 @@ EXPORTED_SYMBOLS = (
     "vad_head_num_launches",
     "vad_head_flops",
     "vad_head_destroy",
+    "vad_tf32_plan_create",
+    "vad_tf32_plan_configure",
+    "vad_tf32_plan_forward",
+    "vad_tf32_plan_slot_info",
+    "vad_tf32_plan_num_launches",
+    "vad_tf32_plan_flops",
+    "vad_tf32_plan_destroy",
+    "vad_tf32_ingest_ncthw",
 )
 
 
@@ -162,6 +170,22 @@ def load() -> ctypes.CDLL:
     lib.vad_head_loss.restype = c_int32
     lib.vad_head_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                   c_void_p, c_void_p, c_void_p]
+    lib.vad_tf32_plan_create.restype = c_int32
+    lib.vad_tf32_plan_create.argtypes = [POINTER(c_void_p), POINTER(OpDesc), c_int32, c_int32, c_void_p, c_uint64, c_int32, c_int32]
+    lib.vad_tf32_plan_configure.restype = c_int32
+    lib.vad_tf32_plan_configure.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_uint64)]
+    lib.vad_tf32_plan_forward.restype = c_int32
+    lib.vad_tf32_plan_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]
+    lib.vad_tf32_plan_slot_info.restype = c_int32
+    lib.vad_tf32_plan_slot_info.argtypes = [c_void_p, c_int32, POINTER(c_int32), POINTER(c_uint64), POINTER(c_uint64)]
+    lib.vad_tf32_plan_num_launches.restype = c_int32
+    lib.vad_tf32_plan_num_launches.argtypes = [c_void_p]
+    lib.vad_tf32_plan_flops.restype = c_double
+    lib.vad_tf32_plan_flops.argtypes = [c_void_p]
+    lib.vad_tf32_plan_destroy.restype = None
+    lib.vad_tf32_plan_destroy.argtypes = [c_void_p]
+    lib.vad_tf32_ingest_ncthw.restype = c_int32
+    lib.vad_tf32_ingest_ncthw.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.vad_head_num_launches.restype = c_int32
     lib.vad_head_num_launches.argtypes = [c_void_p]
     lib.vad_head_flops.restype = c_double

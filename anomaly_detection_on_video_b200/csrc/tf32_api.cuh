@@ -1,0 +1,295 @@
+// Host side of the TF32 precision mode (include/vad_b200.h: vad_tf32_*).  Same op table (vad_op_desc) and the same
+// slot / channel-slice semantics as vad_plan_*, but every slot is a plain fp32 [batch, T, H, W, C] tensor, weights are
+// fp32 [cout, K_pad32], and every op runs through the general kernels of tf32_kernels.cuh.  No fused-pool / folded-stem
+// flags: the Python layer tables emit the unfused op list for this mode.
+#pragma once
+
+#include "tf32_kernels.cuh"
+
+namespace {
+
+struct Tf32Op {
+  vad::Tf32ConvParams cp;
+  vad::PoolF32Params pp;
+  CUtensorMap tmB;
+  int bn = 128;
+  int grid = 1;
+  int K_pad = 0;
+  int avg_P = 0, avg_C = 0;
+  uint64_t in_off = 0, out_off = 0, res_off = 0;  // byte offsets inside the workspace (src slot 0: the input pointer)
+};
+
+}  // namespace
+
+struct vad_tf32_plan {
+  std::vector<vad_op_desc> ops;
+  std::vector<SlotInfo> slots;
+  std::vector<Tf32Op> rt;
+  int n_slots = 0, in_channels = 4, device = 0, sm_count = 148, batch = 0, feat_c = 0;
+  const uint8_t* params = nullptr;
+  uint64_t params_bytes = 0, ws_bytes = 0;
+  double flops = 0.0;
+  bool configured = false;
+  EncodeTiledFn encode_tiled = nullptr;
+};
+
+extern "C" int32_t vad_tf32_plan_create(vad_tf32_plan_t** plan, const vad_op_desc* ops, int32_t n_ops, int32_t n_slots,
+                                        const void* params_dev, uint64_t params_bytes, int32_t in_channels, int32_t device) {
+  if (!plan || !ops || n_ops <= 0 || n_slots <= 1 || !params_dev) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_create: bad arguments");
+  if (in_channels <= 0 || in_channels % 4) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_create: in_channels must be a positive multiple of 4");
+  int32_t rc = require_sm100(device);
+  if (rc != VAD_OK) return rc;
+  for (int i = 0; i < n_ops; ++i) {
+    const vad_op_desc& d = ops[i];
+    if (d.kind < VAD_OP_CONV || d.kind > VAD_OP_AVGPOOL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad kind %d", i, d.kind);
+    if (d.src < 0 || d.src >= n_slots) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: src slot %d out of range", i, d.src);
+    if (d.kind != VAD_OP_AVGPOOL && (d.dst <= 0 || d.dst >= n_slots || d.dst == d.src))
+      return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad dst slot %d", i, d.dst);
+    if (d.flags & (VAD_FLAG_STEM_FOLD_W | VAD_FLAG_POOL_T2))
+      return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: the TF32 mode takes the unfused op table (no STEM_FOLD_W / POOL_T2)", i);
+    if (d.kind == VAD_OP_CONV) {
+      if (d.cin <= 0 || d.cin % 4 || d.cout <= 0 || d.cout % 4 || d.dst_c_off % 4)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: cin, cout and dst_c_off must be multiples of 4", i);
+      if (d.res >= n_slots) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: res slot out of range", i);
+      if (d.w_off % 128 || d.scale_off % 16 || d.shift_off % 16) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: misaligned parameter offsets", i);
+      if (d.kt < 1 || d.kh < 1 || d.kw < 1 || d.st < 1 || d.sh < 1 || d.sw < 1 || d.pt < 0 || d.ph < 0 || d.pw < 0)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad kernel/stride/pad", i);
+    }
+  }
+  vad_tf32_plan* p = new vad_tf32_plan();
+  p->ops.assign(ops, ops + n_ops);
+  p->n_slots = n_slots;
+  p->params = static_cast<const uint8_t*>(params_dev);
+  p->params_bytes = params_bytes;
+  p->in_channels = in_channels;
+  p->device = device;
+  void* fn = nullptr;
+  rc = driver_symbol("cuTensorMapEncodeTiled", &fn);
+  if (rc != VAD_OK) { delete p; return rc; }
+  p->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (p->sm_count <= 0) p->sm_count = 148;
+  *plan = p;
+  return VAD_OK;
+}
+
+extern "C" void vad_tf32_plan_destroy(vad_tf32_plan_t* p) { delete p; }
+
+extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, int32_t t, int32_t h, int32_t w, uint64_t* workspace_bytes) {
+  if (!p) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_configure: null plan");
+  if (batch <= 0 || t <= 0 || h <= 0 || w <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_configure: bad size");
+  p->configured = false;
+  p->slots.assign(p->n_slots, SlotInfo());
+  p->rt.assign(p->ops.size(), Tf32Op());
+  p->flops = 0.0;
+  p->feat_c = 0;
+  p->batch = batch;
+  SlotInfo& s0 = p->slots[0];
+  s0.T = t; s0.H = h; s0.W = w; s0.C = p->in_channels; s0.defined = true;
+  s0.bytes = (uint64_t)batch * t * h * w * s0.C * 4;
+  // pass 1: shapes in op order, the largest extent every slot ever has
+  struct Shape { int T, H, W, C; };
+  std::vector<Shape> src_shape(p->ops.size()), dst_shape(p->ops.size());
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const vad_op_desc& d = p->ops[i];
+    const SlotInfo src = p->slots[d.src];
+    if (!src.defined) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu reads slot %d before it is written", i, d.src);
+    src_shape[i] = {src.T, src.H, src.W, src.C};
+    Tf32Op& r = p->rt[i];
+    int To, Ho, Wo, Cdst;
+    if (d.kind == VAD_OP_CONV) {
+      if (src.C != d.cin) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: cin=%d but slot %d has C=%d", i, d.cin, d.src, src.C);
+      int pf[3] = {d.pt, d.ph, d.pw};
+      if (d.flags & VAD_FLAG_CONV_SAME) {
+        const int in3[3] = {src.T, src.H, src.W}, k3[3] = {d.kt, d.kh, d.kw}, s3[3] = {d.st, d.sh, d.sw};
+        int out3[3];
+        for (int a = 0; a < 3; ++a) {
+          out3[a] = (in3[a] + s3[a] - 1) / s3[a];
+          int tot = (out3[a] - 1) * s3[a] + k3[a] - in3[a];
+          if (tot < 0) tot = 0;
+          pf[a] = tot / 2;  // back padding is implied: out-of-range taps read zeros
+        }
+        To = out3[0]; Ho = out3[1]; Wo = out3[2];
+      } else {
+        To = (src.T + 2 * d.pt - d.kt) / d.st + 1;
+        Ho = (src.H + 2 * d.ph - d.kh) / d.sh + 1;
+        Wo = (src.W + 2 * d.pw - d.kw) / d.sw + 1;
+      }
+      if (To <= 0 || Ho <= 0 || Wo <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: empty output", i);
+      Cdst = d.dst_c_total ? d.dst_c_total : d.cout;
+      if (d.dst_c_off + d.cout > Cdst) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: channel slice exceeds dst_c_total", i);
+      const long long M = (long long)batch * To * Ho * Wo;
+      if (M > 0x7fffffffLL - 256) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: too many output pixels", i);
+      vad::Tf32ConvParams& c = r.cp;
+      memset(&c, 0, sizeof(c));
+      c.M = (int)M; c.N = d.cout;
+      c.To = To; c.Ho = Ho; c.Wo = Wo; c.Ti = src.T; c.Hi = src.H; c.Wi = src.W;
+      c.kt = d.kt; c.kh = d.kh; c.kw = d.kw; c.st = d.st; c.sh = d.sh; c.sw = d.sw; c.pt = pf[0]; c.ph = pf[1]; c.pw = pf[2];
+      c.cin = d.cin; c.ntaps = d.kt * d.kh * d.kw;
+      c.sW = d.cin; c.sH = (long long)src.W * d.cin; c.sT = c.sH * src.H; c.sN = c.sT * src.T;
+      const int K = c.ntaps * d.cin;
+      r.K_pad = (int)align_up(K, 32);
+      c.num_kb = r.K_pad / 32;
+      c.relu = (d.flags & VAD_FLAG_RELU) ? 1 : 0;
+      c.ldo = Cdst;
+      if (d.w_off + (uint64_t)d.cout * r.K_pad * 4 > p->params_bytes || d.scale_off + (uint64_t)d.cout * 4 > p->params_bytes ||
+          d.shift_off + (uint64_t)d.cout * 4 > p->params_bytes)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: parameters run past the blob", i);
+      r.bn = d.cout > 64 ? 128 : 64;
+      const long long m_tiles = (M + vad::kBlockM - 1) / vad::kBlockM, n_tiles = (d.cout + r.bn - 1) / r.bn;
+      if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
+      c.n_tiles = (int)n_tiles; c.num_tiles = (int)(m_tiles * n_tiles);
+      r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;
+      if (d.res >= 0) {
+        const SlotInfo& rs = p->slots[d.res];
+        if (!rs.defined || rs.T != To || rs.H != Ho || rs.W != Wo || rs.C < d.cout)
+          return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: residual slot %d does not match the output", i, d.res);
+        c.ldr = rs.C;
+      }
+      p->flops += 2.0 * (double)M * d.cout * K;
+    } else if (d.kind == VAD_OP_MAXPOOL) {
+      vad::PoolF32Params& q = r.pp;
+      memset(&q, 0, sizeof(q));
+      if (src.C % 4) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: max-pool needs C %% 4 == 0", i);
+      if (d.flags & VAD_FLAG_POOL_SAME) {
+        To = pool_out_same(src.T, d.st); Ho = pool_out_same(src.H, d.sh); Wo = pool_out_same(src.W, d.sw);
+        auto front = [](int in, int out, int k, int s) { int tot = (out - 1) * s + k - in; if (tot < 0) tot = 0; return tot / 2; };
+        q.pt = front(src.T, To, d.kt, d.st); q.ph = front(src.H, Ho, d.kh, d.sh); q.pw = front(src.W, Wo, d.kw, d.sw);
+        q.pad_zero = 1;
+      } else {
+        To = (src.T + 2 * d.pt - d.kt) / d.st + 1;
+        Ho = (src.H + 2 * d.ph - d.kh) / d.sh + 1;
+        Wo = (src.W + 2 * d.pw - d.kw) / d.sw + 1;
+        q.pt = d.pt; q.ph = d.ph; q.pw = d.pw; q.pad_zero = 0;
+      }
+      if (To <= 0 || Ho <= 0 || Wo <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: empty output", i);
+      Cdst = d.dst_c_total ? d.dst_c_total : src.C;
+      if (d.dst_c_off % 4 || d.dst_c_off + src.C > Cdst) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: bad channel slice", i);
+      q.B = batch; q.Ti = src.T; q.Hi = src.H; q.Wi = src.W; q.C = src.C;
+      q.To = To; q.Ho = Ho; q.Wo = Wo;
+      q.kt = d.kt; q.kh = d.kh; q.kw = d.kw; q.st = d.st; q.sh = d.sh; q.sw = d.sw;
+      q.ldo = Cdst;
+    } else {
+      if (src.C % 32) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: avg-pool needs C %% 32 == 0", i);
+      r.avg_P = src.T * src.H * src.W;
+      r.avg_C = src.C;
+      p->feat_c = src.C;
+      dst_shape[i] = {0, 0, 0, 0};
+      continue;
+    }
+    dst_shape[i] = {To, Ho, Wo, Cdst};
+    SlotInfo& dst = p->slots[d.dst];
+    dst.T = To; dst.H = Ho; dst.W = Wo; dst.C = Cdst; dst.defined = true;
+    const uint64_t bytes = (uint64_t)batch * To * Ho * Wo * Cdst * 4;
+    if (bytes > dst.bytes) dst.bytes = bytes;
+  }
+  uint64_t off = 0;
+  for (int s = 1; s < p->n_slots; ++s) {
+    p->slots[s].offset = off;
+    off += align_up(p->slots[s].bytes, 1024);
+  }
+  p->ws_bytes = off;
+  // pass 2: offsets and weight maps
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const vad_op_desc& d = p->ops[i];
+    Tf32Op& r = p->rt[i];
+    r.in_off = d.src == 0 ? 0 : p->slots[d.src].offset;
+    if (d.kind == VAD_OP_AVGPOOL) continue;
+    r.out_off = p->slots[d.dst].offset + (uint64_t)d.dst_c_off * 4;
+    if (d.kind == VAD_OP_CONV) {
+      if (d.res == 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: the input slot cannot be a residual", i);
+      if (d.res > 0) r.res_off = p->slots[d.res].offset;
+      cuuint64_t gdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
+      cuuint64_t gstr[1] = {(cuuint64_t)r.K_pad * 4};
+      cuuint32_t box[2] = {32, (cuuint32_t)r.bn};
+      cuuint32_t es[2] = {1, 1};
+      CUresult cr = p->encode_tiled(&r.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(p->params + d.w_off), gdim, gstr, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(fp32 weights) failed: %d", i, (int)cr);
+      r.cp.scale = reinterpret_cast<const float*>(p->params + d.scale_off);
+      r.cp.shift = reinterpret_cast<const float*>(p->params + d.shift_off);
+    }
+  }
+  p->configured = true;
+  if (workspace_bytes) *workspace_bytes = p->ws_bytes;
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_tf32_plan_slot_info(const vad_tf32_plan_t* p, int32_t slot, int32_t* dims4, uint64_t* offset, uint64_t* bytes) {
+  if (!p || !p->configured) return fail(VAD_ERR_NOT_CONFIGURED, "vad_tf32_plan_slot_info: plan is not configured");
+  if (slot < 0 || slot >= p->n_slots) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_slot_info: slot out of range");
+  const SlotInfo& s = p->slots[slot];
+  if (dims4) { dims4[0] = s.T; dims4[1] = s.H; dims4[2] = s.W; dims4[3] = s.C; }
+  if (offset) *offset = slot == 0 ? 0 : s.offset;
+  if (bytes) *bytes = s.bytes;
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_tf32_plan_num_launches(const vad_tf32_plan_t* p) { return p ? (int32_t)p->ops.size() : 0; }
+extern "C" double vad_tf32_plan_flops(const vad_tf32_plan_t* p) { return (p && p->configured) ? p->flops : 0.0; }
+
+template <int BN>
+static cudaError_t launch_conv_tf32(const Tf32Op& r, const vad::Tf32ConvParams& c, cudaStream_t st) {
+  using Cfg = vad::Tf32Cfg<BN>;
+  auto kern = vad::conv_tf32_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<r.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(r.tmB, c);
+  return cudaGetLastError();
+}
+
+extern "C" int32_t vad_tf32_plan_forward(vad_tf32_plan_t* p, const void* x_dev, void* workspace_dev, uint64_t workspace_bytes,
+                                         float* feat_out_dev, void* stream) {
+  if (!p || !p->configured) return fail(VAD_ERR_NOT_CONFIGURED, "vad_tf32_plan_forward: plan is not configured");
+  if (!x_dev || (!workspace_dev && p->ws_bytes)) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_forward: null pointer");
+  if (workspace_bytes < p->ws_bytes)
+    return fail(VAD_ERR_WORKSPACE_TOO_SMALL, "workspace %llu < required %llu", (unsigned long long)workspace_bytes, (unsigned long long)p->ws_bytes);
+  if ((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) || (reinterpret_cast<uintptr_t>(x_dev) & 15))
+    return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_forward: workspace must be 1024-byte and input 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const vad_op_desc& d = p->ops[i];
+    Tf32Op& r = p->rt[i];
+    const uint8_t* src = d.src == 0 ? static_cast<const uint8_t*>(x_dev) : ws + r.in_off;
+    cudaError_t e = cudaSuccess;
+    if (d.kind == VAD_OP_CONV) {
+      vad::Tf32ConvParams c = r.cp;
+      c.in = reinterpret_cast<const float*>(src);
+      c.out = reinterpret_cast<float*>(ws + r.out_off);
+      c.res = d.res > 0 ? reinterpret_cast<const float*>(ws + r.res_off) : nullptr;
+      e = r.bn == 128 ? launch_conv_tf32<128>(r, c, st) : launch_conv_tf32<64>(r, c, st);
+    } else if (d.kind == VAD_OP_MAXPOOL) {
+      vad::PoolF32Params q = r.pp;
+      q.in = reinterpret_cast<const float*>(src);
+      q.out = reinterpret_cast<float*>(ws + r.out_off);
+      const long long total = (long long)q.B * q.To * q.Ho * q.Wo * (q.C / 4);
+      vad::maxpool3d_f32_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(q);
+      e = cudaGetLastError();
+    } else {
+      if (!feat_out_dev) return fail(VAD_ERR_INVALID_ARGUMENT, "plan ends in AVGPOOL but feat_out_dev is null");
+      const long long warps = (long long)p->batch * (r.avg_C / 32);
+      vad::avgpool_f32_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), p->batch, r.avg_P,
+                                                                                r.avg_C, feat_out_dev);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "tf32 op %zu launch failed: %s", i, cudaGetErrorString(e));
+  }
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_tf32_ingest_ncthw(const float* x_dev, int32_t batch, int32_t t, int32_t h, int32_t w, float* out_dev, void* stream) {
+  if (!x_dev || !out_dev || batch <= 0 || t <= 0 || h <= 0 || w <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_ingest_ncthw: bad arguments");
+  if (reinterpret_cast<uintptr_t>(out_dev) & 15) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_ingest_ncthw: output must be 16-byte aligned");
+  const long long thw = (long long)t * h * w;
+  vad::ingest_ncthw_f32_to_ndhwc4_kernel<<<grid_for((long long)batch * thw, 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_dev, batch, thw, reinterpret_cast<float4*>(out_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "vad_tf32_ingest_ncthw launch failed: %s", cudaGetErrorString(e));
+  return VAD_OK;
+}

@@ -1261,3 +1261,6 @@ extern "C" int32_t vad_add_magnitude(const float* feats_dev, int64_t rows, int32
 
 // ------------------------------------------------------------------------------------ MGFN scoring head
 #include "head_api.cuh"
+
+// ------------------------------------------------------------------------------------ TF32 precision mode
+#include "tf32_api.cuh"

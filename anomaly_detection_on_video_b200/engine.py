@@ -79,8 +79,9 @@ class ParamPacker:
         return off
 
     def add_conv(self, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, fold_w: bool = False,
-                 cin_pad: Optional[int] = None) -> Tuple[int, int, int]:
-        """weight: [cout, cin, kt, kh, kw] fp32 (torch Conv3d layout)."""
+                 cin_pad: Optional[int] = None, tf32: bool = False) -> Tuple[int, int, int]:
+        """weight: [cout, cin, kt, kh, kw] fp32 (torch Conv3d layout).  ``tf32``: keep the weights in fp32 with K padded
+        to 32 (the layout of the TF32 precision mode, ``Tf32Plan``)."""
         w = weight.detach().to(torch.float32).cpu()
         cout, cin, kt, kh, kw = w.shape
         w = w.permute(0, 2, 3, 4, 1)  # [cout, kt, kh, kw, cin]
@@ -100,10 +101,14 @@ class ParamPacker:
                 w = wp
             w2 = w.reshape(cout, -1)
         k = w2.shape[1]
-        k_pad = (k + KBLOCK - 1) // KBLOCK * KBLOCK
+        kblock = 32 if tf32 else KBLOCK
+        k_pad = (k + kblock - 1) // kblock * kblock
         if k_pad != k:
             w2 = torch.cat([w2, torch.zeros(cout, k_pad - k)], dim=1)
-        w_off = self._append(w2.to(torch.bfloat16), 128)
+        if tf32:
+            # round to the nearest TF32 value (ties away from zero, = cvt.rna.tf32.f32): the tensor core truncates
+            w2 = ((w2.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        w_off = self._append(w2 if tf32 else w2.to(torch.bfloat16), 128)
         s_off = self._append(scale.detach().to(torch.float32).cpu(), 16)
         b_off = self._append(shift.detach().to(torch.float32).cpu(), 16)
         return w_off, s_off, b_off
@@ -230,6 +235,108 @@ class BackbonePlan:
                                         self._ws_bytes, ctypes.c_void_p(out.data_ptr()) if has_feat else None,
                                         ctypes.c_void_p(_stream_ptr(self.device))), "vad_plan_forward")
         return out if has_feat else None
+
+
+class Tf32Plan:
+    """Owns a ``vad_tf32_plan_t``: the same op table run with fp32 activations / weights and tcgen05 kind::tf32 MMAs
+    (features within 1e-3 of the reference's fp32 path; ``BackbonePlan`` is the bf16 production mode)."""
+
+    def __init__(self, ops: Sequence[Op], params: torch.Tensor, n_slots: int, device: torch.device, in_channels: int = 4) -> None:
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("Tf32Plan needs a CUDA device: this path has no CPU fallback")
+        self.ops = list(ops)
+        self.n_slots = n_slots
+        self.in_channels = in_channels
+        self.params = params.to(self.device) if not params.is_cuda else params
+        self._c_ops = (OpDesc * len(self.ops))(*[o.to_c() for o in self.ops])
+        self._h = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(self.lib.vad_tf32_plan_create(ctypes.byref(self._h), self._c_ops, len(self.ops), n_slots,
+                                            ctypes.c_void_p(self.params.data_ptr()), self.params.numel(), in_channels, dev_index),
+              "vad_tf32_plan_create")
+        self._cfg: Optional[Tuple[int, int, int, int]] = None
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_ptr = 0
+        self._ws_bytes = 0
+
+    def __del__(self) -> None:
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.lib.vad_tf32_plan_destroy(h)
+            self._h = ctypes.c_void_p()
+
+    def configure(self, batch: int, t: int, h: int, w: int) -> None:
+        if self._cfg == (batch, t, h, w):
+            return
+        need = ctypes.c_uint64()
+        check(self.lib.vad_tf32_plan_configure(self._h, batch, t, h, w, ctypes.byref(need)), "vad_tf32_plan_configure")
+        self._cfg = (batch, t, h, w)
+        self._ws_bytes = int(need.value)
+        if self._ws is None or self._ws.numel() < self._ws_bytes + 1024:
+            self._ws = None
+            self._ws = torch.empty(self._ws_bytes + 1024, dtype=torch.uint8, device=self.device)
+        self._ws_ptr = (self._ws.data_ptr() + 1023) // 1024 * 1024
+
+    @property
+    def flops(self) -> float:
+        return float(self.lib.vad_tf32_plan_flops(self._h))
+
+    @property
+    def num_launches(self) -> int:
+        return int(self.lib.vad_tf32_plan_num_launches(self._h))
+
+    def feature_dim(self) -> int:
+        for op in reversed(self.ops):
+            if op.kind == _lib.VAD_OP_AVGPOOL:
+                return self.slot_shape(op.src)[3]
+        raise RuntimeError("plan has no AVGPOOL op")
+
+    def slot_shape(self, slot: int) -> Tuple[int, int, int, int]:
+        dims = (ctypes.c_int32 * 4)()
+        check(self.lib.vad_tf32_plan_slot_info(self._h, slot, dims, None, None), "vad_tf32_plan_slot_info")
+        return tuple(int(v) for v in dims)
+
+    def slot_tensor(self, slot: int) -> torch.Tensor:
+        """fp32 view [batch, T, H, W, C] of a workspace slot (valid after ``forward``)."""
+        dims = (ctypes.c_int32 * 4)()
+        off = ctypes.c_uint64()
+        check(self.lib.vad_tf32_plan_slot_info(self._h, slot, dims, ctypes.byref(off), None), "vad_tf32_plan_slot_info")
+        batch = self._cfg[0]
+        t, h, w, c = (int(v) for v in dims)
+        start = self._ws_ptr - self._ws.data_ptr() + int(off.value)
+        n = batch * t * h * w * c
+        return self._ws[start:start + 4 * n].view(torch.float32).view(batch, t, h, w, c)
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """x: contiguous fp32 [batch, T, H, W, in_channels] on the device."""
+        _require_cuda(x, "x")
+        if x.dtype != torch.float32 or x.dim() != 5 or x.shape[-1] != self.in_channels or not x.is_contiguous():
+            raise ValueError(f"input must be a contiguous fp32 [batch, T, H, W, {self.in_channels}] tensor")
+        b, t, h, w, _ = x.shape
+        self.configure(b, t, h, w)
+        has_feat = any(op.kind == _lib.VAD_OP_AVGPOOL for op in self.ops)
+        if has_feat and out is None:
+            out = torch.empty(b, self.feature_dim(), dtype=torch.float32, device=self.device)
+        check(self.lib.vad_tf32_plan_forward(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(self._ws_ptr), self._ws_bytes,
+                                             ctypes.c_void_p(out.data_ptr()) if has_feat else None,
+                                             ctypes.c_void_p(_stream_ptr(self.device))), "vad_tf32_plan_forward")
+        return out if has_feat else None
+
+
+def ingest_ncthw_tf32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [B, 3, T, H, W] clips -> fp32 [B, T, H, W, 4] (zero fourth channel): the input of a ``Tf32Plan``."""
+    _require_cuda(x, "x")
+    if x.dtype != torch.float32 or x.dim() != 5 or x.shape[1] != 3:
+        raise ValueError("expected a float32 [B, 3, T, H, W] tensor")
+    x = x.contiguous()
+    b, _, t, h, w = x.shape
+    out = torch.empty(b, t, h, w, 4, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    check(lib.vad_tf32_ingest_ncthw(ctypes.c_void_p(x.data_ptr()), b, t, h, w, ctypes.c_void_p(out.data_ptr()),
+                                    ctypes.c_void_p(_stream_ptr(x.device))), "vad_tf32_ingest_ncthw")
+    return out
 
 
 def ingest_ncthw(x: torch.Tensor, pad_left: int) -> torch.Tensor:

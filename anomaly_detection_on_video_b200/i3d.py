@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import BackbonePlan, Op, ParamPacker, fold_bn, ingest_ncthw
+from .engine import BackbonePlan, Op, ParamPacker, Tf32Plan, fold_bn, ingest_ncthw, ingest_ncthw_tf32
 
 # (planes, blocks, spatial stride, temporal-conv flag per block): reference src/i3d.py:220-243
 I3RES50_STAGES: Tuple[Tuple[int, int, int, Tuple[int, ...]], ...] = (
@@ -68,6 +68,9 @@ class _NativeBackbone(nn.Module):
         self.force_gather = False  # debug: feed every conv through the cp.async gather producer
         self.fuse_stem_pool = True  # temporal half of maxpool1 in the stem epilogue (VAD_FLAG_POOL_T2)
         self.fuse_pool2 = False     # maxpool2 in layer1's last conv3 epilogue; set per forward from the clip length
+        # "bf16" (production: bf16 activations / weights, fp32 accumulate) or "tf32" (fp32 activations / weights, tcgen05
+        # kind::tf32 MMAs, general kernels only: features within 1e-3 of the reference's fp32 path)
+        self.precision = "bf16"
 
     # subclasses return (ops, packer, n_slots)
     def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
@@ -78,8 +81,15 @@ class _NativeBackbone(nn.Module):
         scale, shift = fold_bn(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
         if conv.bias is not None:
             shift = shift + conv.bias.detach().float() * scale
-        w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, fold_w=fold_w)
         k, s, p = _conv_geom(conv)
+        if self.precision == "tf32":
+            # fp32 weights, K padded to 32; the RGB stem reads the 4-channel (zero-padded) fp32 input, no folded window
+            cin = (conv.in_channels + 3) // 4 * 4
+            w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, cin_pad=cin, tf32=True)
+            return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, res=res, cin=cin, cout=conv.out_channels, kernel=k, stride=s, pad=p,
+                      flags=_lib.VAD_FLAG_RELU if relu else 0, dst_c_off=dst_c_off, dst_c_total=dst_c_total, w_off=w_off,
+                      scale_off=s_off, shift_off=b_off, name=name)
+        w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, fold_w=fold_w)
         flags = (_lib.VAD_FLAG_RELU if relu else 0) | (_lib.VAD_FLAG_STEM_FOLD_W if fold_w else 0)
         if self.force_gather:
             flags |= _lib.VAD_FLAG_FORCE_GATHER
@@ -91,13 +101,23 @@ class _NativeBackbone(nn.Module):
         # rebuild the packed blob whenever a parameter / buffer tensor was replaced or modified in place
         return tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers()))
 
-    def plan(self, device: torch.device) -> BackbonePlan:
-        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool, self.fuse_pool2)
+    def plan(self, device: torch.device):
+        if self.precision not in ("bf16", "tf32"):
+            raise ValueError(f"precision must be 'bf16' or 'tf32', not {self.precision!r}")
+        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool, self.fuse_pool2, self.precision)
         if self._plan is None or self._plan_key != key:
             ops, packer, n_slots = self._build_table()
-            self._plan = BackbonePlan(ops, packer.blob(), n_slots, self.pad_left, device)
+            if self.precision == "tf32":
+                self._plan = Tf32Plan(ops, packer.blob(), n_slots, device, in_channels=4)
+            else:
+                self._plan = BackbonePlan(ops, packer.blob(), n_slots, self.pad_left, device)
             self._plan_key = key
         return self._plan
+
+    @property
+    def _fused(self) -> bool:
+        """Fused-pool / folded-stem op-table variants exist for the bf16 kernels only."""
+        return self.precision == "bf16" and not self.force_gather
 
     def op_table(self) -> List[Op]:
         return self._build_table()[0]
@@ -106,6 +126,8 @@ class _NativeBackbone(nn.Module):
         """bf16 stem-layout clips [B, T, H, W+8, 4] (what ``Preprocessor`` emits) -> [B, C] fp32."""
         if self.training:
             raise RuntimeError("the native backbone is inference-only: call .eval() first (extract_features.py:36)")
+        if self.precision != "bf16":
+            raise RuntimeError("the stem layout is the bf16 mode's input; in tf32 mode call forward() with fp32 NCTHW clips")
         self._select_fusions(int(x_stem.shape[1]))
         return self.plan(x_stem.device).forward(x_stem)
 
@@ -117,7 +139,13 @@ class _NativeBackbone(nn.Module):
         if not batch.is_cuda:
             raise RuntimeError("I3D features are computed by sm_100a kernels only; move the input (and the model) "
                                "to a CUDA device. There is no CPU fallback.")
-        feats = self.forward_stem_layout(ingest_ncthw(batch.float(), self.pad_left))
+        if self.precision == "tf32":
+            if self.training:
+                raise RuntimeError("the native backbone is inference-only: call .eval() first (extract_features.py:36)")
+            self._select_fusions(int(batch.shape[2]))
+            feats = self.plan(batch.device).forward(ingest_ncthw_tf32(batch.float()))
+        else:
+            feats = self.forward_stem_layout(ingest_ncthw(batch.float(), self.pad_left))
         return feats.view(feats.shape[0], feats.shape[1], 1, 1, 1)
 
 
@@ -163,7 +191,7 @@ class I3Res50(_NativeBackbone):
         ops: List[Op] = []
         T1, T2, DS = 3, 4, 5  # bottleneck temporaries; slots 1/2 ping-pong the block input/output
         stem = self._conv_op(pk, self.conv1, self.bn1, src=0, dst=1, relu=True, fold_w=True, name="conv1")
-        if self.fuse_stem_pool and not self.force_gather:
+        if self.fuse_stem_pool and self._fused:
             # maxpool1 = max over (2,3,3) / stride (2,2,2), pad 0 (reference src/i3d.py:212-214) separates exactly into
             # a max over frame pairs -- done in the stem kernel's epilogue, so the full-rate stem output never
             # reaches HBM -- followed by a spatial (1,3,3) / (1,2,2) max-pool.
@@ -186,7 +214,7 @@ class I3Res50(_NativeBackbone):
                     res = DS
                 conv3 = self._conv_op(pk, blk.conv3, blk.bn3, T2, nxt, relu=True, res=res, name=n + ".conv3")
                 last_of_layer1 = li == 1 and bi == len(getattr(self, "layer1")) - 1
-                if last_of_layer1 and self.fuse_pool2 and not self.force_gather:
+                if last_of_layer1 and self.fuse_pool2 and self._fused:
                     # maxpool2 = max over frame pairs (reference src/i3d.py:215-217,309) in conv3's staged epilogue: the
                     # unpooled block output (991 MB per 160 clips) is never written and no pool kernel runs.  Needs the
                     # 4-frame feature map of a 16-frame clip; other clip lengths take the separate pool below.
@@ -194,7 +222,7 @@ class I3Res50(_NativeBackbone):
                     conv3.name = n + ".conv3+maxpool2"
                 ops.append(conv3)
                 cur = nxt
-            if li == 1 and not (self.fuse_pool2 and not self.force_gather):
+            if li == 1 and not (self.fuse_pool2 and self._fused):
                 nxt = 1 if cur == 2 else 2
                 ops.append(Op(kind=_lib.VAD_OP_MAXPOOL, src=cur, dst=nxt, kernel=(2, 1, 1), stride=(2, 1, 1), name="maxpool2"))
                 cur = nxt

@@ -256,6 +256,31 @@ int32_t vad_head_num_launches(const vad_head_t* head);
 double vad_head_flops(const vad_head_t* head, int32_t n_seq, int32_t t);
 void vad_head_destroy(vad_head_t* head);
 
+/* ------------------------------------------------------------------------------------------------
+ * TF32 precision mode of the backbone (BASELINE.json: "bf16 vs TF32 modes"; features within 1e-3 of the
+ * reference's fp32 path).  Same op table and slot / channel-slice semantics as vad_plan_*, with
+ *   - every slot a plain fp32 [batch, T, H, W, C] tensor (slot 0: the caller's input, C = in_channels,
+ *     a multiple of 4 -- RGB padded with a zero channel, see vad_tf32_ingest_ncthw),
+ *   - weights fp32 [cout][K_pad], K = (dt, dh, dw, cin) padded to a multiple of 32, scale / shift fp32,
+ *   - no STEM_FOLD_W / POOL_T2 flags (the unfused op list).
+ * Replaces the same reference code as vad_plan_* (src/i3d.py:199-318) in the higher-precision mode. */
+typedef struct vad_tf32_plan vad_tf32_plan_t;
+int32_t vad_tf32_plan_create(vad_tf32_plan_t** plan, const vad_op_desc* ops, int32_t n_ops, int32_t n_slots,
+                             const void* params_dev, uint64_t params_bytes, int32_t in_channels, int32_t device);
+int32_t vad_tf32_plan_configure(vad_tf32_plan_t* plan, int32_t batch, int32_t t, int32_t h, int32_t w,
+                                uint64_t* workspace_bytes);
+int32_t vad_tf32_plan_forward(vad_tf32_plan_t* plan, const void* x_dev, void* workspace_dev,
+                              uint64_t workspace_bytes, float* feat_out_dev, void* stream);
+int32_t vad_tf32_plan_slot_info(const vad_tf32_plan_t* plan, int32_t slot, int32_t* dims4, uint64_t* offset,
+                                uint64_t* bytes);
+int32_t vad_tf32_plan_num_launches(const vad_tf32_plan_t* plan);
+double vad_tf32_plan_flops(const vad_tf32_plan_t* plan);
+void vad_tf32_plan_destroy(vad_tf32_plan_t* plan);
+/* fp32 [batch, 3, T, H, W] (the tensor the reference hands its model, extract_features.py:86) ->
+ * fp32 [batch, T, H, W, 4] with a zero fourth channel: slot 0 of a TF32 plan with in_channels = 4. */
+int32_t vad_tf32_ingest_ncthw(const float* x_dev, int32_t batch, int32_t t, int32_t h, int32_t w, float* out_dev,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,146 @@
+"""-m gpu: the TF32 precision mode (vad_tf32_*: fp32 activations / weights, tcgen05 kind::tf32 MMAs).
+
+Tolerance (BASELINE.json north_star: "1e-3 for the TF32 mode"): as for bf16, relative error is measured against the
+scale of the tensor -- max|a-b| <= 1e-3 * max|b| and ||a-b|| <= 1e-3 * ||b|| -- with cosine >= 0.99999.
+Reference = the reference's own fp32 PyTorch path (golden features made by the unmodified reference, tests/golden) and
+torch fp32 conv3d / max_pool3d on the CPU for the single-op cases.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import i3res50 as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def close_tf32(got: torch.Tensor, ref: torch.Tensor, tol: float = TOL):
+    got, ref = got.double(), ref.double()
+    assert got.shape == ref.shape
+    max_norm = ((got - ref).abs().max() / ref.abs().max()).item()
+    rel_l2 = ((got - ref).norm() / ref.norm()).item()
+    print(f"max-normalised err {max_norm:.2e}, rel L2 {rel_l2:.2e}")
+    assert max_norm <= tol and rel_l2 <= tol, (max_norm, rel_l2)
+
+
+CONV_CASES = [
+    # name, cin, cout, k, s, p, B, T, H, W, res, relu
+    ("stem 5x7x7/2 4->64", 4, 64, (5, 7, 7), (2, 2, 2), (2, 3, 3), 1, 8, 32, 32, False, True),
+    ("1x1 64->256 +res", 256, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 2, 9, 9, True, True),
+    ("t3 256->64", 256, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 4, 7, 7, False, True),
+    ("s3x3 stride 2 128->128", 128, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), 2, 2, 14, 14, False, True),
+    ("1x1 stride 2 256->512 ds, linear", 256, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, 2, 14, 14, False, False),
+    ("3x3x3 24->40 (cin % 32 != 0, N tail)", 24, 40, (3, 3, 3), (1, 1, 1), (1, 1, 1), 2, 3, 6, 5, False, True),
+    ("1x1 2048->512 long K", 2048, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 7, 7, False, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_tf32_matches_fp32_conv3d(cuda_device, case):
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+
+    _, cin, cout, k, s, p, B, T, H, W, res, relu = case
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, T, H, W, generator=g)
+    w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
+    scale, shift = 0.5 + torch.rand(cout, generator=g), 0.2 * torch.randn(cout, generator=g)
+    ref = F.conv3d(x, w, None, s, p) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    if res:
+        ref = ref + x[:, :cout]
+    if relu:
+        ref = F.relu(ref)
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, scale, shift, tf32=True)
+    ops = []
+    if res:  # residual = the conv input, copied into slot 1 by an identity max-pool
+        ops.append(eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=1, kernel=(1, 1, 1), stride=(1, 1, 1)))
+    ops.append(eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=2, res=1 if res else -1, cin=cin, cout=cout, kernel=k, stride=s, pad=p,
+                      flags=lib.VAD_FLAG_RELU if relu else 0, w_off=w_off, scale_off=s_off, shift_off=b_off))
+    plan = eng.Tf32Plan(ops, pk.blob(), 3, cuda_device, in_channels=cin)
+    plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
+    torch.cuda.synchronize()
+    out = plan.slot_tensor(2).cpu().permute(0, 4, 1, 2, 3)
+    close_tf32(out, ref)
+
+
+def test_pools_and_channel_slices_are_exact(cuda_device):
+    """fp32 max-pools (torch semantics and the SAME-padding port) are exact; two ops write disjoint channel slices of
+    one destination (the Inception concat)."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+    from oracle.inception import _same_pad
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 5, 11, 9, generator=g)
+    pk = eng.ParamPacker()
+    pk.add_conv(torch.zeros(4, 4, 1, 1, 1), torch.ones(4), torch.zeros(4), tf32=True)  # a non-empty blob
+    ops = [eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=1, kernel=(2, 3, 3), stride=(2, 2, 2)),
+           eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=2, kernel=(3, 3, 3), stride=(1, 1, 1), flags=lib.VAD_FLAG_POOL_SAME, dst_c_off=0,
+                  dst_c_total=64),
+           eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=2, kernel=(1, 1, 1), stride=(1, 1, 1), dst_c_off=32, dst_c_total=64)]
+    plan = eng.Tf32Plan(ops, pk.blob(), 3, cuda_device, in_channels=32)
+    plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
+    torch.cuda.synchronize()
+    a = plan.slot_tensor(1).cpu().permute(0, 4, 1, 2, 3)
+    assert torch.equal(a, F.max_pool3d(x, (2, 3, 3), (2, 2, 2)))
+    b = plan.slot_tensor(2).cpu().permute(0, 4, 1, 2, 3)
+    assert torch.equal(b[:, :32], F.max_pool3d(_same_pad(x, (3, 3, 3), (1, 1, 1)), (3, 3, 3), (1, 1, 1)))
+    assert torch.equal(b[:, 32:], x)
+
+
+@pytest.fixture(scope="module")
+def model(cuda_device):
+    from anomaly_detection_on_video_b200.i3d import I3Res50
+
+    m = I3Res50()
+    m.load_state_dict(O.seeded_state_dict(0), strict=True)
+    m.precision = "tf32"
+    return m.eval().to(cuda_device)
+
+
+@pytest.mark.parametrize("tag", ["small", "odd", "full"])
+def test_i3res50_tf32_features_match_reference_golden(model, cuda_device, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "i3res50.npz"))
+    shape = tuple(int(v) for v in g[f"{tag}/shape"])
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).clamp(-2.0, 2.4444)
+    y = model(x.to(cuda_device))
+    assert tuple(y.shape) == (shape[0], 2048, 1, 1, 1) and y.dtype == torch.float32
+    got, want = y.cpu().view(shape[0], -1), torch.from_numpy(g[f"{tag}/features"])
+    for b in range(shape[0]):
+        close_tf32(got[b], want[b])
+        assert F.cosine_similarity(got[b].double(), want[b].double(), dim=0).item() >= 0.99999
+
+
+def test_tf32_is_tighter_than_bf16_and_modes_switch(model, cuda_device):
+    """Same module, both modes: tf32 lands >= 5x closer to the fp32 oracle than bf16, and switching back works."""
+    x = torch.randn(2, 3, 8, 64, 64, generator=torch.Generator().manual_seed(4)).clamp(-2.0, 2.4444)
+    y32, _ = O.forward(x, O.seeded_state_dict(0))
+    scale = y32.abs().max()
+    e_tf32 = ((model(x.to(cuda_device)).cpu().view(2, -1) - y32.view(2, -1)).abs().max() / scale).item()
+    model.precision = "bf16"
+    try:
+        e_bf16 = ((model(x.to(cuda_device)).cpu().view(2, -1) - y32.view(2, -1)).abs().max() / scale).item()
+    finally:
+        model.precision = "tf32"
+    print(f"max-normalised error: tf32 {e_tf32:.2e}, bf16 {e_bf16:.2e}")
+    assert e_tf32 <= TOL and e_tf32 * 5 <= e_bf16
+    with pytest.raises(RuntimeError):
+        model.forward_stem_layout(torch.zeros(1, 8, 64, 72, 4, dtype=torch.bfloat16, device=cuda_device))
+
+
+def test_inception_tf32_features_match_fp32_oracle(cuda_device):
+    from anomaly_detection_on_video_b200.inception import InceptionI3d
+    from oracle import inception as OI
+
+    m = InceptionI3d()
+    m.load_state_dict(OI.seeded_state_dict(0), strict=True)
+    m.precision = "tf32"
+    m.eval().to(cuda_device)
+    x = torch.randn(1, 3, 16, 224, 224, generator=torch.Generator().manual_seed(1)).clamp(-2.0, 2.4444)
+    got = m(x.to(cuda_device)).cpu().view(1, -1)
+    ref = OI.extract_features(x, OI.seeded_state_dict(0)).view(1, -1)
+    close_tf32(got[0], ref[0])

@@ -203,3 +203,27 @@ def test_bind_to_gpu_is_best_effort_without_nvml(monkeypatch):
     monkeypatch.setenv("VAD_NO_NUMA_BIND", "1")
     assert bind_to_gpu(0)["bound"] is False
     assert os.sched_getaffinity(0) == before
+
+
+def test_tf32_weight_packing_rounds_to_tf32_and_pads_k_to_32():
+    """ParamPacker.add_conv(tf32=True): fp32 [cout, K_pad32] rows, every value rounded to the nearest TF32 (10-bit mantissa,
+    ties away from zero -- what cvt.rna.tf32.f32 does), (kt, kh, kw, cin) order with cin padded."""
+    import torch
+
+    from anomaly_detection_on_video_b200.engine import ParamPacker
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 3, 1, 2, 2, generator=g)
+    pk = ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, torch.ones(8), torch.zeros(8), cin_pad=4, tf32=True)
+    blob = pk.blob()
+    k, k_pad = 1 * 2 * 2 * 4, 32
+    rows = blob[w_off:w_off + 8 * k_pad * 4].view(torch.float32).view(8, k_pad)
+    assert s_off >= w_off + 8 * k_pad * 4 and b_off > s_off
+    assert torch.all(rows[:, k:] == 0)
+    packed = rows[:, :k].view(8, 1, 2, 2, 4)
+    assert torch.all(packed[..., 3] == 0)
+    want = w.permute(0, 2, 3, 4, 1)
+    got = packed[..., :3]
+    assert torch.all((got.contiguous().view(torch.int32) & 0x1FFF) == 0)          # low 13 mantissa bits clear
+    assert torch.all((got - want).abs() <= want.abs() * 2.0 ** -11 + 1e-30)       # nearest, not truncated
