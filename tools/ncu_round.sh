@@ -19,7 +19,7 @@ full() {  # name, kernel regex, skip, count
   if [ "$sz" -gt 12000000 ]; then rm -f gpurun_out/${TAG}_$1.ncu-rep; fi
 }
 full stem 'stem_umma' 0 1
-full conv_l1 'conv_umma|conv_thalo|conv_s3x3' 0 8
-full conv_l3 'conv_umma|conv_thalo|conv_s3x3' 27 4
+full conv_l1 'conv_umma|conv_thalo|conv_s3x3|conv_pair' 0 8
+full conv_l3 'conv_umma|conv_thalo|conv_s3x3|conv_pair' 27 4
 full aux 'maxpool|preprocess|avgpool|segment' 0 5
 du -sh gpurun_out
