@@ -162,6 +162,12 @@ def main():
         reference_arm(args)
         return
 
+    # stdout carries exactly one line, the JSON result: anything a library prints there while the bench runs (NCCL's
+    # version banner on the first communicator, for one) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -437,7 +443,8 @@ def main():
                                        "profiled pass (events between launches switch off the PDL overlap, so that pass is "
                                        "slower than step_ms); the rest is preprocessing, feature scatter, segment mean, gaps"},
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
