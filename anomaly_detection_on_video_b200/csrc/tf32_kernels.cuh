@@ -4,11 +4,12 @@
 // :262-272, :303-318) for the accuracy mode BASELINE.json asks for beside bf16 (features within 1e-3 of the fp32
 // reference instead of 1e-2).  One general kernel per op kind -- this mode trades the layer-specialised bf16 kernels for
 // precision, so it is built for coverage (any kernel / stride / padding, cin % 4 == 0) rather than for peak:
-//   conv_tf32_kernel<BN>   persistent 128 x BN tiles; warp 0: TMA producer of the weight tile (fp32 [cout, K_pad] map,
-//                          32 floats = one 128-byte swizzled row per k-block), warp 1: single-thread MMA issuer,
-//                          warps 2-5: epilogue (TMEM -> scale/shift (+residual) (+ReLU) -> fp32 channels-last, written into
-//                          a channel slice of the destination), warps 6-9: activation gather (cp.async 16 B = 4 channels
-//                          with zero fill for padding, into the 128B-swizzled A tile).
+//   conv_tf32_kernel<BN, TMA_A>  persistent 128 x BN tiles; warp 0: TMA producer of the weight tile (fp32 [cout, K_pad] map,
+//                          32 floats = one 128-byte swizzled row per k-block) and, for Cin % 32 == 0, of the activation
+//                          tile (rank-5 fp32 im2col map); warp 1: single-thread MMA issuer; warps 2-5: epilogue (TMEM ->
+//                          scale/shift (+residual) (+ReLU) -> TF32-rounded fp32 channels-last, written into a channel
+//                          slice of the destination); warps 6-9: activation gather for the other layers (cp.async
+//                          16 B = 4 channels with zero fill for padding, into the 128B-swizzled A tile).
 //   maxpool3d_f32_kernel   one thread per (output pixel, 4-channel vector)
 //   avgpool_f32_kernel     [B, P, C] fp32 -> [B, C] fp32, a warp per 128 channels
 //   ingest_ncthw_f32_to_ndhwc4_kernel   the reference's fp32 NCTHW clip -> channels-last with RGB padded to 4 channels
@@ -26,6 +27,8 @@ struct Tf32ConvParams {
   int Ti, Hi, Wi;
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
   int cin, ntaps;
+  int fold;  // 1 (RGB stem, Cin = 4, kw <= 8): a k-block is one (dt, dh) tap x a window of 8 consecutive pixels x 4 channels,
+             // 128 contiguous bytes of the input row; weights carry zeros for window pixels >= kw
   long long sN, sT, sH, sW;  // input strides in elements
   int relu;
   int ldo, ldr;  // output / residual row pitch in elements
@@ -58,9 +61,12 @@ struct Tf32Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * BN * 4 + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
-template <int BN>
+// TMA_A: the activation tile comes from a rank-5 fp32 im2col tensor map (128 output pixels x 32 channels per k-block,
+// halo zero-filled by the TMA unit) issued by the producer thread next to the weight tile; needs Cin % 32 == 0.  Otherwise
+// the four gather warps build the tile with zero-filling cp.async (any Cin % 4 == 0: the RGB stem, Inception's 16/24/48).
+template <int BN, bool TMA_A>
 __global__ void __launch_bounds__(Tf32Cfg<BN>::kThreads, 1)
-conv_tf32_kernel(const __grid_constant__ CUtensorMap tmB, const Tf32ConvParams p) {
+conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tf32ConvParams p) {
   using Cfg = Tf32Cfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -80,8 +86,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmB, const Tf32ConvParams p
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmB);
+    if (TMA_A) tma_prefetch_desc(&tmA);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1 + 128);  // weight TMA (expect_tx) + one arrival per gather thread
+      mbar_init(&full_bar[s], TMA_A ? 1 : 1 + 128);  // TMA (expect_tx) (+ one arrival per gather thread)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -106,9 +113,27 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmB, const Tf32ConvParams p
       uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * BN;
+        int wq = 0, hq = 0, dq = 0, nq = 0;
+        if (TMA_A) {  // base pixel of the tile's first row, in input coordinates
+          int t = (tile / p.n_tiles) * kBlockM;
+          const int wo = t % p.Wo; t /= p.Wo;
+          const int ho = t % p.Ho; t /= p.Ho;
+          const int to = t % p.To; t /= p.To;
+          wq = wo * p.sw - p.pw; hq = ho * p.sh - p.ph; dq = to * p.st - p.pt; nq = t;
+        }
+        int c0 = 0, dw = 0, dh = 0, dt = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait_a(empty0 + s * 8, ph ^ 1u);
-          mbar_arrive_expect_tx_a(full0 + s * 8, (uint32_t)Cfg::kBBytes);
+          mbar_arrive_expect_tx_a(full0 + s * 8, (uint32_t)(TMA_A ? Cfg::kStageBytes : Cfg::kBBytes));
+          if (TMA_A) {
+            tma_load_im2col_5d_a(stage0 + s * Cfg::kStageBytes, &tmA, full0 + s * 8, c0, wq, hq, dq, nq, (uint16_t)dw, (uint16_t)dh,
+                                 (uint16_t)dt);
+            c0 += 32;
+            if (c0 >= p.cin) {
+              c0 = 0;
+              if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
+            }
+          }
           tma_load_2d_a(stage0 + s * Cfg::kStageBytes + Cfg::kABytes, &tmB, full0 + s * 8, kb * 32, n0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -206,7 +231,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmB, const Tf32ConvParams p
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
-  } else {
+  } else if (!TMA_A) {
     // ------------------------------------------------------------------ activation gather (one tile row per thread)
     constexpr int LAG = Cfg::kGatherLag;
     const int t = threadIdx.x - 192;
@@ -239,6 +264,27 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmB, const Tf32ConvParams p
         const uint32_t ph = (g / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t dst_row = smem_u32(stage_base + s * Cfg::kStageBytes) + (uint32_t)t * 128u;
+        if (p.fold) {
+          // one (dt, dh) tap: 8 consecutive input pixels x 4 channels, one 16-byte chunk per pixel
+          const int ti = t_base + dt, hi = h_base + dh;
+          const bool rv = row_ok && (unsigned)ti < (unsigned)p.Ti && (unsigned)hi < (unsigned)p.Hi;
+          const float* row = img + ti * p.sT + hi * p.sH;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int wi = w_base + j;
+            const bool okj = rv && (unsigned)wi < (unsigned)p.Wi;
+            cp_async_16_zfill(dst_row + (((uint32_t)j ^ sw_xor) << 4), okj ? row + wi * 4 : p.in, okj ? 16u : 0u);
+          }
+          if (++dh == p.kh) { dh = 0; ++dt; }
+          cp_async_commit();
+          ++g;
+          if (g > LAG) {
+            cp_async_wait<LAG>();
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[(g - 1 - LAG) % STAGES]);
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 8 chunks of 4 channels
           cp_async_16_zfill(dst_row + (((uint32_t)j ^ sw_xor) << 4), src + (ok ? c : 0), ok ? 16u : 0u);

@@ -85,10 +85,11 @@ class _NativeBackbone(nn.Module):
         if self.precision == "tf32":
             # fp32 weights, K padded to 32; the RGB stem reads the 4-channel (zero-padded) fp32 input, no folded window
             cin = (conv.in_channels + 3) // 4 * 4
-            w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, cin_pad=cin, tf32=True)
+            fold = fold_w and cin == 4 and k[2] <= 8  # RGB stem: contract 8-pixel x 4-channel windows (contiguous 128 B)
+            w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, cin_pad=cin, tf32=True, fold_w=fold)
             return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, res=res, cin=cin, cout=conv.out_channels, kernel=k, stride=s, pad=p,
-                      flags=_lib.VAD_FLAG_RELU if relu else 0, dst_c_off=dst_c_off, dst_c_total=dst_c_total, w_off=w_off,
-                      scale_off=s_off, shift_off=b_off, name=name)
+                      flags=(_lib.VAD_FLAG_RELU if relu else 0) | (_lib.VAD_FLAG_STEM_FOLD_W if fold else 0), dst_c_off=dst_c_off,
+                      dst_c_total=dst_c_total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
         w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, fold_w=fold_w)
         flags = (_lib.VAD_FLAG_RELU if relu else 0) | (_lib.VAD_FLAG_STEM_FOLD_W if fold_w else 0)
         if self.force_gather:

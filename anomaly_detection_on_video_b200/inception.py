@@ -111,9 +111,11 @@ class InceptionI3d(_NativeBackbone):
         if self.precision == "tf32":
             conv = u.conv3d
             cin = (conv.in_channels + 3) // 4 * 4
-            w_off, s_off, b_off = pk.add_conv(conv.weight, scale, shift, cin_pad=cin, tf32=True)
+            fold = fold_w and cin == 4 and conv.kernel_size[2] <= 8
+            w_off, s_off, b_off = pk.add_conv(conv.weight, scale, shift, cin_pad=cin, tf32=True, fold_w=fold)
             return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, cin=cin, cout=conv.out_channels, kernel=tuple(conv.kernel_size),
-                      stride=tuple(conv.stride), pad=(0, 0, 0), flags=_lib.VAD_FLAG_RELU | _lib.VAD_FLAG_CONV_SAME, dst_c_off=off,
+                      stride=tuple(conv.stride), pad=(0, 0, 0),
+                      flags=_lib.VAD_FLAG_RELU | _lib.VAD_FLAG_CONV_SAME | (_lib.VAD_FLAG_STEM_FOLD_W if fold else 0), dst_c_off=off,
                       dst_c_total=total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
         w_off, s_off, b_off = pk.add_conv(u.conv3d.weight, scale, shift, fold_w=fold_w)
         flags = _lib.VAD_FLAG_RELU | _lib.VAD_FLAG_CONV_SAME | (_lib.VAD_FLAG_STEM_FOLD_W if fold_w else 0)

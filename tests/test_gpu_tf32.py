@@ -41,7 +41,9 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_tf32_matches_fp32_conv3d(cuda_device, case):
+def test_conv_tf32_matches_fp32_conv3d(cuda_device, case, monkeypatch):
+    """Every case runs twice: activation tile by TMA im2col where Cin % 32 == 0 (the default) and by the cp.async gather
+    (VAD_TF32_GATHER=1); same k order per accumulator, so the two must agree bit for bit."""
     from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
 
     _, cin, cout, k, s, p, B, T, H, W, res, relu = case
@@ -61,11 +63,62 @@ def test_conv_tf32_matches_fp32_conv3d(cuda_device, case):
         ops.append(eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=1, kernel=(1, 1, 1), stride=(1, 1, 1)))
     ops.append(eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=2, res=1 if res else -1, cin=cin, cout=cout, kernel=k, stride=s, pad=p,
                       flags=lib.VAD_FLAG_RELU if relu else 0, w_off=w_off, scale_off=s_off, shift_off=b_off))
-    plan = eng.Tf32Plan(ops, pk.blob(), 3, cuda_device, in_channels=cin)
+    outs = []
+    for gather in ("0", "1"):
+        monkeypatch.setenv("VAD_TF32_GATHER", gather)
+        plan = eng.Tf32Plan(ops, pk.blob(), 3, cuda_device, in_channels=cin)
+        plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
+        torch.cuda.synchronize()
+        outs.append(plan.slot_tensor(2).cpu().permute(0, 4, 1, 2, 3).clone())
+    close_tf32(outs[0], ref)
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("cin,cout,k,s,T,H,W", [(64, 64, (3, 3, 3), (2, 2, 2), 6, 15, 20), (64, 128, (7, 7, 7), (2, 2, 2), 8, 16, 16),
+                                                (48, 64, (3, 3, 3), (1, 1, 1), 4, 7, 7), (4, 64, (7, 7, 7), (2, 2, 2), 8, 32, 32)])
+def test_conv_tf32_same_padding(cuda_device, cin, cout, k, s, T, H, W):
+    """VAD_FLAG_CONV_SAME (asymmetric TF-style padding of the Inception port) through both activation producers."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+    from oracle.inception import _same_pad
+
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, cin, T, H, W, generator=g)
+    w = torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5
+    scale, shift = 0.5 + torch.rand(cout, generator=g), 0.2 * torch.randn(cout, generator=g)
+    ref = F.relu(F.conv3d(_same_pad(x, k, s), w, None, s) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, scale, shift, tf32=True)
+    ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=cin, cout=cout, kernel=k, stride=s, flags=lib.VAD_FLAG_RELU | lib.VAD_FLAG_CONV_SAME,
+                  w_off=w_off, scale_off=s_off, shift_off=b_off)]
+    plan = eng.Tf32Plan(ops, pk.blob(), 2, cuda_device, in_channels=cin)
     plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
     torch.cuda.synchronize()
-    out = plan.slot_tensor(2).cpu().permute(0, 4, 1, 2, 3)
-    close_tf32(out, ref)
+    close_tf32(plan.slot_tensor(1).cpu().permute(0, 4, 1, 2, 3), ref)
+
+
+@pytest.mark.parametrize("k,s,same", [((5, 7, 7), (2, 2, 2), False), ((7, 7, 7), (2, 2, 2), True), ((3, 5, 8), (1, 1, 2), False)])
+def test_stem_folded_window_gather(cuda_device, k, s, same):
+    """VAD_FLAG_STEM_FOLD_W in the TF32 mode: the RGB stem contracts (dt, dh) taps x 8-pixel x 4-channel windows (128
+    contiguous bytes per tile row and k-block) instead of gathering 16 bytes per tap."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+    from oracle.inception import _same_pad
+
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 3, 9, 30, 34, generator=g)
+    w = torch.randn(64, 3, *k, generator=g) * (2.0 / (3 * k[0] * k[1] * k[2])) ** 0.5
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    pad = (0, 0, 0) if same else (k[0] // 2, k[1] // 2, k[2] // 2)
+    xin = _same_pad(x, k, s) if same else x
+    ref = F.relu(F.conv3d(xin, w, None, s, pad) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, scale, shift, fold_w=True, tf32=True)
+    flags = lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W | (lib.VAD_FLAG_CONV_SAME if same else 0)
+    ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=4, cout=64, kernel=k, stride=s, pad=pad, flags=flags, w_off=w_off,
+                  scale_off=s_off, shift_off=b_off)]
+    plan = eng.Tf32Plan(ops, pk.blob(), 2, cuda_device, in_channels=4)
+    plan.forward(eng.ingest_ncthw_tf32(x.to(cuda_device)))
+    torch.cuda.synchronize()
+    close_tf32(plan.slot_tensor(1).cpu().permute(0, 4, 1, 2, 3), ref)
 
 
 def test_pools_and_channel_slices_are_exact(cuda_device):
