@@ -66,7 +66,8 @@ struct ConvCfg {
   static_assert(BK == 64 || BK == 32, "BK is one swizzle row: 64 (SW128) or 32 (SW64) bf16");
   static_assert(!GATHER || BK == 64, "the gather producer writes 128-byte swizzled rows");
   static_assert(!EPI || BN <= 128, "the staged epilogue keeps two 128 x BN bf16 tiles in shared memory");
-  static_assert(KPS == 1 || (KPS == 2 && !GATHER && BK == 64), "two k-blocks per stage: TMA producers, SW128 only");
+  static_assert(KPS == 1 || (KPS == 2 && !GATHER && BK == 64) || (KPS == 4 && !GATHER && BK == 32),
+                "several k-blocks per stage: TMA producers; 2 x 64-wide (SW128) or 4 x 32-wide (SW64: the folded stem window view)");
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kABytes = kBlockM * kRowBytes;   // one k-block of A
   static constexpr int kBBytes = BN * kRowBytes;        // one k-block of B
@@ -362,7 +363,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           };
           if (KPS == 1 || nk == KPS) issue(std::integral_constant<int, KPS>{});
-          else                       issue(std::integral_constant<int, 1>{});
+          else if (KPS > 2 && nk == 3) issue(std::integral_constant<int, (KPS > 2 ? 3 : 1)>{});
+          else if (KPS > 2 && nk == 2) issue(std::integral_constant<int, (KPS > 2 ? 2 : 1)>{});
+          else                         issue(std::integral_constant<int, 1>{});
           if (MC) umma_commit_mc(empty0 + s * 8, (uint16_t)3);  // frees the slot in both CTAs of the pair
           else    umma_commit_a(empty0 + s * 8);               // frees the smem stage once these MMAs have read it
           if (last_stage) { umma_commit_a(tfull0 + acc * 8); ++tc; }  // accumulator complete

@@ -363,6 +363,9 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         if (c128 * 100 < c256 * p->bn_model) r.bn = 128;
       }
       r.kps = (r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2 && !r.epi) ? 2 : 1;
+      // folded stem through the generic kernel (InceptionI3d's 7x7x7): a 32-wide k-block is only two N = 64 MMAs, far below
+      // the ~300 cycles a barrier round trip costs the issuing thread; four of them per stage
+      if (r.a_mode == A_TMA_IM2COL && r.bk == 32 && c.num_kb >= 4 && !r.epi) r.kps = 4;
       if (p->kps_override == 1) r.kps = 1;
       if (p->kps_override == 2 && r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2) r.kps = 2;
       long long m_tiles = (M + kBlockM - 1) / kBlockM;
@@ -880,7 +883,8 @@ static cudaError_t launch_conv_pair(const OpRuntime& r, cudaStream_t st) {
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
   if (r.pair || r.pair_epi) return launch_conv_pair(r, st);
   if (r.mc) return launch_conv_mc(r, st);
-  if (r.bk == 32) return launch_conv<64, 32, 1, false, false>(r, st);  // folded stem, TMA window view
+  if (r.bk == 32)  // folded stem, TMA window view
+    return r.kps == 4 ? launch_conv<64, 32, 4, false, false>(r, st) : launch_conv<64, 32, 1, false, false>(r, st);
   if (r.epi) return r.bn == 128 ? launch_conv_bn<128, true>(r, st) : launch_conv_bn<64, true>(r, st);
   switch (r.bn) {
     case 256: return r.a_mode == A_GATHER ? launch_conv<256, 64, 1, true, false>(r, st) : launch_conv<256, 64, 1, false, false>(r, st);

@@ -102,6 +102,33 @@ def test_stem_conv_folded_window(cuda_device, shape):
     assert_bf16_close(out, ref)
 
 
+@pytest.mark.parametrize("k,kps", [((5, 7, 7), "0"), ((5, 7, 7), "1"), ((7, 7, 7), "0"), ((3, 7, 7), "0"), ((2, 5, 7), "0")])
+def test_stem_through_the_generic_kernel(cuda_device, k, kps, monkeypatch):
+    """VAD_STEM_GENERIC=1: the folded stem window view through conv_umma_kernel<64, 32, 4> -- four 32-wide k-blocks per
+    pipeline stage, with 35 / 49 / 21 / 10 k-blocks leaving a last stage of 3 / 1 / 1 / 2 -- and (VAD_KPS=1) one per stage.
+    This is the path InceptionI3d's 7x7x7 stem takes."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+    from gpu_util import assert_bf16_close
+
+    monkeypatch.setenv("VAD_STEM_GENERIC", "1")
+    if kps != "0":
+        monkeypatch.setenv("VAD_KPS", kps)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 8, 40, 36, generator=g).clamp(-2, 2.44)
+    w = (torch.randn(64, 3, *k, generator=g) * 0.045).to(torch.bfloat16).float()
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    pad = (k[0] // 2, k[1] // 2, k[2] // 2)
+    ref = F.relu(F.conv3d(x.to(torch.bfloat16).float(), w, None, (2, 2, 2), pad) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, scale, shift, fold_w=True)
+    ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=4, cout=64, kernel=k, stride=(2, 2, 2), pad=pad,
+                  flags=lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W, w_off=w_off, scale_off=s_off, shift_off=b_off)]
+    plan = eng.BackbonePlan(ops, pk.blob(), 2, 3, cuda_device)
+    plan.forward(eng.ingest_ncthw(x.to(cuda_device), 3))
+    torch.cuda.synchronize()
+    assert_bf16_close(plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3), ref)
+
+
 @pytest.mark.parametrize("shape,slice_", [((1, 16, 224, 224), (0, 0)), ((2, 10, 64, 48), (0, 0)), ((1, 8, 50, 38), (64, 192))])
 def test_stem_fused_temporal_pool_is_exact(cuda_device, shape, slice_):
     """VAD_FLAG_POOL_T2 (max over output frame pairs in the stem epilogue) == unfused stem followed by a
