@@ -332,6 +332,115 @@ __global__ void __launch_bounds__(256) maxpool3d_fixed_kernel(const PoolParams p
   }
 }
 
+// Padded windows with compile-time extents (the SAME-padding pools of the Inception port between stages: (1,3,3)/(1,2,2),
+// (3,3,3)/(2,2,2), (2,2,2)/(2,2,2)): every tap's 128-bit load is issued (predicated on its bounds) before the first max,
+// instead of the dependent load -> max chain of the general kernel.
+// read-only 128-bit load that DOES allocate in L1: neighbouring threads of the sliding-window pool re-read the same lines
+__device__ __forceinline__ uint4 ld_nc_16(const void* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+
+template <int KT, int KH, int KW>
+__global__ void __launch_bounds__(256) maxpool3d_checked_kernel(const PoolParams p) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)p.B * p.To * p.Ho * p.Wo * cv;
+  const long long sW = p.C, sH = (long long)p.Wi * p.C, sT = sH * p.Hi;
+  const uint32_t neg_inf2 = 0xFF80FF80u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long m = i / cv;
+    const long long m_out = m;
+    const int wo = (int)(m % p.Wo); m /= p.Wo;
+    const int ho = (int)(m % p.Ho); m /= p.Ho;
+    const int to = (int)(m % p.To); m /= p.To;
+    const int t0 = to * p.st - p.pt, h0 = ho * p.sh - p.ph, w0 = wo * p.sw - p.pw;
+    const __nv_bfloat16* base = p.in + (m * p.Ti + t0) * sT + (long long)h0 * sH + (long long)w0 * sW + v * 8;
+    uint4 x[KT * KH * KW];
+    bool any_oob = false;
+#pragma unroll
+    for (int dt = 0; dt < KT; ++dt)
+#pragma unroll
+      for (int dh = 0; dh < KH; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < KW; ++dw) {
+          const bool ok = (unsigned)(t0 + dt) < (unsigned)p.Ti && (unsigned)(h0 + dh) < (unsigned)p.Hi && (unsigned)(w0 + dw) < (unsigned)p.Wi;
+          any_oob |= !ok;
+          x[(dt * KH + dh) * KW + dw] = ok ? ld_stream_16(base + dt * sT + dh * sH + dw * sW) : make_uint4(neg_inf2, neg_inf2, neg_inf2, neg_inf2);
+        }
+    uint4 acc = x[0];
+#pragma unroll
+    for (int k = 1; k < KT * KH * KW; ++k) {
+      acc.x = bf16x2_max(acc.x, x[k].x);
+      acc.y = bf16x2_max(acc.y, x[k].y);
+      acc.z = bf16x2_max(acc.z, x[k].z);
+      acc.w = bf16x2_max(acc.w, x[k].w);
+    }
+    if (any_oob && p.pad_zero) {
+      acc.x = bf16x2_max(acc.x, 0u);
+      acc.y = bf16x2_max(acc.y, 0u);
+      acc.z = bf16x2_max(acc.z, 0u);
+      acc.w = bf16x2_max(acc.w, 0u);
+    }
+    *reinterpret_cast<uint4*>(p.out + m_out * p.ldo + v * 8) = acc;
+  }
+}
+
+// 3x3x3 / stride 1 / pad 1 (the pooling branch of every Inception module): one thread walks all T frames of one
+// (clip, h, w, 8-channel vector) column, computes each frame's 3x3 spatial max once (9 loads, not 27 per output) and
+// slides a 3-frame window over those.  Out-of-range taps are ignored, or count as 0 when pad_zero (SAME-padding port).
+__global__ void __launch_bounds__(256) maxpool3d_k3s1_kernel(const PoolParams p) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)p.B * p.Hi * p.Wi * cv;
+  const long long sW = p.C, sH = (long long)p.Wi * p.C, sT = sH * p.Hi;
+  const uint32_t neg_inf2 = 0xFF80FF80u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long m = i / cv;
+    const int w = (int)(m % p.Wi); m /= p.Wi;
+    const int h = (int)(m % p.Hi); m /= p.Hi;
+    const long long b = m;
+    const bool border = h == 0 || w == 0 || h == p.Hi - 1 || w == p.Wi - 1;
+    const __nv_bfloat16* col = p.in + (b * p.Ti) * sT + (long long)h * sH + (long long)w * sW + v * 8;
+    auto spatial = [&](int t) {
+      const __nv_bfloat16* c = col + t * sT;
+      uint4 x[9];
+#pragma unroll
+      for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+        for (int dw = -1; dw <= 1; ++dw) {
+          const bool ok = (unsigned)(h + dh) < (unsigned)p.Hi && (unsigned)(w + dw) < (unsigned)p.Wi;
+          x[(dh + 1) * 3 + dw + 1] = ok ? ld_nc_16(c + dh * sH + dw * sW) : make_uint4(neg_inf2, neg_inf2, neg_inf2, neg_inf2);
+        }
+      uint4 a = x[0];
+#pragma unroll
+      for (int k = 1; k < 9; ++k) {
+        a.x = bf16x2_max(a.x, x[k].x); a.y = bf16x2_max(a.y, x[k].y); a.z = bf16x2_max(a.z, x[k].z); a.w = bf16x2_max(a.w, x[k].w);
+      }
+      return a;
+    };
+    const uint4 none = make_uint4(neg_inf2, neg_inf2, neg_inf2, neg_inf2);
+    uint4 prev = none, cur = spatial(0);
+    __nv_bfloat16* out = p.out + ((b * p.Ti) * (long long)p.Hi * p.Wi + (long long)h * p.Wi + w) * p.ldo + v * 8;
+    const long long oT = (long long)p.Hi * p.Wi * p.ldo;
+    for (int t = 0; t < p.Ti; ++t) {
+      const uint4 next = (t + 1 < p.Ti) ? spatial(t + 1) : none;
+      uint4 a;
+      a.x = bf16x2_max(bf16x2_max(prev.x, cur.x), next.x);
+      a.y = bf16x2_max(bf16x2_max(prev.y, cur.y), next.y);
+      a.z = bf16x2_max(bf16x2_max(prev.z, cur.z), next.z);
+      a.w = bf16x2_max(bf16x2_max(prev.w, cur.w), next.w);
+      if (p.pad_zero && (border || t == 0 || t == p.Ti - 1)) {
+        a.x = bf16x2_max(a.x, 0u); a.y = bf16x2_max(a.y, 0u); a.z = bf16x2_max(a.z, 0u); a.w = bf16x2_max(a.w, 0u);
+      }
+      *reinterpret_cast<uint4*>(out + t * oT) = a;
+      prev = cur;
+      cur = next;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- K4
 // global average pool: in [B, P, C] bf16 -> out [B, C] fp32.  A warp covers 64 channels: lane =
 // pg*8 + cv reads 16 B of channel vector cv at positions pg, pg+4, ... (4 x 128 B contiguous per

@@ -1000,6 +1000,15 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
         maxpool3d_fixed_kernel<2, 1, 1><<<g, 256, 0, st>>>(q);   // I3Res50 maxpool2
       else if (inb && q.kt == 1 && q.kh == 1 && q.kw == 1)
         maxpool3d_fixed_kernel<1, 1, 1><<<g, 256, 0, st>>>(q);   // strided copy
+      else if (q.kt == 3 && q.kh == 3 && q.kw == 3 && q.st == 1 && q.sh == 1 && q.sw == 1 && q.pt == 1 && q.ph == 1 && q.pw == 1 &&
+               q.To == q.Ti && q.Ho == q.Hi && q.Wo == q.Wi)            // Inception branch pools
+        maxpool3d_k3s1_kernel<<<grid_for((long long)q.B * q.Hi * q.Wi * (q.C / 8), 256, 148 * 64), 256, 0, st>>>(q);
+      else if (q.kt == 1 && q.kh == 3 && q.kw == 3)
+        maxpool3d_checked_kernel<1, 3, 3><<<g, 256, 0, st>>>(q);  // MaxPool3d_2a / 3a (SAME padding)
+      else if (q.kt == 3 && q.kh == 3 && q.kw == 3)
+        maxpool3d_checked_kernel<3, 3, 3><<<g, 256, 0, st>>>(q);  // MaxPool3d_4a
+      else if (q.kt == 2 && q.kh == 2 && q.kw == 2)
+        maxpool3d_checked_kernel<2, 2, 2><<<g, 256, 0, st>>>(q);  // MaxPool3d_5a
       else
         maxpool3d_kernel<<<g, 256, 0, st>>>(q);
       e = cudaGetLastError();

@@ -199,6 +199,32 @@ def test_maxpool_same_padding_into_channel_slice(cuda_device):
     assert (out[..., :64] == -7.0).all() and (out[..., 128:] == -7.0).all(), "neighbouring channel slices untouched"
 
 
+@pytest.mark.parametrize("k,s,C,T,H,W", [((3, 3, 3), (1, 1, 1), 256, 8, 28, 28), ((3, 3, 3), (1, 1, 1), 64, 1, 5, 9), ((3, 3, 3), (1, 1, 1), 832, 2, 7, 7),
+                                         ((1, 3, 3), (1, 2, 2), 64, 4, 28, 28), ((1, 3, 3), (1, 2, 2), 192, 3, 13, 15),
+                                         ((3, 3, 3), (2, 2, 2), 480, 8, 28, 28), ((3, 3, 3), (2, 2, 2), 64, 5, 9, 11),
+                                         ((2, 2, 2), (2, 2, 2), 832, 4, 14, 14), ((2, 2, 2), (2, 2, 2), 64, 3, 7, 5)])
+@pytest.mark.parametrize("negative", [False, True], ids=["randn", "all-negative"])
+def test_inception_same_padding_pools_are_exact(cuda_device, k, s, C, T, H, W, negative):
+    """Every MaxPool3dSamePadding geometry of the Inception port through its specialised kernel (sliding 3-frame window for
+    the 3x3x3 / 1 branch pools, unrolled predicated windows for the strided ones).  SAME padding pads with ZEROS, which
+    only shows on all-negative inputs: border outputs are then 0, interior ones negative."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+    from oracle.inception import _same_pad
+
+    x = torch.randn(2, C, T, H, W, generator=torch.Generator().manual_seed(8))
+    if negative:
+        x = -x.abs() - 0.25
+    x = x.to(torch.bfloat16)
+    ref = F.max_pool3d(_same_pad(x.float(), k, s), k, s, 0)
+    op = eng.Op(kind=lib.VAD_OP_MAXPOOL, src=0, dst=1, kernel=k, stride=s, flags=lib.VAD_FLAG_POOL_SAME)
+    plan = eng.BackbonePlan([op], torch.zeros(16, dtype=torch.uint8), 2, 0, cuda_device, in_channels=C)
+    plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
+    torch.cuda.synchronize()
+    out = plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3)
+    assert out.shape == ref.shape
+    assert torch.equal(out, ref)
+
+
 def test_avgpool(cuda_device):
     from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
 
