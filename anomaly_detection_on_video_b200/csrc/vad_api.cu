@@ -138,6 +138,7 @@ struct vad_plan {
   bool no_s3 = false;        // VAD_NO_S3X3=1: layer1's (1,3,3) convs through the generic im2col kernel
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
+  bool no_bk32 = false;      // VAD_NO_BK32=1: Cin % 64 == 32 layers through the gather producer (as before the 32-wide TMA path)
   int pair_mode = 1;         // VAD_PAIR=0: never use the CTA-pair kernel; 1 (default): for the long-K layers without residual
   int pair_epi_min_kb = 8;   // VAD_PAIR_EPI_MIN_KB: same for residual layers (staged epilogue; measured: K = 512 gains, K = 256 loses); 0 = off
   int pair_min_kb = 12;      // VAD_PAIR_MIN_KB: fewest 64-wide k-blocks for which a layer goes to the CTA-pair kernel
@@ -238,6 +239,7 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR"); p->pair_mode = k ? atoi(k) : 1; }
+  { const char* k = getenv("VAD_NO_BK32"); p->no_bk32 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR_MIN_KB"); p->pair_min_kb = k ? atoi(k) : 12; }
   { const char* k = getenv("VAD_PAIR_EPI_MIN_KB"); p->pair_epi_min_kb = k ? atoi(k) : 8; }
   { const char* k = getenv("VAD_MC_MIN_TILES"); p->mc_min_tiles = k ? atoi(k) : -1; }
@@ -336,9 +338,16 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       const bool tma_geom_ok = r.pb[0] <= 15 && r.pb[1] <= 15 && r.pb[2] <= 15 && d.kt <= 16 && d.kh <= 16 && d.kw <= 16 &&
                                d.st <= 8 && d.sh <= 8 && d.sw <= 8;
       r.bk = 64;
-      if ((d.flags & VAD_FLAG_FORCE_GATHER) || !tma_geom_ok || (!fold && (d.cin % 64)) || (fold && p->stem_gather))
+      // Cin % 64 == 32 (Inception's 96 / 160 / 480-channel inputs, 32-channel 5x5 branches): TMA operands with 32-wide
+      // k-blocks (64-byte rows, SWIZZLE_64B) -- direct epilogue only; anything else that is not a multiple of 64: gather
+      const bool epi_wanted = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K) || p->epi_all);
+      const bool half_k = !fold && (d.cin % 64) == 32 && !epi_wanted && !p->no_bk32;
+      if ((d.flags & VAD_FLAG_FORCE_GATHER) || !tma_geom_ok || (!fold && (d.cin % 64) && !half_k) || (fold && p->stem_gather))
         r.a_mode = A_GATHER;
-      else if (fold) {
+      else if (half_k) {
+        r.a_mode = unit ? A_TMA_2D : A_TMA_IM2COL;
+        r.bk = 32;
+      } else if (fold) {
         r.a_mode = A_TMA_IM2COL;  // im2col over the overlapping 8-pixel window view: 32 bf16 = 64-byte rows
         r.bk = 32;
       } else if (unit)
@@ -350,7 +359,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       // staged epilogue (two 128 x BN tiles in smem, TMA store; residual prefetched by TMA): residual layers, and
       // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections), VAD_EPI_ALL=1: every layer
       r.epi = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K) || p->epi_all);
-      r.bn = (d.cout > 128 && !r.epi) ? 256 : (d.cout > 64 ? 128 : 64);
+      r.bn = (d.cout > 128 && !r.epi && r.bk == 64) ? 256 : (d.cout > 64 ? 128 : 64);
       r.pair_epi = r.epi && p->pair_mode > 0 && p->pair_epi_min_kb > 0 && d.res >= 0 && r.a_mode != A_GATHER && r.bk == 64 && d.cout % 256 == 0 &&
                    !(d.flags & VAD_FLAG_POOL_T2) && (p->sm_count % 2) == 0 && c.num_kb >= p->pair_epi_min_kb && M > kBlockM;
       if (r.pair_epi) r.bn = 256;
@@ -365,7 +374,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       r.kps = (r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2 && !r.epi) ? 2 : 1;
       // folded stem through the generic kernel (InceptionI3d's 7x7x7): a 32-wide k-block is only two N = 64 MMAs, far below
       // the ~300 cycles a barrier round trip costs the issuing thread; four of them per stage
-      if (r.a_mode == A_TMA_IM2COL && r.bk == 32 && c.num_kb >= 4 && !r.epi) r.kps = 4;
+      if (r.a_mode != A_GATHER && r.bk == 32 && c.num_kb >= 4 && !r.epi) r.kps = 4;
       if (p->kps_override == 1) r.kps = 1;
       if (p->kps_override == 2 && r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2) r.kps = 2;
       long long m_tiles = (M + kBlockM - 1) / kBlockM;
@@ -737,10 +746,11 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
       } else if (r.a_mode == A_TMA_2D) {
         cuuint64_t gdim[2] = {(cuuint64_t)r.Ci, (cuuint64_t)c.M};
         cuuint64_t gstr[1] = {(cuuint64_t)r.Ci * 2};
-        cuuint32_t box[2] = {(cuuint32_t)64, (cuuint32_t)kBlockM};
+        cuuint32_t box[2] = {(cuuint32_t)r.bk, (cuuint32_t)kBlockM};
         cuuint32_t es[2] = {1, 1};
         CUresult cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)slot_ptr(d.src), gdim, gstr,
-                                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(A) failed: %d", i, (int)cr);
       } else if (r.a_mode == A_TMA_IM2COL && r.fold) {
@@ -780,8 +790,9 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         int upper[3] = {r.pb[2] - (d.kw - 1), r.pb[1] - (d.kh - 1), r.pb[0] - (d.kt - 1)};
         cuuint32_t es[5] = {1, (cuuint32_t)d.sw, (cuuint32_t)d.sh, (cuuint32_t)d.st, 1};
         CUresult cr = p->encode_im2col(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)slot_ptr(d.src), gdim, gstr,
-                                       lower, upper, 64, (cuuint32_t)kBlockM, es,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       lower, upper, (cuuint32_t)r.bk, (cuuint32_t)kBlockM, es,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeIm2col failed: %d", i, (int)cr);
         // Drivers up to 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (bit 21 of the
@@ -883,8 +894,10 @@ static cudaError_t launch_conv_pair(const OpRuntime& r, cudaStream_t st) {
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
   if (r.pair || r.pair_epi) return launch_conv_pair(r, st);
   if (r.mc) return launch_conv_mc(r, st);
-  if (r.bk == 32)  // folded stem, TMA window view
+  if (r.bk == 32) {  // folded stem (TMA window view) and Cin % 64 == 32 layers: 32-wide k-blocks, direct epilogue
+    if (r.bn == 128) return r.kps == 4 ? launch_conv<128, 32, 4, false, false>(r, st) : launch_conv<128, 32, 1, false, false>(r, st);
     return r.kps == 4 ? launch_conv<64, 32, 4, false, false>(r, st) : launch_conv<64, 32, 1, false, false>(r, st);
+  }
   if (r.epi) return r.bn == 128 ? launch_conv_bn<128, true>(r, st) : launch_conv_bn<64, true>(r, st);
   switch (r.bn) {
     case 256: return r.a_mode == A_GATHER ? launch_conv<256, 64, 1, true, false>(r, st) : launch_conv<256, 64, 1, false, false>(r, st);

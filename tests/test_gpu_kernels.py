@@ -67,6 +67,29 @@ def test_tma_im2col_and_gather_producers_agree_bitwise(cuda_device, case):
         assert torch.equal(a, b)
 
 
+HALF_K_CASES = [
+    # Cin % 64 == 32: 32-wide k-blocks (64-byte rows, SWIZZLE_64B) through TMA, four per pipeline stage
+    ("3x3x3 96->128 (Mixed_3b.b1b)", 96, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), 2, 4, 14, 14, False, True),
+    ("3x3x3 160->320, N tail (Mixed_4f.b1b)", 160, 320, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 2, 7, 7, False, True),
+    ("3x3x3 32->96 (Mixed_3c.b2b)", 32, 96, (3, 3, 3), (1, 1, 1), (1, 1, 1), 2, 3, 9, 11, False, True),
+    ("1x1 480->192, 15 k-blocks (Mixed_4b.b0)", 480, 192, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 2, 14, 14, False, True),
+    ("1x1 32->64, one k-block", 32, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 9, 9, False, False),
+    ("1x3x3 stride 2 96->64", 96, 64, (1, 3, 3), (1, 2, 2), (0, 1, 1), 2, 2, 13, 13, False, True),
+]
+
+
+@pytest.mark.parametrize("case", HALF_K_CASES, ids=[c[0] for c in HALF_K_CASES])
+def test_conv_half_width_k_blocks(cuda_device, case):
+    """TMA operands with BK = 32 for Cin % 64 == 32; the cp.async gather producer (BK = 64 over the same K order) is the
+    cross-check: bit-identical."""
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    tma, ref = run_conv_case(*case[1:])
+    gather, _ = run_conv_case(*case[1:], force_gather=True)
+    assert_bf16_close(tma, ref)
+    assert torch.equal(tma, gather)
+
+
 @pytest.mark.parametrize("case", GATHER_ONLY, ids=[c[0] for c in GATHER_ONLY])
 def test_conv_narrow_channels(cuda_device, case):
     from gpu_util import assert_bf16_close, run_conv_case
