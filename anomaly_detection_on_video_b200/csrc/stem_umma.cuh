@@ -45,6 +45,9 @@ struct StemParams {
   int stage_bytes;
   int seg_bytes;            // bytes of one raw row segment (176 for stride 2)
   int n_stages;
+  int w_stream;             // 0: all kt x kh taps of weights resident in shared memory (<= 150 KB: the 5x7x7 stem);
+                            // 1: the kh taps of frame tap dt travel with dt's stage (InceptionI3d's 7x7x7: 196 KB)
+  int off_w;                // w_stream: byte offset of the kh x 4 KB of weights inside a stage (1024-aligned)
   int relu;
   int dbg;  // VAD_STEM_DEBUG bit mask (bottleneck hunting only): 1 = no global stores, 2 = no MMA issue, 4 = no A loads,
             // multi-frame kernel also: 8 = no tcgen05.ld, 16 = no tcgen05.st zeroing, 32 = no epilogue math / staging
@@ -83,8 +86,8 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   const int ntaps = p.kt * p.kh;
-  uint8_t* w_smem = smem;                                      // ntaps x 4 KB, resident
-  uint8_t* staging = smem + ntaps * kStemTapBytes;             // 2 x 16 KB output staging (1024-aligned)
+  uint8_t* w_smem = smem;                                      // ntaps x 4 KB, resident (nothing when w_stream)
+  uint8_t* staging = smem + (p.w_stream ? 0 : ntaps * kStemTapBytes);  // 2 x 16 KB output staging (1024-aligned)
   uint8_t* stage_base = staging + 2 * kStemStagingBytes;       // n_stages x stage_bytes
   float* s_scale = reinterpret_cast<float*>(stage_base + p.n_stages * p.stage_bytes);
   float* s_shift = s_scale + 64;
@@ -136,10 +139,12 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (one elected thread)
     if (elect_one_sync()) {
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
-      mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
-      for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
+      if (!p.w_stream) {
+        mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTapBytes));
+        for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTapBytes, &tmW, w_bar, tap * 32, 0);
+      }
       griddep_wait();  // the weights are constants; the clips come from the preceding preprocessing kernel
-      const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * p.seg_bytes);
+      const uint32_t tx = (uint32_t)((p.rows_even + p.rows_odd) * p.seg_bytes) + (p.w_stream ? (uint32_t)(p.kh * kStemTapBytes) : 0u);
       uint32_t s = 0, ph = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
         int r = unit;
@@ -161,6 +166,9 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
               mbar_arrive_expect_tx_a(fb, tx);
               tma_load_4d_a(dst, &tmE, fb, x_start, h_start, t0 + dt, n);
               tma_load_4d_a(dst + (uint32_t)p.off_odd, &tmOdd, fb, x_start, h_start + 1, t0 + dt, n);
+              if (p.w_stream)
+                for (int dh = 0; dh < p.kh; ++dh)
+                  tma_load_2d_a(dst + (uint32_t)p.off_w + (uint32_t)dh * kStemTapBytes, &tmW, fb, (dt * p.kh + dh) * 32, 0);
             }
             if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
           }
@@ -176,7 +184,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
       constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
       const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
-      mbar_wait(w_bar, 0);
+      if (!p.w_stream) mbar_wait(w_bar, 0);
       const uint32_t seg = (uint32_t)p.seg_bytes;
       const uint32_t w_addr = smem_u32(w_smem);
       // descriptor high words are loop invariant; only the 14-bit start-address field moves
@@ -200,7 +208,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
             if (ns == (uint32_t)S) { ns = 0; nph ^= 1u; }
             const bool do_wait = !(last_tile && dt == p.kt - 1);
             const uint32_t st_addr = stage0 + s * (uint32_t)p.stage_bytes;
-            uint32_t b_lo = (w_addr + (uint32_t)(dt * p.kh) * kStemTapBytes) >> 4;
+            uint32_t b_lo = (p.w_stream ? st_addr + (uint32_t)p.off_w : w_addr + (uint32_t)(dt * p.kh) * kStemTapBytes) >> 4;
             const uint32_t a_even = st_addr >> 4, a_odd = (st_addr + (uint32_t)p.off_odd) >> 4, seg16 = seg >> 4;
             auto tap = [&](int dh) {
               const uint32_t a_lo = ((dh & 1) ? a_odd : a_even) + (uint32_t)(dh >> 1) * seg16;

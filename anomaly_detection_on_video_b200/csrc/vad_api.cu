@@ -439,8 +439,10 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       if (r.s3) r.s3p.num_tiles = c.num_tiles;
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = Wi; r.fold = fold;
       r.stem = false;
-      if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0 && sym_pad &&
-          d.kt * d.kh * kStemTapBytes <= 150 * 1024) {
+      // (only the front padding enters the stem kernels: out-of-range rows / frames / columns behind the data are
+      // zero-filled by TMA, so the asymmetric SAME padding of the Inception port needs nothing extra)
+      if (fold && r.a_mode == A_TMA_IM2COL && !p->stem_generic && d.sh == 2 && d.sw == 2 && d.cout == 64 && d.res < 0 &&
+          r.pf[2] <= p->in_pad_left) {
         StemParams& q = r.sp;
         memset(&q, 0, sizeof(q));
         q.clk_out = nullptr;
@@ -456,7 +458,14 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         q.seg_bytes = ((tw - 1) * d.sw * 4 + 32) * 2;  // bytes per raw input-row segment in smem (176)
         q.off_odd = (int)align_up((uint64_t)q.rows_even * q.seg_bytes, 128);
         q.stage_bytes = (int)align_up((uint64_t)q.off_odd + (uint64_t)q.rows_odd * q.seg_bytes, 128);
-        const int w_bytes = d.kt * d.kh * kStemTapBytes;
+        int w_bytes = d.kt * d.kh * kStemTapBytes;
+        if (w_bytes > 150 * 1024) {
+          // too many taps to keep resident (7x7x7: 196 KB): the kh taps of one dt ride in that dt's stage
+          q.w_stream = 1;
+          q.off_w = (int)align_up((uint64_t)q.stage_bytes, 1024);
+          q.stage_bytes = q.off_w + d.kh * kStemTapBytes;
+          w_bytes = 0;
+        }
         const int fixed = w_bytes + 2 * kStemStagingBytes + 2 * 64 * 4 + (2 * kStemMaxStages + 17) * 8 + 16 + 32 * 32 + 1024;
         int ns = (227 * 1024 - fixed) / q.stage_bytes;
         if (ns > kStemMaxStages) ns = kStemMaxStages;

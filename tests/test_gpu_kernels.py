@@ -152,6 +152,39 @@ def test_stem_through_the_generic_kernel(cuda_device, k, kps, monkeypatch):
     assert_bf16_close(plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3), ref)
 
 
+@pytest.mark.parametrize("shape", [(1, 16, 224, 224), (2, 9, 50, 38), (1, 4, 32, 32)])
+def test_inception_stem_streams_its_weights(cuda_device, shape, monkeypatch):
+    """The 7x7x7 / 2 SAME-padded stem of the Inception port through the dedicated stem kernel: its 49 taps (196 KB) do not
+    fit in shared memory next to the pipeline, so the 7 taps of each frame tap travel with that frame's stage
+    (StemParams::w_stream); padding is asymmetric (2 in front, 3 behind).  Cross-checked against the generic kernel
+    (VAD_STEM_GENERIC=1), which accumulates in the same k order: bit-identical."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+    from gpu_util import assert_bf16_close
+    from oracle.inception import _same_pad
+
+    B, T, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, T, H, W, generator=g).clamp(-2, 2.44)
+    k, s_ = (7, 7, 7), (2, 2, 2)
+    w = (torch.randn(64, 3, *k, generator=g) * 0.04).to(torch.bfloat16).float()
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    ref = F.relu(F.conv3d(_same_pad(x.to(torch.bfloat16).float(), k, s_), w, None, s_) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    pk = eng.ParamPacker()
+    w_off, s_off, b_off = pk.add_conv(w, scale, shift, fold_w=True)
+    ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=4, cout=64, kernel=k, stride=s_,
+                  flags=lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W | lib.VAD_FLAG_CONV_SAME, w_off=w_off, scale_off=s_off, shift_off=b_off)]
+    outs = []
+    for generic in ("0", "1"):
+        monkeypatch.setenv("VAD_STEM_GENERIC", generic)
+        plan = eng.BackbonePlan(ops, pk.blob(), 2, 2, cuda_device)
+        plan.forward(eng.ingest_ncthw(x.to(cuda_device), 2))
+        torch.cuda.synchronize()
+        outs.append(plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3).clone())
+    assert outs[0].shape == ref.shape
+    assert_bf16_close(outs[0], ref)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("shape,slice_", [((1, 16, 224, 224), (0, 0)), ((2, 10, 64, 48), (0, 0)), ((1, 8, 50, 38), (64, 192))])
 def test_stem_fused_temporal_pool_is_exact(cuda_device, shape, slice_):
     """VAD_FLAG_POOL_T2 (max over output frame pairs in the stem epilogue) == unfused stem followed by a
