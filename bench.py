@@ -360,6 +360,39 @@ def main():
     except Exception as exc:  # the head is reported beside the metric; it must never take the bench line down
         head_info = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- the backbone north_star names (InceptionV1-3D; not in the reference): same clip-crop batch, backbone only,
+    # reported beside the I3Res50 numbers, never mixed into `value`
+    inception_info = None
+    if rank == 0:
+        try:
+            from anomaly_detection_on_video_b200.inception import InceptionI3d
+            from oracle import inception as OI  # seeded synthetic weights only
+
+            inc = InceptionI3d()
+            inc.load_state_dict(OI.seeded_state_dict(0), strict=True)
+            inc.eval().to(dev)
+            nb = cpb * CROPS
+            xs = torch.randn(nb, 16, 224, 224 + 8, 4, device=dev).to(torch.bfloat16)
+            for _ in range(W):
+                inc.forward_stem_layout(xs)
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            i0.record()
+            for _ in range(4 * K):
+                inc.forward_stem_layout(xs)
+            i1.record()
+            torch.cuda.synchronize(dev)
+            inc_ms = i0.elapsed_time(i1) / (4 * K)
+            inception_info = {"model": "InceptionI3d (extract_features, 1024-d)", "clip_crops_per_forward": nb, "ms_per_forward": inc_ms,
+                              "clips_per_s": nb / (inc_ms / 1e3), "flop_per_clip": 55575138304,
+                              "tflops": nb * 55575138304 / (inc_ms / 1e3) / 1e12,
+                              "frac_of_sustained_peak": nb * 55575138304 / (inc_ms / 1e3) / 1e12 / load_peaks()["bf16_sustained"],
+                              "launches_per_forward": inc.plan(dev).num_launches, "n_gpus": 1,
+                              "note": "backbone forward from the bf16 stem layout, HBM-resident input, rank 0 only"}
+            del inc, xs
+        except Exception as exc:
+            inception_info = {"error": f"{type(exc).__name__}: {exc}"}
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -435,6 +468,7 @@ def main():
             "roofline_conv_family": family,
             "cpu_baseline": cpu_baseline,
             "head": head_info,
+            "inception": inception_info,
             "host": host_info,
             "tflops_whole_step": value * FLOP_PER_CLIP / 1e12,
             "step_breakdown": {"step_ms": ms / K, "profiled_pass_step_ms": (ms_profiled / K) if prof else None,
