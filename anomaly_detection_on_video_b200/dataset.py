@@ -9,6 +9,7 @@ produced on the GPU; ``clips_stem`` hands the native backbone its bf16 input lay
 from __future__ import annotations
 
 import os
+from collections import OrderedDict
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
@@ -117,6 +118,28 @@ def _frames_to_tensor(src) -> torch.Tensor:
     return t
 
 
+# Preprocessor handles (resize tap tables + crop table on the device) depend only on the frame geometry, never on the
+# frames: one per geometry and device is shared by every dataset of the process.  Creating one costs several
+# cudaMalloc / synchronous upload / (on destruction) cudaFree calls -- 10-150 ms of host time once the context holds the
+# backbone's multi-GB workspace -- which would otherwise sit in front of every video, where nothing can hide it.
+_PP_CACHE: "OrderedDict[tuple, Preprocessor]" = OrderedDict()
+_PP_CACHE_MAX = 32
+
+
+def _shared_preprocessor(src_h: int, src_w: int, resize: int, crop: int, ncrops: int, device: torch.device) -> Preprocessor:
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (int(src_h), int(src_w), int(resize), int(crop), int(ncrops), int(index))
+    pp = _PP_CACHE.get(key)
+    if pp is None:
+        pp = Preprocessor(src_h, src_w, resize, crop, ncrops, device)
+        _PP_CACHE[key] = pp
+        while len(_PP_CACHE) > _PP_CACHE_MAX:
+            _PP_CACHE.popitem(last=False)
+    else:
+        _PP_CACHE.move_to_end(key)
+    return pp
+
+
 class TenCropVideoFrameDataset(Dataset):
     """GPU clip source with the reference's interface (src/dataset.py:145-195)."""
 
@@ -160,7 +183,7 @@ class TenCropVideoFrameDataset(Dataset):
         self.cropsize = cropsize
         n_frames = self.frames.shape[0]
         self.indices = list(range((n_frames - 1) // frames_per_clip + 1))  # src/dataset.py:171-173
-        self._pp = Preprocessor(self.frames.shape[1], self.frames.shape[2], resize, cropsize, ncrops, self.device)
+        self._pp = _shared_preprocessor(self.frames.shape[1], self.frames.shape[2], resize, cropsize, ncrops, self.device)
 
     def __len__(self) -> int:
         return len(self.indices)

@@ -299,6 +299,18 @@ def main():
         except RuntimeError:
             prof = []
 
+    # ---- the box's host link on its own: the same pinned 461 MB, one copy, nothing else running (e2e below hides this
+    # transfer behind the backbone only if it is shorter than the compute of a step)
+    h2d_alone = []
+    for _ in range(3):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        c0.record()
+        frames_dev.copy_(frames_host, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        h2d_alone.append(c0.elapsed_time(c1))
+
     # ---- e2e
     for _ in range(2):
         step_e2e()
@@ -461,7 +473,11 @@ def main():
                        "cache": "inputs larger than L2 (461 MB of frames, >4 GB of activations per batch; no flush needed)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames_host.numel()),
                     "d2h_bytes_per_step": int(f_host.numel() * 4 + s_host.numel() * 4), "ms_per_step": ms_e2e / K,
-                    "wall_ms_per_step": wall_e2e / K},
+                    "wall_ms_per_step": wall_e2e / K,
+                    "h2d_alone_ms": [round(v, 2) for v in h2d_alone],
+                    "h2d_alone_gbs": round(frames_host.numel() / (min(h2d_alone) / 1e3) / 1e9, 1),
+                    "note": "h2d_alone_*: this rank's pinned frame buffer copied once with the GPU idle; a step cannot be "
+                            "shorter than that copy, whatever the kernels do"},
             "gpu_launches": int(launches_timed_region),
             "clocks": clocks,
             "roofline": roofline,
