@@ -63,11 +63,11 @@ constexpr int kUmmaK = 16;
 
 template <int BN, int BK, int KPS, bool GATHER, bool EPI>
 struct ConvCfg {
-  static_assert(BK == 64 || BK == 32, "BK is one swizzle row: 64 (SW128) or 32 (SW64) bf16");
+  static_assert(BK == 64 || BK == 32 || BK == 16, "BK is one swizzle row: 64 (SW128), 32 (SW64) or 16 (SW32) bf16");
   static_assert(!GATHER || BK == 64, "the gather producer writes 128-byte swizzled rows");
   static_assert(!EPI || BN <= 128, "the staged epilogue keeps two 128 x BN bf16 tiles in shared memory");
-  static_assert(KPS == 1 || (KPS == 2 && !GATHER && BK == 64) || (KPS == 4 && !GATHER && BK == 32),
-                "several k-blocks per stage: TMA producers; 2 x 64-wide (SW128) or 4 x 32-wide (SW64: the folded stem window view)");
+  static_assert(KPS == 1 || (KPS == 2 && !GATHER && BK == 64) || (KPS == 4 && !GATHER && BK == 32) || (KPS == 8 && !GATHER && BK == 16),
+                "several k-blocks per stage (TMA producers): 2 x 64-wide (SW128), 4 x 32-wide (SW64) or 8 x 16-wide (SW32), i.e. 8 MMAs");
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kABytes = kBlockM * kRowBytes;   // one k-block of A
   static constexpr int kBBytes = BN * kRowBytes;        // one k-block of B
@@ -105,7 +105,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// K-major operand tile with ROW_BYTES-wide rows (128: SWIZZLE_128B, 64: SWIZZLE_64B), rows packed
+// nk (1 .. N, runtime) -> f(integral_constant<nk>): the issue loop is instantiated per k-block count of a stage
+template <int N, class F>
+__device__ __forceinline__ void call_with_nk(int nk, F& f) {
+  if (nk == N) f(std::integral_constant<int, N>{});
+  else if constexpr (N > 1) call_with_nk<N - 1>(nk, f);
+}
+
+// K-major operand tile with ROW_BYTES-wide rows (128: SWIZZLE_128B, 64: SWIZZLE_64B, 32: SWIZZLE_32B), rows packed
 // densely, 8-row groups SBO apart.
 template <int ROW_BYTES>
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
@@ -114,7 +121,7 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 16;                                // LBO (ignored)   [16,30)
   d |= static_cast<uint64_t>((8 * ROW_BYTES) >> 4) << 32;             // SBO             [32,46)
   d |= static_cast<uint64_t>(1) << 46;                                // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(ROW_BYTES == 128 ? 2 : 4) << 61;         // SWIZZLE_128B / SWIZZLE_64B
+  d |= static_cast<uint64_t>(ROW_BYTES == 128 ? 2 : (ROW_BYTES == 64 ? 4 : 6)) << 61;  // SWIZZLE_128B / _64B / _32B
   return d;
 }
 
@@ -362,10 +369,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           };
-          if (KPS == 1 || nk == KPS) issue(std::integral_constant<int, KPS>{});
-          else if (KPS > 2 && nk == 3) issue(std::integral_constant<int, (KPS > 2 ? 3 : 1)>{});
-          else if (KPS > 2 && nk == 2) issue(std::integral_constant<int, (KPS > 2 ? 2 : 1)>{});
-          else                         issue(std::integral_constant<int, 1>{});
+          call_with_nk<KPS>(nk, issue);
           if (MC) umma_commit_mc(empty0 + s * 8, (uint16_t)3);  // frees the slot in both CTAs of the pair
           else    umma_commit_a(empty0 + s * 8);               // frees the smem stage once these MMAs have read it
           if (last_stage) { umma_commit_a(tfull0 + acc * 8); ++tc; }  // accumulator complete

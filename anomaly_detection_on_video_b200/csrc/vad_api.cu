@@ -341,12 +341,14 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       // Cin % 64 == 32 (Inception's 96 / 160 / 480-channel inputs, 32-channel 5x5 branches): TMA operands with 32-wide
       // k-blocks (64-byte rows, SWIZZLE_64B) -- direct epilogue only; anything else that is not a multiple of 64: gather
       const bool epi_wanted = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K) || p->epi_all);
-      const bool half_k = !fold && (d.cin % 64) == 32 && !epi_wanted && !p->no_bk32;
+      // ... and Cin % 32 == 16 (16 / 48 / 112 / 144 / 528 channels) with 16-wide ones (32-byte rows, SWIZZLE_32B, one MMA each)
+      const int sub_k = (fold || epi_wanted || p->no_bk32) ? 0 : ((d.cin % 64) == 32 ? 32 : ((d.cin % 32) == 16 ? 16 : 0));
+      const bool half_k = sub_k != 0;
       if ((d.flags & VAD_FLAG_FORCE_GATHER) || !tma_geom_ok || (!fold && (d.cin % 64) && !half_k) || (fold && p->stem_gather))
         r.a_mode = A_GATHER;
       else if (half_k) {
         r.a_mode = unit ? A_TMA_2D : A_TMA_IM2COL;
-        r.bk = 32;
+        r.bk = sub_k;
       } else if (fold) {
         r.a_mode = A_TMA_IM2COL;  // im2col over the overlapping 8-pixel window view: 32 bf16 = 64-byte rows
         r.bk = 32;
@@ -355,7 +357,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       else
         r.a_mode = A_TMA_IM2COL;
       c.a_mode = r.a_mode;
-      c.num_kb = r.bk == 64 ? r.K_pad / 64 : (K + 31) / 32;
+      c.num_kb = r.bk == 64 ? r.K_pad / 64 : (K + r.bk - 1) / r.bk;
       // staged epilogue (two 128 x BN tiles in smem, TMA store; residual prefetched by TMA): residual layers, and
       // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections), VAD_EPI_ALL=1: every layer
       r.epi = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K) || p->epi_all);
@@ -375,6 +377,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       // folded stem through the generic kernel (InceptionI3d's 7x7x7): a 32-wide k-block is only two N = 64 MMAs, far below
       // the ~300 cycles a barrier round trip costs the issuing thread; four of them per stage
       if (r.a_mode != A_GATHER && r.bk == 32 && c.num_kb >= 4 && !r.epi) r.kps = 4;
+      if (r.a_mode != A_GATHER && r.bk == 16 && !r.epi) r.kps = 8;
       if (p->kps_override == 1) r.kps = 1;
       if (p->kps_override == 2 && r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2) r.kps = 2;
       long long m_tiles = (M + kBlockM - 1) / kBlockM;
@@ -607,7 +610,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         cuuint32_t es[2] = {1, 1};
         CUresult cr = p->encode_tiled(&r.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), gdim,
                                       gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                      r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (r.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(weights) failed: %d", i, (int)cr);
       }
@@ -759,7 +762,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         cuuint32_t es[2] = {1, 1};
         CUresult cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)slot_ptr(d.src), gdim, gstr,
                                       box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                      r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (r.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(A) failed: %d", i, (int)cr);
       } else if (r.a_mode == A_TMA_IM2COL && r.fold) {
@@ -801,7 +804,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         CUresult cr = p->encode_im2col(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)slot_ptr(d.src), gdim, gstr,
                                        lower, upper, (cuuint32_t)r.bk, (cuuint32_t)kBlockM, es,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                       r.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (r.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeIm2col failed: %d", i, (int)cr);
         // Drivers up to 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (bit 21 of the
@@ -903,6 +906,8 @@ static cudaError_t launch_conv_pair(const OpRuntime& r, cudaStream_t st) {
 static cudaError_t launch_conv_any(const OpRuntime& r, cudaStream_t st) {
   if (r.pair || r.pair_epi) return launch_conv_pair(r, st);
   if (r.mc) return launch_conv_mc(r, st);
+  if (r.bk == 16)  // Cin % 32 == 16 layers: 16-wide k-blocks, eight per stage
+    return r.bn == 128 ? launch_conv<128, 16, 8, false, false>(r, st) : launch_conv<64, 16, 8, false, false>(r, st);
   if (r.bk == 32) {  // folded stem (TMA window view) and Cin % 64 == 32 layers: 32-wide k-blocks, direct epilogue
     if (r.bn == 128) return r.kps == 4 ? launch_conv<128, 32, 4, false, false>(r, st) : launch_conv<128, 32, 1, false, false>(r, st);
     return r.kps == 4 ? launch_conv<64, 32, 4, false, false>(r, st) : launch_conv<64, 32, 1, false, false>(r, st);

@@ -75,13 +75,19 @@ HALF_K_CASES = [
     ("1x1 480->192, 15 k-blocks (Mixed_4b.b0)", 480, 192, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 2, 14, 14, False, True),
     ("1x1 32->64, one k-block", 32, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 9, 9, False, False),
     ("1x3x3 stride 2 96->64", 96, 64, (1, 3, 3), (1, 2, 2), (0, 1, 1), 2, 2, 13, 13, False, True),
+    # Cin % 32 == 16: 16-wide k-blocks (32-byte rows, SWIZZLE_32B), eight per pipeline stage
+    ("3x3x3 16->32, 27 k-blocks (Mixed_3b.b2b)", 16, 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), 2, 4, 14, 14, False, True),
+    ("3x3x3 144->288, N tail (Mixed_4e.b1b)", 144, 288, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 2, 7, 7, False, True),
+    ("1x1 528->256, 33 k-blocks (Mixed_4f.b0)", 528, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 2, 14, 14, False, True),
+    ("3x3x3 48->128 (Mixed_5c.b2b)", 48, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), 2, 2, 7, 7, False, False),
+    ("1x1 16->64, one k-block", 16, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 9, 9, False, True),
 ]
 
 
 @pytest.mark.parametrize("case", HALF_K_CASES, ids=[c[0] for c in HALF_K_CASES])
 def test_conv_half_width_k_blocks(cuda_device, case):
-    """TMA operands with BK = 32 for Cin % 64 == 32; the cp.async gather producer (BK = 64 over the same K order) is the
-    cross-check: bit-identical."""
+    """TMA operands with BK = 32 for Cin % 64 == 32 and BK = 16 for Cin % 32 == 16; the cp.async gather producer (BK = 64
+    over the same K order) is the cross-check: bit-identical."""
     from gpu_util import assert_bf16_close, run_conv_case
 
     tma, ref = run_conv_case(*case[1:])
