@@ -126,6 +126,18 @@ _PP_CACHE: "OrderedDict[tuple, Preprocessor]" = OrderedDict()
 _PP_CACHE_MAX = 32
 
 
+_UPLOAD_STREAMS: dict = {}
+
+
+def _upload_stream(device: torch.device) -> "torch.cuda.Stream":
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    st = _UPLOAD_STREAMS.get(index)
+    if st is None:
+        st = torch.cuda.Stream(torch.device("cuda", index))
+        _UPLOAD_STREAMS[index] = st
+    return st
+
+
 def _shared_preprocessor(src_h: int, src_w: int, resize: int, crop: int, ncrops: int, device: torch.device) -> Preprocessor:
     index = device.index if device.index is not None else torch.cuda.current_device()
     key = (int(src_h), int(src_w), int(resize), int(crop), int(ncrops), int(index))
@@ -163,18 +175,21 @@ class TenCropVideoFrameDataset(Dataset):
                     frames = frames.pin_memory()
                 except RuntimeError:
                     pass
-            dst = torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
-            copy_stream = torch.cuda.Stream(self.device)
-            copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            # The destination is ALLOCATED on the (per-device, long-lived) upload stream: the caching allocator then
+            # orders its reuse against that stream, so the copies need not wait for whatever is still queued on the
+            # compute stream -- the upload of the next video overlaps the backbone of the current one
+            # (extract_features.extract_stream).  The compute stream reads it, hence record_stream.
+            copy_stream = _upload_stream(self.device)
             chunk = max(frames_per_clip, (256 // frames_per_clip) * frames_per_clip)
             with torch.cuda.stream(copy_stream):
+                dst = torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
                 for c0 in range(0, frames.shape[0], chunk):
                     c1 = min(frames.shape[0], c0 + chunk)
                     dst[c0:c1].copy_(frames[c0:c1], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
                     self._ready.append((c1, ev))
-            dst.record_stream(copy_stream)
+            dst.record_stream(torch.cuda.current_stream(self.device))
             self._host_frames = frames  # keep the pinned source alive until the copies are done
             frames = dst
         self.frames = frames.contiguous()

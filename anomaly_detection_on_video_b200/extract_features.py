@@ -108,6 +108,44 @@ def extract_clip_features(video_dataset: TenCropVideoFrameDataset, model: torch.
     return feats.cpu().numpy() if as_numpy else feats
 
 
+def extract_stream(videos: Iterable, model: torch.nn.Module, device: torch.device, *, clips_per_batch: int = CLIPS_PER_BATCH,
+                   seg_length: Optional[int] = 32, frames_per_clip: int = 16, ncrops: int = 10):
+    """Features of a sequence of videos with the host <-> device traffic of neighbouring videos overlapped.
+
+    ``videos`` yields frame containers (anything ``TenCropVideoFrameDataset`` accepts).  For each one, in order, yields
+    ``(features, segments)`` as host tensors: ``(n_clips, ncrops, C)`` fp32 and ``(ncrops, seg_length, C)`` fp32 (``None``
+    when ``seg_length`` is None) -- what ``extract`` + ``segment`` (extract_features.py:55-185) write per video.
+    Software pipeline, one video deep: while video *i* runs on the compute stream, the frames of video *i+1* are already
+    uploading (own stream) and the results of video *i-1* are copied back into pinned buffers; the host blocks only on
+    the event of the video it is about to yield.  No collective, no CPU compute.
+    """
+    from .engine import segment_mean
+
+    pending = None  # (features_host, segments_host, event, keep-alive) of the previous video
+
+    def finish(p):
+        p[2].synchronize()
+        return p[0], p[1]
+
+    for frames in videos:
+        ds = TenCropVideoFrameDataset(frames, frames_per_clip=frames_per_clip, device=device, ncrops=ncrops)  # upload starts here
+        feats = extract_clip_features(ds, model, device, clips_per_batch=clips_per_batch, strict_compat=False, as_numpy=False)
+        seg = segment_mean(feats, seg_length) if seg_length else None
+        f_host = torch.empty(feats.shape, dtype=feats.dtype, pin_memory=True)
+        f_host.copy_(feats, non_blocking=True)
+        s_host = None
+        if seg is not None:
+            s_host = torch.empty(seg.shape, dtype=seg.dtype, pin_memory=True)
+            s_host.copy_(seg, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        if pending is not None:
+            yield finish(pending)  # everything of video i is queued before the host waits for video i-1
+        pending = (f_host, s_host, ev, (ds, feats, seg))
+    if pending is not None:
+        yield finish(pending)
+
+
 def _iter_rows(dataset) -> Iterable[Mapping]:
     for row in dataset:
         yield row

@@ -187,3 +187,28 @@ def test_extract_native_backbone_fast_path(model, cuda_device, tmp_path):
     np.save(path, frames)
     out = E.extract([{"video_path": path, "size": 10}], model, cuda_device, os.path.join(str(tmp_path), "o"))
     assert np.array_equal(np.load(out[0]), feats)
+
+
+def test_extract_stream_matches_per_video_extraction(model, cuda_device):
+    """extract_stream (uploads / read-backs of neighbouring videos overlapped) returns, video by video, exactly what the
+    sequential calls return -- including for videos of different lengths and geometries back to back -- and datasets of
+    one frame geometry share a single preprocessing handle."""
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+    from anomaly_detection_on_video_b200.engine import segment_mean
+    from anomaly_detection_on_video_b200.extract_features import extract_clip_features, extract_stream
+
+    rng = np.random.default_rng(5)
+    videos = [rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8) for n, h, w in [(70, 240, 320), (33, 240, 320), (16, 120, 160), (90, 240, 320)]]
+    want = []
+    for v in videos:
+        ds = TenCropVideoFrameDataset(v, device=cuda_device)
+        f = extract_clip_features(ds, model, cuda_device, strict_compat=False, as_numpy=False)
+        want.append((f.cpu(), segment_mean(f, 32).cpu()))
+    a = TenCropVideoFrameDataset(videos[0], device=cuda_device)
+    b = TenCropVideoFrameDataset(videos[1], device=cuda_device)
+    c = TenCropVideoFrameDataset(videos[2], device=cuda_device)
+    assert a._pp is b._pp and a._pp is not c._pp
+    got = list(extract_stream(iter(videos), model, cuda_device))
+    assert len(got) == len(want)
+    for (gf, gs), (wf, ws) in zip(got, want):
+        assert torch.equal(gf, wf) and torch.equal(gs, ws)
