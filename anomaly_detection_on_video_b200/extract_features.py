@@ -179,32 +179,50 @@ def extract(dataset, model: torch.nn.Module, device: torch.device, outpath: str,
     else:
         todo = iter(range(len(rows)))
     written: List[str] = []
-    for ri in todo:
-        sample = rows[ri]
-        filename = _stem_name(sample["video_path"])
-        savepath = os.path.join(outpath, filename + "_i3d.npy")
-        if os.path.exists(savepath):  # idempotent resume, extract_features.py:109-110
-            continue
-        if sample.get("size", 0) > 1024 ** 2:  # > 1 GB (size is in KB), extract_features.py:116
-            src = FrameSource(sample["video_path"])
-            n_seg = (len(src) + chunk_frames - 1) // chunk_frames
-            seg_folder = os.path.join(outpath, filename)
-            os.makedirs(seg_folder, exist_ok=True)
-            segments = []
-            for seg in range(n_seg):
-                seg_savepath = os.path.join(seg_folder, filename + f"_{seg}.npy")
-                if os.path.exists(seg_savepath):
-                    outputs = np.load(seg_savepath)
-                else:
-                    frames = src.read(seg * chunk_frames, (seg + 1) * chunk_frames)
-                    outputs = extract_clip_features(TenCropVideoFrameDataset(frames, device=device), model, device,
-                                                    clips_per_batch, strict_compat)
-                    _atomic_save(seg_savepath, outputs)
-                segments.append(outputs)
-            outputs = np.vstack(segments)  # extract_features.py:148
-        else:
-            outputs = extract_clip_features(TenCropVideoFrameDataset(sample["video_path"], device=device), model, device,
-                                            clips_per_batch, strict_compat)
+    from collections import deque
+
+    streamed: "deque[str]" = deque()  # save paths of the videos currently inside the pipeline, in order
+
+    def small_videos():
+        """Claims rows; videos above the reference's 1 GB threshold are chunked right here (sequentially, with the
+        chunk cache), everything else is handed to extract_stream so that neighbouring videos overlap."""
+        for ri in todo:
+            sample = rows[ri]
+            filename = _stem_name(sample["video_path"])
+            savepath = os.path.join(outpath, filename + "_i3d.npy")
+            if os.path.exists(savepath):  # idempotent resume, extract_features.py:109-110
+                continue
+            if sample.get("size", 0) > 1024 ** 2:  # > 1 GB (size is in KB), extract_features.py:116
+                _extract_chunked(sample, filename, savepath)
+                continue
+            streamed.append(savepath)
+            yield sample["video_path"]
+
+    def _extract_chunked(sample, filename, savepath):
+        src = FrameSource(sample["video_path"])
+        n_seg = (len(src) + chunk_frames - 1) // chunk_frames
+        seg_folder = os.path.join(outpath, filename)
+        os.makedirs(seg_folder, exist_ok=True)
+        segments = []
+        for seg in range(n_seg):
+            seg_savepath = os.path.join(seg_folder, filename + f"_{seg}.npy")
+            if os.path.exists(seg_savepath):
+                outputs = np.load(seg_savepath)
+            else:
+                frames = src.read(seg * chunk_frames, (seg + 1) * chunk_frames)
+                outputs = extract_clip_features(TenCropVideoFrameDataset(frames, device=device), model, device,
+                                                clips_per_batch, strict_compat)
+                _atomic_save(seg_savepath, outputs)
+            segments.append(outputs)
+        outputs = np.vstack(segments)  # extract_features.py:148
+        _atomic_save(savepath, outputs)
+        written.append(savepath)
+
+    for f_host, _ in extract_stream(small_videos(), model, device, clips_per_batch=clips_per_batch, seg_length=None):
+        savepath = streamed.popleft()
+        outputs = f_host.numpy()
+        if strict_compat:
+            outputs = np.squeeze(outputs)  # np.squeeze at extract_features.py:100
         _atomic_save(savepath, outputs)
         written.append(savepath)
     return written
