@@ -80,7 +80,7 @@ def extract_clip_features(video_dataset: TenCropVideoFrameDataset, model: torch.
     -> (n_clips, ncrops, C)."""
     n_clips, k = len(video_dataset), video_dataset.ncrops
     feats: Optional[torch.Tensor] = None
-    if isinstance(model, _NativeBackbone):
+    if isinstance(model, _NativeBackbone) and model.precision == "bf16":
         stem_buf = None
         for start in range(0, n_clips, clips_per_batch):
             n = min(clips_per_batch, n_clips - start)
@@ -94,7 +94,8 @@ def extract_clip_features(video_dataset: TenCropVideoFrameDataset, model: torch.
                 feats = torch.empty(n_clips, k, f.shape[1], dtype=torch.float32, device=f.device)
             feats[start:start + n] = f.view(n, k, -1)
     else:
-        # any other nn.Module: same call pattern as the reference (one forward per crop index)
+        # any other nn.Module (and the native backbones in tf32 mode, which take the reference's fp32 NCTHW crops): same
+        # call pattern as the reference, one forward per crop index
         for start in range(0, n_clips, clips_per_batch):
             n = min(clips_per_batch, n_clips - start)
             inputs = video_dataset.clips_f32(start, n).permute(0, 1, 3, 2, 4, 5)  # (B, 10, 3, 16, H, W), :83

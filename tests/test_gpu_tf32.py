@@ -197,3 +197,19 @@ def test_inception_tf32_features_match_fp32_oracle(cuda_device):
     got = m(x.to(cuda_device)).cpu().view(1, -1)
     ref = OI.extract_features(x, OI.seeded_state_dict(0)).view(1, -1)
     close_tf32(got[0], ref[0])
+
+
+def test_extract_clip_features_in_tf32_mode(model, cuda_device):
+    """extract_clip_features with a tf32-mode backbone takes the reference's call pattern (fp32 NCTHW crops, one forward per
+    crop index) and lands within the TF32 tolerance of the fp32 oracle run on the same preprocessed clips."""
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+    from anomaly_detection_on_video_b200.extract_features import extract_clip_features
+
+    frames = np.random.default_rng(3).integers(0, 256, size=(20, 120, 160, 3), dtype=np.uint8)
+    ds = TenCropVideoFrameDataset(frames, device=cuda_device)
+    feats = extract_clip_features(ds, model, cuda_device, strict_compat=False, as_numpy=False).cpu()   # (2, 10, 2048)
+    assert feats.shape == (2, 10, 2048)
+    clip = ds[1].cpu()                                                                                  # (10, 16, 3, 224, 224)
+    ref, _ = O.forward(clip[[0, 4, 9]].permute(0, 2, 1, 3, 4).contiguous(), O.seeded_state_dict(0))
+    for j, c in enumerate([0, 4, 9]):
+        close_tf32(feats[1, c], ref[j].view(-1))
