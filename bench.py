@@ -473,7 +473,7 @@ def main():
         cpu_baseline = None
         if not args.no_cpu_baseline:
             os.sched_setaffinity(0, cpus_at_start)  # the CPU baseline gets every core the box allows
-            v, d = cpu_reference_run(steps=4, warmup=1, clips_per_step=2)
+            v, d = cpu_reference_run(steps=8, warmup=1, clips_per_step=4)  # ~12 s of CPU work
             cpu_baseline = {"value": v, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": d["sample"],
                             "seconds": d["seconds"]}
         line = {
