@@ -73,3 +73,34 @@ def test_python_api_refuses_cpu_tensors(native_lib):
         engine.segment_mean(torch.zeros(4, 10, 8))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         I3Res50().eval()(torch.zeros(1, 3, 8, 32, 32))
+
+
+def test_tf32_and_pair_paths_are_in_the_binary():
+    """The TF32 mode and the CTA-pair kernels are compiled into the same library: kind::tf32 and cta_group::2 MMAs in SASS."""
+    from anomaly_detection_on_video_b200 import _lib, build
+
+    build.build()
+    res = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = res.stdout
+    assert "conv_tf32_kernel" in sass and "conv_pair_kernel" in sass
+    assert "2CTA" in sass, "tcgen05.mma.cta_group::2 missing from SASS"
+
+
+def test_tf32_mode_fails_loudly_without_gpu(native_lib):
+    import torch
+
+    from anomaly_detection_on_video_b200 import engine
+    from anomaly_detection_on_video_b200.i3d import I3Res50
+
+    m = I3Res50().eval()
+    m.precision = "tf32"
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 8, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.ingest_ncthw_tf32(torch.zeros(1, 3, 8, 32, 32))
+    m.precision = "fp16"
+    if torch.cuda.is_available():
+        with pytest.raises(ValueError):
+            m(torch.zeros(1, 3, 8, 32, 32, device="cuda"))
