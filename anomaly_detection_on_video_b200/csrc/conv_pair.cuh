@@ -122,7 +122,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int STAGES = Cfg::kStages;
   constexpr int NB = Cfg::kEpiBufs;
   const int crank = (int)cluster_ctarank();
-  const int w_first = (int)(blockIdx.x >> 1), w_step = (int)(gridDim.x >> 1), w_total = p.mc_items;
+  // SPLIT (BN = 256, direct epilogue, one n tile): the items of the last, partly filled round run as two 128-column halves
+  // each, so 3.3 rounds of work take 3.5 rounds instead of 4 (wave quantisation of the 74 CTA pairs)
+  constexpr bool SPLIT = BN == 256 && !EPI;
+  const int w_first = (int)(blockIdx.x >> 1), w_step = (int)(gridDim.x >> 1);
+  const int w_split = SPLIT ? p.pair_split : p.mc_items, w_total = SPLIT ? p.pair_total : p.mc_items;
+  // item -> (m pair, first column, half-width?)
+  auto item_mpair = [&](int w) { return w < w_split ? w / p.n_tiles : w_split / p.n_tiles + ((w - w_split) >> 1); };
+  auto item_n0 = [&](int w) { return w < w_split ? (w % p.n_tiles) * BN : ((w - w_split) & 1) * (BN / 2); };
 
   extern __shared__ __align__(1024) uint8_t pair_smem[];
   uint8_t* smem = pair_smem;
@@ -182,8 +189,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t s = 0, ph = 0;
       griddep_wait();
       for (int tile = w_first; tile < w_total; tile += w_step) {
-        const int n0 = (tile % p.n_tiles) * BN + crank * (BN / 2);
-        const int m0 = (2 * (tile / p.n_tiles) + crank) * kBlockM;
+        const bool half = SPLIT && tile >= w_split;
+        const int b_rows = half ? BN / 4 : BN / 2;  // weight rows this CTA supplies
+        const int n0 = item_n0(tile) + crank * b_rows;
+        const int m0 = (2 * item_mpair(tile) + crank) * kBlockM;
+        const uint32_t stage_tx = (uint32_t)(Cfg::kABytes + b_rows * 128);
         int wq = 0, hq = 0, dq = 0, nq = 0;
         if (p.a_mode == A_TMA_IM2COL) {
           int t = m0;
@@ -202,7 +212,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_dst = stage0 + s * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + KPS * Cfg::kABytes;
           const uint32_t fb = lfull0 + s * 8;
-          if (crank == 0) mbar_arrive_expect_tx_a(full0 + s * 8, (uint32_t)nk * 2u * Cfg::kKbBytes);  // both CTAs' bytes
+          if (crank == 0) mbar_arrive_expect_tx_a(full0 + s * 8, (uint32_t)nk * 2u * stage_tx);  // both CTAs' bytes
 #pragma unroll
           for (int j = 0; j < KPS; ++j) {
             if (j < nk) {
@@ -216,7 +226,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
                 }
               }
-              tma_load_2d_pair(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * 64, n0);
+              if (SPLIT && p.pair_box_rows == 64) {  // 64-row weight boxes: two for a full-width item, one for a half
+                tma_load_2d_pair(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * 64, n0);
+                if (!half) tma_load_2d_pair(b_dst + j * Cfg::kBBytes + 64 * 128, &tmB, fb, (kb + j) * 64, n0 + 64);
+              } else {
+                tma_load_2d_pair(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * 64, n0);
+              }
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -227,7 +242,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (crank == 0 && elect_one_sync()) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m256(BN);
+      constexpr uint32_t idesc_full = umma_idesc_bf16_m256(BN), idesc_half = umma_idesc_bf16_m256(BN / 2);
       const uint64_t desc_hi = umma_desc_kmajor<128>(0);
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
       const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
@@ -240,6 +255,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         const bool last_tile = tile + w_step >= w_total;
+        const uint32_t idesc = (SPLIT && tile >= w_split) ? idesc_half : idesc_full;
         for (int kb = 0; kb < p.num_kb; kb += KPS) {
           const int nk = (KPS == 1 || kb + KPS <= p.num_kb) ? KPS : p.num_kb - kb;
           const bool last_stage = kb + KPS >= p.num_kb;
@@ -298,8 +314,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int prev_eb = -1;          // staging tile whose TMA store has been issued but not yet waited for
     int tc = 0, cached_n0 = -1;
     for (int tile = w_first; tile < w_total; tile += w_step) {
-      const int n0 = (tile % p.n_tiles) * BN;
-      const int m0 = (2 * (tile / p.n_tiles) + crank) * kBlockM;
+      const int n0 = item_n0(tile);
+      const int m0 = (2 * item_mpair(tile) + crank) * kBlockM;
+      const bool half = SPLIT && tile >= w_split;        // a 128-column item of the tail round: 64 columns per warp
+      const int cpw_i = half ? CPW / 2 : CPW;
+      const int col0_i = ((warp - 2) >> 2) * cpw_i;
       const int acc = tc & 1;
       const uint32_t aph = (tc >> 1) & 1;
       ++tc;
@@ -316,7 +335,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m0 + q * 32 + lane;
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0_i);
       if (EPI) {
         // two 128-column halves; in each, this warp owns rows [32q, 32q+32) x columns [col0, col0+64) of the staging tile
         const int lrow = q * 32 + lane;
@@ -386,9 +405,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         continue;
       }
       const bool row_ok = row < p.M;
-      __nv_bfloat16* out_row = p.out + (long long)row * p.ldo + n0 + col0;
+      __nv_bfloat16* out_row = p.out + (long long)row * p.ldo + n0 + col0_i;
 #pragma unroll 1
-      for (int c = 0; c < CPW / 32; ++c) {
+      for (int c = 0; c < cpw_i / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
@@ -396,11 +415,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = c * 32 + g * 8;
-            if (n0 + col0 + col < p.N) {
+            if (n0 + col0_i + col < p.N) {
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col0 + col + j], s_shift[col0 + col + j]);
+                f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col0_i + col + j], s_shift[col0_i + col + j]);
               if (p.relu) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);

@@ -38,6 +38,9 @@ struct ConvParams {
   int M, N, num_kb;
   int n_tiles, num_tiles;
   int mc_items;          // MC kernels: work items = ceil(m_tiles / 2) * n_tiles (a cluster of two CTAs per item)
+  int pair_split;        // conv_pair_kernel<256>: items [0, pair_split) are 256 x 256 tiles; item pair_split + h is the
+  int pair_total;        //   (h & 1)-th 128-column half of m-pair pair_split + h / 2 (tail round at half width); total items
+  int pair_box_rows;     //   rows of one weight box (128, or 64 when there are half-width items)
   int To, Ho, Wo;
   int Ti, Hi, Wi;
   int kt, kh, kw, st, sh, sw, pt, ph, pw;

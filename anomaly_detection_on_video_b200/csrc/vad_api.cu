@@ -138,6 +138,7 @@ struct vad_plan {
   bool no_s3 = false;        // VAD_NO_S3X3=1: layer1's (1,3,3) convs through the generic im2col kernel
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
+  bool no_pair_split = false; // VAD_NO_PAIR_SPLIT=1: no half-width tail items in the CTA-pair kernel
   bool no_bk32 = false;      // VAD_NO_BK32=1: Cin % 64 == 32 layers through the gather producer (as before the 32-wide TMA path)
   int pair_mode = 1;         // VAD_PAIR=0: never use the CTA-pair kernel; 1 (default): for the long-K layers without residual
   int pair_epi_min_kb = 8;   // VAD_PAIR_EPI_MIN_KB: same for residual layers (staged epilogue; measured: K = 512 gains, K = 256 loses); 0 = off
@@ -240,6 +241,7 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR"); p->pair_mode = k ? atoi(k) : 1; }
   { const char* k = getenv("VAD_NO_BK32"); p->no_bk32 = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_NO_PAIR_SPLIT"); p->no_pair_split = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR_MIN_KB"); p->pair_min_kb = k ? atoi(k) : 12; }
   { const char* k = getenv("VAD_PAIR_EPI_MIN_KB"); p->pair_epi_min_kb = k ? atoi(k) : 8; }
   { const char* k = getenv("VAD_MC_MIN_TILES"); p->mc_min_tiles = k ? atoi(k) : -1; }
@@ -435,6 +437,16 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       if (r.mc || r.pair || r.pair_epi) {
         c.mc_items = (int)(((m_tiles + 1) / 2) * n_tiles);
         r.grid = 2 * c.mc_items < p->sm_count ? 2 * c.mc_items : p->sm_count;  // whole clusters, each with at least one item
+        c.pair_split = c.pair_total = c.mc_items;
+        c.pair_box_rows = r.bn / 2;
+        // wave quantisation: when the last round of pair tiles fills at most half of the CTA pairs, run its items as two
+        // 128-column halves each (one n tile only: cout == 256), e.g. layer3: 245 tiles on 74 pairs = 3.31 -> 3.5 rounds, not 4
+        const int clusters = r.grid / 2, rem = clusters > 0 ? c.mc_items % clusters : 0;
+        if (r.pair && r.bn == 256 && n_tiles == 1 && !p->no_pair_split && c.mc_items > clusters && rem > 0 && 2 * rem <= clusters) {
+          c.pair_split = c.mc_items - rem;
+          c.pair_total = c.pair_split + 2 * rem;
+          c.pair_box_rows = 64;
+        }
       }
       if (r.thalo) { r.tp.n_tiles = c.n_tiles; r.tp.num_tiles = c.num_tiles; }
       c.l2_ahead = (r.epi && d.res >= 0) ? p->l2_ahead : 0;
@@ -622,7 +634,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         // each CTA of a pair loads half of the BN weight rows (mc: and multicasts them)
         cuuint64_t gdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
         cuuint64_t gstr[1] = {(cuuint64_t)r.K_pad * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)(r.bn / 2)};
+        cuuint32_t box[2] = {64, (cuuint32_t)(r.mc ? r.bn / 2 : c.pair_box_rows)};
         cuuint32_t es[2] = {1, 1};
         CUresult cr = p->encode_tiled(r.mc ? &r.tmR : &r.tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), gdim, gstr, box, es,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

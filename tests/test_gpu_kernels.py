@@ -467,6 +467,32 @@ PAIR_CASES = MC_CASES + [
 ]
 
 
+SPLIT_CASES = [
+    # cout == 256 (one n tile), 98 pair-tiles on 74 CTA pairs: 74 full-width items + 24 tiles as 48 half-width items
+    ("1x1 256->256, 98 pair tiles", 256, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 8, 4, 28, 28),
+    ("s3x3 128->256 im2col, 98 pair tiles", 128, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), 8, 4, 28, 28),
+    ("1x1 512->256, odd m-tiles (197 -> 99 pairs)", 512, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 1, 158, 159),
+]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES, ids=[c[0] for c in SPLIT_CASES])
+def test_cta_pair_tail_round_at_half_width(cuda_device, case, monkeypatch):
+    """When the last round of 256 x 256 pair tiles fills at most half of the CTA pairs, its tiles run as two 128-column
+    halves each (M = 256, N = 128 MMAs into the same accumulator columns); bit-identical to the unsplit schedule and to
+    the single-CTA kernel."""
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    monkeypatch.setenv("VAD_PAIR_MIN_KB", "1")
+    monkeypatch.setenv("VAD_PAIR", "0")
+    plain, ref = run_conv_case(*case[1:], False, True)
+    monkeypatch.setenv("VAD_PAIR", "1")
+    split, _ = run_conv_case(*case[1:], False, True)
+    monkeypatch.setenv("VAD_NO_PAIR_SPLIT", "1")
+    unsplit, _ = run_conv_case(*case[1:], False, True)
+    assert_bf16_close(split, ref)
+    assert torch.equal(split, plain) and torch.equal(unsplit, plain)
+
+
 @pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
 def test_cta_pair_kernel_matches_the_plain_kernel(cuda_device, case, monkeypatch):
     """conv_pair_kernel (tcgen05 cta_group::2: two CTAs share one 256 x 256 tile, each loading half of the weight rows) is
