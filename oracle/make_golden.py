@@ -101,6 +101,41 @@ def golden_mgfn(ref) -> None:
     np.savez_compressed(os.path.join(GOLDEN, "mgfn.npz"), **out)
 
 
+def golden_mgfn_train(ref) -> None:
+    """a23 (src/runner.py:29-39,53-59): one training step of the live reference -- train() mode, every dropout at 0 so that
+    it is deterministic -- on a batch of 2 normal + 2 abnormal bags: loss, per-parameter gradient digests (L2 norm, sum,
+    first 6 entries), the BatchNorm running statistics after the step and the digests of the parameters after one Adam
+    step (lr 1e-3, weight_decay 5e-4: configs/runner/default.yaml:5-7)."""
+    import importlib
+
+    modeling = importlib.import_module("src.models.mgfn.modeling_mgfn")
+    configuration = importlib.import_module("src.models.mgfn.configuration_mgfn")
+    sd = MG.seeded_state_dict(0)
+    model = modeling.MGFNForVideoAnomalyDetection(configuration.MGFNConfig(dropout_rate=0.0))
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    video = MG.synthetic_video(3, 4, 10, 32)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    r = model(video, abnormal_labels=torch.ones(2), normal_labels=torch.zeros(2))
+    opt.zero_grad()
+    r.loss.backward()
+    out = {"video_sha": np.array(sha(video.numpy())), "loss": r.loss.detach().numpy(), "scores": r.scores.detach().numpy()}
+    names = []
+    for name, p_ in model.named_parameters():
+        g = p_.grad.detach().double().reshape(-1)
+        names.append(name)
+        out[f"grad/{name}"] = np.array([float(g.norm()), float(g.sum())] + [float(v) for v in g[:6]], dtype=np.float64)
+    opt.step()
+    for name, p_ in model.named_parameters():
+        w = p_.detach().double().reshape(-1)
+        out[f"adam/{name}"] = np.array([float(w.norm()), float(w.sum())] + [float(v) for v in w[:6]], dtype=np.float64)
+    for name, b in model.named_buffers():
+        if name.endswith("running_mean") or name.endswith("running_var"):
+            out[f"buf/{name}"] = b.detach().numpy()
+    out["param_names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLDEN, "mgfn_train.npz"), **out)
+
+
 def main() -> None:
     ref = _refload.load()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -108,7 +143,12 @@ def main() -> None:
         golden_mgfn(ref)
         print("mgfn.npz", os.path.getsize(os.path.join(GOLDEN, "mgfn.npz")))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "mgfn_train":
+        golden_mgfn_train(ref)
+        print("mgfn_train.npz", os.path.getsize(os.path.join(GOLDEN, "mgfn_train.npz")))
+        return
     golden_mgfn(ref)
+    golden_mgfn_train(ref)
 
     # ---------------------------------------------------------------- P1 preprocessing
     frames = synth_frames(0, 5, 60, 80)

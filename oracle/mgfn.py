@@ -109,9 +109,12 @@ def _glance_attention(x, sd, p, heads, dim_head):  # modeling_mgfn.py:109-127
     return F.conv1d(out, sd[p + ".to_out.weight"], sd[p + ".to_out.bias"])
 
 
-def _focus_attention(x, sd, p, heads):  # modeling_mgfn.py:178-186
-    x = F.batch_norm(x, sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"], sd[p + ".norm.weight"], sd[p + ".norm.bias"],
-                     training=False, eps=1e-5)
+def _focus_attention(x, sd, p, heads, training=False):  # modeling_mgfn.py:178-186
+    # training: BatchNorm1d normalises with the batch statistics (the running buffers are updated on copies: the oracle
+    # never mutates the state dict it is given)
+    x = F.batch_norm(x, sd[p + ".norm.running_mean"].clone() if training else sd[p + ".norm.running_mean"],
+                     sd[p + ".norm.running_var"].clone() if training else sd[p + ".norm.running_var"], sd[p + ".norm.weight"],
+                     sd[p + ".norm.bias"], training=training, eps=1e-5)
     b, _, n = x.shape
     v = F.conv1d(x, sd[p + ".to_v.weight"])
     c = v.shape[1] // heads
@@ -122,7 +125,7 @@ def _focus_attention(x, sd, p, heads):  # modeling_mgfn.py:178-186
     return F.conv1d(out, sd[p + ".to_out.weight"], sd[p + ".to_out.bias"])
 
 
-def backbone(video: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: Optional[dict] = None) -> torch.Tensor:
+def backbone(video: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: Optional[dict] = None, training: bool = False) -> torch.Tensor:
     """MGFNModel.forward (modeling_mgfn.py:67-94,241-283): [bs, ncrops, t, C+1] -> [bs*ncrops, d_last, t]."""
     c = dict(DEFAULT, **(cfg or {}))
     bs, ncrops, t, ch = video.shape
@@ -138,7 +141,7 @@ def backbone(video: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: Optional[dic
             if ty == "gb":
                 x = _glance_attention(x, sd, p + ".attention", heads, c["dim_head"]) + x
             else:
-                x = _focus_attention(x, sd, p + ".attention", heads) + x
+                x = _focus_attention(x, sd, p + ".attention", heads, training) + x
             x = _ffn(x, sd, p + ".ffn") + x
         if si != len(c["dims"]) - 1:
             p = f"backbone.layers.{si}.{depth}"
@@ -152,11 +155,18 @@ def contrastive(o1, o2, label, margin=200.0):  # src/loss/base.py:36-48
 
 
 def forward(video: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: Optional[dict] = None, split: bool = False,
-            normal_labels: Optional[torch.Tensor] = None, abnormal_labels: Optional[torch.Tensor] = None) -> dict:
-    """MGFNForVideoAnomalyDetection.forward in eval mode (dropout inactive), modeling_mgfn.py:302-427."""
+            normal_labels: Optional[torch.Tensor] = None, abnormal_labels: Optional[torch.Tensor] = None,
+            training: bool = False) -> dict:
+    """MGFNForVideoAnomalyDetection.forward, modeling_mgfn.py:302-427.  Default: eval mode (dropout inactive).
+    ``training=True`` is the train-mode forward with every dropout probability at 0 (``MGFNConfig(dropout_rate=0.0)``;
+    the shipped 0.7 on the selection mask makes the step stochastic and is not restated): BatchNorm1d of the Focus blocks
+    uses batch statistics, inputs are always split into the normal and the abnormal half (modeling_mgfn.py:320-331).
+    Everything is differentiable torch, so ``torch.autograd`` over this function is the gradient oracle for the training
+    step (src/runner.py:29-39) -- pinned against the live reference's ``loss.backward()`` by tests/golden/mgfn_train.npz."""
     c = dict(DEFAULT, **(cfg or {}))
     bs, ncrops = video.shape[:2]
-    x = backbone(video.float(), sd, c).permute(0, 2, 1)
+    split = split or training
+    x = backbone(video.float(), sd, c, training).permute(0, 2, 1)
     x = F.layer_norm(x, (x.shape[-1],), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
     scores_tok = torch.sigmoid(F.linear(x, sd["fc.weight"], sd["fc.bias"]))
     _, t, f = x.shape

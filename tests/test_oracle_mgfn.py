@@ -83,3 +83,46 @@ def test_product_module_keeps_the_reference_parameter_names(sd):
         m.eval()(M.synthetic_video(0, 2, 10, 8))
     with pytest.raises(RuntimeError, match="inference-only"):
         m.train()(M.synthetic_video(0, 2, 10, 8))
+
+
+def test_training_step_gradients_match_the_live_reference(golden_dir):
+    """a23 groundwork: torch.autograd over the oracle's train-mode forward (dropout probabilities 0, BatchNorm on batch
+    statistics) reproduces the live reference's ``loss.backward()`` -- per-parameter gradient digests from
+    tests/golden/mgfn_train.npz -- and one Adam step (lr 1e-3, weight_decay 5e-4, src/runner.py:53-59) lands on the
+    reference's updated parameters.  This is the oracle the backward kernels of the scoring head will be held to."""
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle import mgfn as MG
+
+    g = np.load(os.path.join(golden_dir, "mgfn_train.npz"))
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running_" not in k and "num_batches" not in k)
+          for k, v in MG.seeded_state_dict(0).items()}
+    video = MG.synthetic_video(3, 4, 10, 32)
+    out = MG.forward(video, sd, normal_labels=torch.zeros(2), abnormal_labels=torch.ones(2), training=True)
+    np.testing.assert_allclose(out["loss"].detach().numpy(), g["loss"], rtol=1e-5)
+    np.testing.assert_allclose(out["scores"].detach().numpy(), g["scores"], rtol=1e-4, atol=1e-6)
+    names = [str(n) for n in g["param_names"]]
+    params = [sd[n] for n in names]
+    grads = torch.autograd.grad(out["loss"], params, allow_unused=False)
+    worst = 0.0
+    for n, p, gr in zip(names, params, grads):
+        d = gr.detach().double().reshape(-1)
+        got = np.array([float(d.norm()), float(d.sum())] + [float(v) for v in d[:6]])
+        want = g[f"grad/{n}"]
+        scale = max(want[0], 1e-12)
+        err = np.abs(got - want).max() / scale
+        worst = max(worst, err)
+        assert err < 2e-3, (n, got, want)
+    # one Adam step with L2 weight decay folded into the gradient (torch.optim.Adam semantics), first step: m = (1-b1) g,
+    # v = (1-b2) g^2, bias-corrected -> delta = lr * g / (|g| + eps)
+    lr, wd, eps = 1e-3, 5e-4, 1e-8
+    for n, p, gr in zip(names, params, grads):
+        gt = gr.detach().double() + wd * p.detach().double()
+        new = (p.detach().double() - lr * gt / (gt.abs() + eps)).reshape(-1)
+        got = np.array([float(new.norm()), float(new.sum())])
+        want = g[f"adam/{n}"][:2]
+        assert abs(got[0] - want[0]) <= 1e-4 * max(want[0], 1e-6) + 1e-7, (n, got, want)
+    print(f"worst gradient digest error (relative to the gradient norm): {worst:.2e}")
