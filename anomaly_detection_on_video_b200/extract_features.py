@@ -51,12 +51,24 @@ def load_ucf_crime_dataset(repo_id: str = DEFAULT_REPO_ID, cache_dir: str = DEFA
 
 
 def load_feature_extraction_model(model_name: str = "tushar-n-baseline", state_dict_path: Optional[str] = None,
-                                  device: Optional[torch.device] = None) -> Tuple[torch.nn.Module, torch.device]:
+                                  device: Optional[torch.device] = None, precision: str = "bf16") -> Tuple[torch.nn.Module, torch.device]:
     """extract_features.py:34-40.  The default is the reference *factory's* default backbone (I3Res50);
-    the reference CLI's own default, pytorchvideo's ``i3d_8x8_r50``, is third-party and not built."""
+    the reference CLI's own default, pytorchvideo's ``i3d_8x8_r50``, is third-party and not built.
+    ``model_name="inception-i3d"`` builds the InceptionV1-3D backbone BASELINE.json names (1024-d features; not part of
+    the reference).  ``precision``: "bf16" (production) or "tf32" (fp32 activations, features within 1e-3)."""
+    if precision not in ("bf16", "tf32"):
+        raise ValueError(f"precision must be 'bf16' or 'tf32', not {precision!r}")
     if not torch.cuda.is_available():
         raise RuntimeError("feature extraction runs on sm_100a GPUs only; no CUDA device is visible")
-    model = build_i3d_feature_extractor(model_name=model_name, state_dict_path=state_dict_path)
+    if model_name == "inception-i3d":
+        from .inception import InceptionI3d
+
+        model = InceptionI3d()
+        if state_dict_path is not None:
+            model.load_state_dict(torch.load(state_dict_path, map_location="cpu"), strict=True)
+    else:
+        model = build_i3d_feature_extractor(model_name=model_name, state_dict_path=state_dict_path)
+    model.precision = precision
     model.eval()
     model.to(device if device is not None else "cuda")
     return model, next(model.parameters()).device
@@ -247,11 +259,11 @@ def segment(feature_path: str, seg_outpath: str, seg_length: int = 32, queue: Op
 
 
 def main(outdir: str = "/content/drive/MyDrive/ucf_crime", dataset=None, model_name: str = "tushar-n-baseline",
-         state_dict_path: Optional[str] = None, queue: Optional[WorkQueue] = None) -> None:
+         state_dict_path: Optional[str] = None, queue: Optional[WorkQueue] = None, precision: str = "bf16") -> None:
     """extract_features.py:43-52."""
     outpath = os.path.join(outdir, "anomaly_features")
     anomaly = dataset if dataset is not None else load_ucf_crime_dataset()
-    model, device = load_feature_extraction_model(model_name, state_dict_path)
+    model, device = load_feature_extraction_model(model_name, state_dict_path, precision=precision)
     extract(anomaly, model, device, outpath, queue=queue)
     seg_length = 32
     seg_outpath = os.path.join(outdir, f"segment_features_{seg_length}")
@@ -276,7 +288,10 @@ def cli(argv: Optional[Sequence[str]] = None) -> None:
     ap.add_argument("--outdir", required=True)
     ap.add_argument("--videos", help="directory of videos (.npy frame arrays or containers); one 'train' split")
     ap.add_argument("--weights", help="state_dict for the backbone (reference checkpoint format)")
-    ap.add_argument("--model-name", default="tushar-n-baseline")
+    ap.add_argument("--model-name", default="tushar-n-baseline", help="tushar-n-baseline (I3Res50, 2048-d) or inception-i3d (1024-d)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="bf16: bf16 operands / activations, fp32 accumulate (features within 1e-2 of the fp32 reference); "
+                         "tf32: fp32 activations, TF32 tensor-core products (within 1e-3, ~5x slower)")
     args = ap.parse_args(argv)
     queue = WorkQueue.from_env()
     if queue is not None:
@@ -285,7 +300,7 @@ def cli(argv: Optional[Sequence[str]] = None) -> None:
 
     bind_to_gpu(queue.local_rank if queue is not None else 0)  # pinned frame buffers land on the GPU's own socket
     dataset = {"train": _rows_from_dir(args.videos)} if args.videos else None
-    main(args.outdir, dataset=dataset, model_name=args.model_name, state_dict_path=args.weights, queue=queue)
+    main(args.outdir, dataset=dataset, model_name=args.model_name, state_dict_path=args.weights, queue=queue, precision=args.precision)
 
 
 if __name__ == "__main__":

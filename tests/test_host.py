@@ -227,3 +227,20 @@ def test_tf32_weight_packing_rounds_to_tf32_and_pads_k_to_32():
     got = packed[..., :3]
     assert torch.all((got.contiguous().view(torch.int32) & 0x1FFF) == 0)          # low 13 mantissa bits clear
     assert torch.all((got - want).abs() <= want.abs() * 2.0 ** -11 + 1e-30)       # nearest, not truncated
+
+
+def test_cli_precision_and_model_arguments():
+    """--precision is validated before anything touches a device; without a GPU the loader still fails loudly."""
+    import pytest
+    import torch
+
+    from anomaly_detection_on_video_b200 import extract_features as E
+
+    with pytest.raises(ValueError, match="precision"):
+        E.load_feature_extraction_model(precision="fp8")
+    with pytest.raises(SystemExit):
+        E.cli(["--outdir", "/tmp/unused", "--precision", "int8"])
+    if not torch.cuda.is_available():
+        for name in ("tushar-n-baseline", "inception-i3d"):
+            with pytest.raises(RuntimeError, match="sm_100a"):
+                E.load_feature_extraction_model(name, precision="tf32")
