@@ -18,6 +18,7 @@
 #include "conv_thalo.cuh"
 #include "conv_s3x3.cuh"
 #include "conv_pair.cuh"
+#include "conv_tail.cuh"
 
 using namespace vad;
 
@@ -116,6 +117,13 @@ struct OpRuntime {
   bool stem_mf = false;  // multi-frame (input-frame stationary) stem kernel
   int stem_ti = 0, stem_ti_max = 0;
   int a_mode = 0;
+  // bottleneck-tail fusion (conv_tail.cuh): this (1,3,3) 64 -> 64 op also runs the following 1x1x1 64 -> 256 conv3
+  // (+ residual: tail = 1; + the block's 1x1x1 downsample of X folded into conv3's contraction: tail = 2)
+  int tail = 0;
+  int tail_c3 = -1, tail_ds = -1;  // op indices of the fused conv3 / downsample
+  bool skip = false;               // this op runs inside an earlier op's launch
+  TailParams tlp;
+  CUtensorMap tmW3, tmX;
   int avg_P = 0, avg_C = 0;
   // for tensor-map encoding
   int Ci = 0, Ti = 0, Hi = 0, Wi = 0;
@@ -135,6 +143,11 @@ struct vad_plan {
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool epi_all = false;      // VAD_EPI_ALL=1: staged TMA-store epilogue for every layer (tuning only)
+  int tail_cfg = 0;          // VAD_TAIL_CFG: shared-memory split of the residual tail kernel (tuning)
+  bool no_tail = false;      // VAD_NO_TAIL=1: no conv2 -> conv3 (+ downsample) fusion in layer1 (A/B and bit-identity tests)
+  std::vector<std::pair<int, void*>> fold_bufs;  // (op index, 64 KB device buffer): BN-scaled [W3 | Wd] of a tail = 2 op
+  bool fold_pending = false;                     // fold_bufs must be (re)filled on the next bind
+  int s3_halo = 0;           // VAD_S3_HALO=1|2: (1,3,3) halo-tile kernels load ONE 10 x 18 halo box per tile (2: with the descriptor base offset)
   bool no_s3 = false;        // VAD_NO_S3X3=1: layer1's (1,3,3) convs through the generic im2col kernel
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
@@ -170,6 +183,7 @@ struct vad_plan {
   std::vector<double> op_bytes;       // algorithmic bytes per op (inputs read once + outputs written once)
   std::vector<double> prof_flops, prof_bytes;  // totals over the profiled launches
   ~vad_plan() {
+    for (auto& fb : fold_bufs) cudaFree(fb.second);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_used) cudaEventDestroy(e);
   }
@@ -237,6 +251,9 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   const char* sgen = getenv("VAD_STEM_GENERIC");
   p->stem_generic = sgen && sgen[0] == '1';
   { const char* k = getenv("VAD_NO_S3X3"); p->no_s3 = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_NO_TAIL"); p->no_tail = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_S3_HALO"); p->s3_halo = k ? atoi(k) : 0; }
+  { const char* k = getenv("VAD_TAIL_CFG"); p->tail_cfg = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR"); p->pair_mode = k ? atoi(k) : 1; }
@@ -422,6 +439,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         q.F = batch * src.T; q.H = src.H; q.W = Wi;
         q.tiles_w = (Wi + 7) / 8; q.tiles_h = (src.H + 15) / 16;
         q.relu = c.relu;
+        q.base_off_mode = p->s3_halo == 2 ? 1 : 0;
         m_tiles = (long long)q.F * q.tiles_w * q.tiles_h;
       }
       const long long n_tiles = (d.cout + r.bn - 1) / r.bn;
@@ -568,6 +586,69 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
     const uint64_t bytes = (uint64_t)batch * To * Ho * Wo * Cdst * 2;
     if (bytes > dst.bytes) dst.bytes = bytes;
   }
+  // ---- bottleneck-tail fusion: a (1,3,3) 64 -> 64 halo-tile conv whose output feeds only the next 1x1x1 64 -> 256
+  // residual conv runs both in one launch (conv_tail.cuh); when the residual is the block's own 1x1x1 downsample of a
+  // 64-channel X, that conv joins the contraction as well.  The intermediate slots must be dead afterwards.
+  if (!p->no_tail) {
+    const int n_ops = (int)p->ops.size();
+    auto dead_after = [&](int slot, int last_reader) {
+      for (int j = last_reader + 1; j < n_ops; ++j) {
+        const vad_op_desc& e = p->ops[j];
+        if (e.src == slot || (e.kind == VAD_OP_CONV && e.res == slot)) return false;
+        if (e.kind != VAD_OP_AVGPOOL && e.dst == slot) return true;
+      }
+      return true;
+    };
+    auto is_proj = [&](int j) {  // 1x1x1, stride 1, 64 -> 256 into a whole 256-channel slot, TMA operands
+      if (j >= n_ops) return false;
+      const vad_op_desc& e = p->ops[j];
+      return e.kind == VAD_OP_CONV && e.kt == 1 && e.kh == 1 && e.kw == 1 && e.st == 1 && e.sh == 1 && e.sw == 1 && !e.pt && !e.ph && !e.pw &&
+             !(e.flags & ~VAD_FLAG_RELU) && e.cin == 64 && e.cout == 256 && e.dst_c_off == 0 && (e.dst_c_total == 0 || e.dst_c_total == 256) &&
+             p->rt[j].K_pad == 64;
+    };
+    for (int i = 0; i + 1 < n_ops; ++i) {
+      OpRuntime& r = p->rt[i];
+      const vad_op_desc& d = p->ops[i];
+      if (!r.s3 || r.skip) continue;
+      int c3 = -1, ds = -1;
+      if (is_proj(i + 1) && p->ops[i + 1].src == d.dst && p->ops[i + 1].res >= 0 && p->ops[i + 1].res != d.dst &&
+          p->rt[i + 1].res_c == 256 && p->ops[i + 1].dst != p->ops[i + 1].res && dead_after(d.dst, i + 1)) {
+        c3 = i + 1;
+      } else if (is_proj(i + 1) && is_proj(i + 2) && p->ops[i + 1].res < 0 && p->ops[i + 1].src != d.dst && p->ops[i + 1].dst != d.dst &&
+                 p->rt[i + 1].cp.M == r.cp.M && p->ops[i + 2].src == d.dst && p->ops[i + 2].res == p->ops[i + 1].dst &&
+                 p->ops[i + 2].dst != p->ops[i + 1].src && p->ops[i + 2].dst != d.dst && dead_after(d.dst, i + 2) &&
+                 dead_after(p->ops[i + 1].dst, i + 2)) {
+        ds = i + 1; c3 = i + 2;
+      }
+      if (c3 < 0) continue;
+      r.tail = ds >= 0 ? 2 : 1;
+      r.tail_c3 = c3; r.tail_ds = ds;
+      p->rt[c3].skip = true;
+      if (ds >= 0) p->rt[ds].skip = true;
+      TailParams& q = r.tlp;
+      memset(&q, 0, sizeof(q));
+      q.F = r.s3p.F; q.H = r.s3p.H; q.W = r.s3p.W;
+      q.tiles_w = r.s3p.tiles_w; q.tiles_h = r.s3p.tiles_h; q.num_tiles = r.s3p.num_tiles;
+      q.relu2 = r.cp.relu; q.relu3 = p->rt[c3].cp.relu;
+      // per-op accounting: the fused launch carries the FLOPs of its parts; bytes = each tensor touched once
+      const double Md = (double)r.cp.M;
+      p->op_flops[i] += p->op_flops[c3] + (ds >= 0 ? p->op_flops[ds] : 0.0);
+      p->op_flops[c3] = 0.0;
+      p->op_bytes[i] = 2.0 * (Md * 64 + Md * 256 + Md * (ds >= 0 ? 64 : 256) + 9.0 * 64 * 64 + 256.0 * 64 * (ds >= 0 ? 2 : 1));
+      p->op_bytes[c3] = 0.0;
+      if (ds >= 0) {
+        p->op_flops[ds] = 0.0; p->op_bytes[ds] = 0.0;
+        bool have = false;
+        for (auto& fb : p->fold_bufs) have = have || fb.first == i;
+        if (!have) {
+          void* buf = nullptr;
+          VAD_CUDA_CHECK(cudaMalloc(&buf, 256 * 128 * 2));
+          p->fold_bufs.emplace_back(i, buf);
+        }
+        p->fold_pending = true;
+      }
+    }
+  }
   uint64_t off = 0;
   for (int s = 1; s < p->n_slots; ++s) {
     if (!p->slots[s].defined) continue;
@@ -594,12 +675,18 @@ extern "C" int32_t vad_plan_slot_info(const vad_plan_t* p, int32_t slot, int32_t
   return VAD_OK;
 }
 
-extern "C" int32_t vad_plan_num_launches(const vad_plan_t* p) { return p ? (int32_t)p->ops.size() : 0; }
+extern "C" int32_t vad_plan_num_launches(const vad_plan_t* p) {
+  if (!p) return 0;
+  int32_t n = (int32_t)p->ops.size();
+  if (p->configured)
+    for (const OpRuntime& r : p->rt) n -= r.skip ? 1 : 0;  // ops that run inside a fused launch
+  return n;
+}
 extern "C" double vad_plan_flops(const vad_plan_t* p) { return (p && p->configured) ? p->flops : 0.0; }
 
 // Slot shapes change while the op list runs (slots are reused), so shapes are re-derived here in
 // op order; only pointers and tensor maps are (re)bound.
-static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
+static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) {
   auto slot_ptr = [&](int s) -> uint8_t* {
     return s == 0 ? const_cast<uint8_t*>(static_cast<const uint8_t*>(x)) : static_cast<uint8_t*>(ws) + p->slots[s].offset;
   };
@@ -738,7 +825,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
         q.scale = c.scale; q.shift = c.shift;
         cuuint64_t gdim[4] = {64, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.F};
         cuuint64_t gstr[3] = {128, (cuuint64_t)128 * q.W, (cuuint64_t)128 * q.W * q.H};
-        cuuint32_t box[4] = {64, 8, 18, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)((p->s3_halo || r.tail) ? 10 : 8), 18, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(d.src), gdim, gstr, box, es,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -753,6 +840,56 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(3x3 halo tile) failed: %d", i, (int)cr);
+        if (r.tail) {
+          // fused conv3 (+ downsample): resident 256 x 64 weight tiles; 64 ch x 8 w x 16 h boxes over the 256-channel
+          // residual (tail = 1) or the 64-channel block input X (tail = 2), and over the 256-channel output
+          const vad_op_desc& d3 = p->ops[r.tail_c3];
+          TailParams& t = r.tlp;
+          t.scale2 = c.scale; t.shift2 = c.shift;
+          t.scale3 = reinterpret_cast<const float*>(p->params + d3.scale_off);
+          t.shift3 = reinterpret_cast<const float*>(p->params + d3.shift_off);
+          t.shiftd = nullptr;
+          cuuint32_t es2[2] = {1, 1};
+          cuuint32_t wbox[2] = {64, 256};
+          cuuint32_t cbox[4] = {64, 8, 16, 1};
+          cuuint64_t wide[4] = {256, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.F};
+          cuuint64_t wstr4[3] = {512, (cuuint64_t)512 * q.W, (cuuint64_t)512 * q.W * q.H};
+          cr = p->encode_tiled(&r.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(d3.dst), wide, wstr4, cbox, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cr == CUDA_SUCCESS && r.tail == 1) {
+            cuuint64_t wdim[2] = {64, 256};
+            cuuint64_t wstr[1] = {128};
+            cr = p->encode_tiled(&r.tmW3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d3.w_off), wdim, wstr, wbox, es2,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr == CUDA_SUCCESS)
+              cr = p->encode_tiled(&r.tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(d3.res), wide, wstr4, cbox, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          } else if (cr == CUDA_SUCCESS) {
+            const vad_op_desc& dd = p->ops[r.tail_ds];
+            t.shiftd = reinterpret_cast<const float*>(p->params + dd.shift_off);
+            void* fb = nullptr;
+            for (auto& e : p->fold_bufs) if (e.first == (int)i) fb = e.second;
+            if (!fb) return fail(VAD_ERR_CUDA, "op %zu: folded tail weights were not allocated", i);
+            if (p->fold_pending) {
+              fold_tail_weights_kernel<<<(256 * 128 + 255) / 256, 256, 0, st>>>(
+                  reinterpret_cast<const __nv_bfloat16*>(p->params + d3.w_off), reinterpret_cast<const __nv_bfloat16*>(p->params + dd.w_off),
+                  t.scale3, reinterpret_cast<const float*>(p->params + dd.scale_off), 64, 64, static_cast<__nv_bfloat16*>(fb));
+              if (cudaGetLastError() != cudaSuccess) return fail(VAD_ERR_CUDA, "op %zu: fold_tail_weights_kernel launch failed", i);
+            }
+            cuuint64_t wdim[2] = {128, 256};
+            cuuint64_t wstr[1] = {256};
+            cr = p->encode_tiled(&r.tmW3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fb, wdim, wstr, wbox, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr == CUDA_SUCCESS)
+              cr = p->encode_tiled(&r.tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(dd.src), gdim, gstr, cbox, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          }
+          if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(bottleneck tail) failed: %d", i, (int)cr);
+        }
       } else if (r.thalo) {
         // (C, HW, T, N): one box = 64 channels x P pixels x all T frames of one clip
         ThaloParams& q = r.tp;
@@ -830,6 +967,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws) {
       r.pp.out = reinterpret_cast<__nv_bfloat16*>(slot_ptr(d.dst)) + d.dst_c_off;
     }
   }
+  p->fold_pending = false;
   p->bound_x = x;
   p->bound_ws = ws;
   return VAD_OK;
@@ -950,7 +1088,7 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
     return fail(VAD_ERR_INVALID_ARGUMENT, "x must be 16 B aligned and the workspace 1024 B aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->bound_x != x_dev || p->bound_ws != workspace_dev) {
-    int32_t rc = bind_plan(p, x_dev, workspace_dev);
+    int32_t rc = bind_plan(p, x_dev, workspace_dev, st);
     if (rc != VAD_OK) return rc;
   }
   auto mark = [&]() -> cudaError_t {
@@ -968,8 +1106,21 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
     const vad_op_desc& d = p->ops[i];
     const OpRuntime& r = p->rt[i];
     cudaError_t e = cudaSuccess;
-    if (d.kind == VAD_OP_CONV) {
-      if (r.stem) {
+    if (r.skip) {
+      // ran inside the fused launch of an earlier op
+    } else if (d.kind == VAD_OP_CONV) {
+      if (r.tail) {
+        // RES: <2 halo stages, ring of 3> or <1, 5> (VAD_TAIL_CFG=1) or <1, 4> (=2); DS: <1 halo stage, ring of 2>
+        auto launch_tail = [&](auto kern, int smem) -> cudaError_t {
+          cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+          if (le != cudaSuccess) return le;
+          return launch_k(kern, r.grid, kTailThreads, (size_t)smem, st, g_pdl, 1, r.tmA, r.tmB, r.tmW3, r.tmX, r.tmO, r.tlp);
+        };
+        if (r.tail == 2)            e = launch_tail(conv_tail_kernel<true, 1, 2>, TailCfg<true, 1, 2>::kSmemBytes);
+        else if (p->tail_cfg == 1)  e = launch_tail(conv_tail_kernel<false, 1, 5>, TailCfg<false, 1, 5>::kSmemBytes);
+        else if (p->tail_cfg == 2)  e = launch_tail(conv_tail_kernel<false, 1, 4>, TailCfg<false, 1, 4>::kSmemBytes);
+        else                        e = launch_tail(conv_tail_kernel<false, 2, 3>, TailCfg<false, 2, 3>::kSmemBytes);
+      } else if (r.stem) {
         static bool stem_attr = false;
         if (!stem_attr) {
           e = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1004,9 +1155,14 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
         }
       } else if (r.s3) {
         static bool attr = false;
-        if (!attr) { e = cudaFuncSetAttribute(conv_s3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes); attr = (e == cudaSuccess); }
+        if (!attr) {
+          e = cudaFuncSetAttribute(conv_s3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes);
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_s3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes);
+          attr = (e == cudaSuccess);
+        }
         if (e == cudaSuccess) {
-          e = launch_k(conv_s3x3_kernel, r.grid, kS3Threads, (size_t)kS3SmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmO, r.s3p);
+          if (p->s3_halo) e = launch_k(conv_s3x3_kernel<true>, r.grid, kS3Threads, (size_t)kS3SmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmO, r.s3p);
+          else            e = launch_k(conv_s3x3_kernel<false>, r.grid, kS3Threads, (size_t)kS3SmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmO, r.s3p);
         }
       } else if (r.thalo) {
         const int w_all = r.tp.resident ? 3 * (r.tp.Cin / 64) * r.bn * 128 : 0;

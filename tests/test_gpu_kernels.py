@@ -533,3 +533,94 @@ def test_cta_pair_residual_kernel_matches_the_plain_kernel(cuda_device, case, re
     pair, _ = run_conv_case(*case[1:], True, relu)
     assert_bf16_close(pair, ref)
     assert torch.equal(pair, plain)
+
+
+# ---------------------------------------------------------------------------------- bottleneck-tail fusion (conv_tail.cuh)
+def _tail_plan(mode, B, T, H, W, seed, device):
+    """layer1 bottleneck tail as its own op table: conv2 (1,3,3) 64->64 + BN + ReLU, conv3 1x1x1 64->256 + BN + residual +
+    ReLU; the residual is a 256-channel tensor (mode 'res': produced by an earlier op) or the block's 1x1x1 downsample of
+    the 64-channel block input (mode 'ds': reference src/i3d.py:262-272)."""
+    from anomaly_detection_on_video_b200 import _lib as lib
+    from anomaly_detection_on_video_b200 import engine as eng
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 64, T, H, W, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(64, 64, 1, 3, 3, generator=g) * (2.0 / 576) ** 0.5).to(torch.bfloat16)
+    w3 = (torch.randn(256, 64, 1, 1, 1, generator=g) * (2.0 / 64) ** 0.5).to(torch.bfloat16)
+    wd = (torch.randn(256, 64, 1, 1, 1, generator=g) * (2.0 / 64) ** 0.5).to(torch.bfloat16)
+    sc = [0.5 + torch.rand(c, generator=g) for c in (64, 256, 256)]
+    sh = [0.2 * torch.randn(c, generator=g) for c in (64, 256, 256)]
+    pk = eng.ParamPacker()
+    o2 = pk.add_conv(w2.float(), sc[0], sh[0])
+    o3 = pk.add_conv(w3.float(), sc[1], sh[1])
+    od = pk.add_conv(wd.float(), sc[2], sh[2])
+    C = lib.VAD_OP_CONV
+    one, zero = (1, 1, 1), (0, 0, 0)
+    proj = eng.Op(kind=C, src=0, dst=1, cin=64, cout=256, kernel=one, stride=one, pad=zero, flags=0, w_off=od[0], scale_off=od[1], shift_off=od[2])
+    conv2 = eng.Op(kind=C, src=0, dst=2, cin=64, cout=64, kernel=(1, 3, 3), stride=one, pad=(0, 1, 1), flags=lib.VAD_FLAG_RELU,
+                   w_off=o2[0], scale_off=o2[1], shift_off=o2[2])
+    conv3 = eng.Op(kind=C, src=2, dst=3, res=1, cin=64, cout=256, kernel=one, stride=one, pad=zero, flags=lib.VAD_FLAG_RELU,
+                   w_off=o3[0], scale_off=o3[1], shift_off=o3[2])
+    ops = [proj, conv2, conv3] if mode == "res" else [conv2, proj, conv3]
+    plan = eng.BackbonePlan(ops, pk.blob(), 4, 0, torch.device(device), in_channels=64)
+    xf = x.float()
+    a2 = F.relu(F.conv3d(xf, w2.float(), None, 1, (0, 1, 1)) * sc[0].view(1, -1, 1, 1, 1) + sh[0].view(1, -1, 1, 1, 1)).to(torch.bfloat16).float()
+    r = F.conv3d(xf, wd.float()) * sc[2].view(1, -1, 1, 1, 1) + sh[2].view(1, -1, 1, 1, 1)
+    y = F.relu(F.conv3d(a2, w3.float()) * sc[1].view(1, -1, 1, 1, 1) + sh[1].view(1, -1, 1, 1, 1) + r)
+    return plan, x.permute(0, 2, 3, 4, 1).contiguous().to(device), y
+
+
+TAIL_SHAPES = [(2, 2, 20, 20), (1, 1, 5, 3), (3, 4, 55, 55), (9, 4, 55, 55)]
+
+
+@pytest.mark.parametrize("shape", TAIL_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_bottleneck_tail_residual_fusion_is_bit_identical(cuda_device, shape, monkeypatch):
+    """conv2 -> conv3 + residual in one launch == conv_s3x3 followed by the generic staged-residual conv3, bit for bit
+    (same MMA order per accumulator, same epilogue arithmetic); both within bf16 resolution of fp32 torch."""
+    from gpu_util import assert_bf16_close
+    outs = []
+    for no_tail in ("1", "0"):
+        monkeypatch.setenv("VAD_NO_TAIL", no_tail)
+        plan, x, ref = _tail_plan("res", *shape, seed=3, device=cuda_device)
+        plan.forward(x)
+        assert plan.num_launches == (3 if no_tail == "1" else 2)
+        torch.cuda.synchronize()
+        outs.append(plan.slot_tensor(3).clone())
+    assert torch.equal(outs[0], outs[1])
+    assert_bf16_close(outs[1].float().cpu().permute(0, 4, 1, 2, 3), ref)
+
+
+@pytest.mark.parametrize("shape", TAIL_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_bottleneck_tail_with_folded_downsample(cuda_device, shape, monkeypatch):
+    """First block of layer1: conv2 -> [conv3 | downsample] as one K = 128 contraction with the BN scales folded into
+    bf16 weights.  Not bit-identical to the unfused path (the residual is no longer rounded to bf16, the weights carry
+    the scale): both must sit within bf16 resolution of the fp32 torch result."""
+    from gpu_util import assert_bf16_close
+    errs = []
+    for no_tail in ("1", "0"):
+        monkeypatch.setenv("VAD_NO_TAIL", no_tail)
+        plan, x, ref = _tail_plan("ds", *shape, seed=5, device=cuda_device)
+        plan.forward(x)
+        plan.forward(x)  # second forward: weights already folded, maps bound
+        assert plan.num_launches == (3 if no_tail == "1" else 1)
+        torch.cuda.synchronize()
+        out = plan.slot_tensor(3).float().cpu().permute(0, 4, 1, 2, 3)
+        assert_bf16_close(out, ref)
+        errs.append((out - ref).abs().max().item())
+    assert errs[1] <= 2.0 * errs[0] + 1e-3
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_s3x3_single_halo_box(cuda_device, mode, monkeypatch):
+    """Hardware probe + regression: the (1,3,3) halo-tile kernel with ONE 10 x 18 halo box per tile (UMMA descriptors that
+    start at rows which are not multiples of the 1024-byte swizzle atom, eight-row groups 1280 B apart) against the
+    three-box form.  mode 1: matrix-base-offset field 0; mode 2: base offset = start row & 7."""
+    from gpu_util import run_conv_case
+    case = (64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 3, 55, 55)
+    monkeypatch.setenv("VAD_NO_TAIL", "1")
+    monkeypatch.setenv("VAD_S3_HALO", "0")
+    base, _ = run_conv_case(*case, device=cuda_device)
+    monkeypatch.setenv("VAD_S3_HALO", mode)
+    out, ref = run_conv_case(*case, device=cuda_device)
+    bad = (out != base)
+    print(f"VAD_S3_HALO={mode}: {int(bad.sum())} of {bad.numel()} elements differ; max |d| {float((out - base).abs().max()):.4g}")
+    assert torch.equal(out, base)
