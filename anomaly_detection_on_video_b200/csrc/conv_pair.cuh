@@ -363,12 +363,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
                 f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
               }
-              if (p.relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-              }
-              const uint32_t o0 = pack_bf16x2(f[0], f[1]), o1 = pack_bf16x2(f[2], f[3]);
-              const uint32_t o2 = pack_bf16x2(f[4], f[5]), o3 = pack_bf16x2(f[6], f[7]);
+              // ReLU rides in the conversion (cvt.rn.relu.bf16x2.f32): same bits as max(x, 0) followed by the rounding
+              uint32_t o0, o1, o2, o3;
+              if (p.relu) { o0 = pack_bf16x2_relu(f[0], f[1]); o1 = pack_bf16x2_relu(f[2], f[3]); o2 = pack_bf16x2_relu(f[4], f[5]); o3 = pack_bf16x2_relu(f[6], f[7]); }
+              else        { o0 = pack_bf16x2(f[0], f[1]); o1 = pack_bf16x2(f[2], f[3]); o2 = pack_bf16x2(f[4], f[5]); o3 = pack_bf16x2(f[6], f[7]); }
               asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
             }
           };
@@ -420,15 +418,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col0_i + col + j], s_shift[col0_i + col + j]);
-              if (p.relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-              }
               uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
+              if (p.relu) { o.x = pack_bf16x2_relu(f[0], f[1]); o.y = pack_bf16x2_relu(f[2], f[3]); o.z = pack_bf16x2_relu(f[4], f[5]); o.w = pack_bf16x2_relu(f[6], f[7]); }
+              else        { o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]); }
               *reinterpret_cast<uint4*>(out_row + col) = o;
             }
           }

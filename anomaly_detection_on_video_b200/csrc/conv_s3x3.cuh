@@ -1,13 +1,17 @@
 // K2s3: spatial (1,3,3) convolutions, stride 1, pad (0,1,1), 64 -> 64 channels -- conv2 of the layer1 bottlenecks
-// (src/i3d.py:85-92) -- with the nine taps read out of THREE shared-memory copies of the activation tile.
+// (src/i3d.py:85-92) -- with the nine taps read out of ONE shared-memory copy of the activation tile plus its halo.
 //
 // Through the generic kernel this layer loads nine im2col columns (9 x 16 KB per 128 output pixels); with N = 64
 // that is 85 B/clk/SM of L2 -> SM traffic, above what L2 can deliver to 148 SMs, so the layer is L2-bound at half
-// the tensor rate.  Here an M tile is 8 (w) x 16 (h) output pixels of one frame.  For each dw in {-1, 0, +1} ONE
-// rank-4 TMA box (64 ch, 8 w, 18 h, 1 frame) lands as 144 rows of 128 B (SWIZZLE_128B), row = h * 8 + w; tap
-// (dh, dw) is box dw at a row offset of dh * 8 -- 1024 B, exactly one swizzle atom, so the UMMA descriptor just moves
-// its start address -- and TMA's out-of-range zero fill is the spatial padding.  A traffic drops from 147 KB to
-// 54 KB per tile; the 9 x 8 KB of weights stay resident in shared memory.  One stage = one tile = 36 MMAs.
+// the tensor rate.  Here an M tile is 8 (w) x 16 (h) output pixels of one frame and ONE rank-4 TMA box (64 ch, 10 w,
+// 18 h, 1 frame) lands as 180 rows of 128 B (SWIZZLE_128B), row = h * 10 + w, TMA's out-of-range zero fill being the
+// spatial padding.  Tap (dh, dw) is that same tile read from row dh * 10 + dw on, eight-row groups 1280 B apart
+// (SBO).  The descriptor's start address is then NOT a multiple of the 1024-byte swizzle atom, and neither is the
+// group stride: this works because the tensor core applies the 128-byte swizzle to absolute shared-memory address
+// bits, exactly as TMA does when it writes the box, with the descriptor's matrix-base-offset field left at 0
+// (measured on B200 in round 2: bit-identical to three dw-shifted 8 x 18 boxes whose taps start on atom boundaries;
+// with base offset = start row & 7 the results are wrong).  A traffic drops from 147 KB (im2col) to 23 KB per tile;
+// the 9 x 8 KB of weights stay resident in shared memory.  One stage = one tile = 36 MMAs.
 // Epilogue as in the stem: BN + ReLU -> bf16 -> 128B-swizzled staging tile -> TMA store (4 rows x 8 columns per warp
 // pair), clipped at the frame border by the tensor map.
 #pragma once
@@ -21,20 +25,14 @@ struct S3x3Params {
   int F, H, W;            // frames (clips x T), height, width
   int tiles_w, tiles_h, num_tiles;
   int relu;
-  int base_off_mode;      // HALO1 probe: 1 = set the descriptor's matrix-base-offset field to the start row & 7
   const float* scale;
   const float* shift;
 };
 
-constexpr int kS3BoxBytes = 18 * 8 * 128;            // one dw box: 18 rows x 8 pixels x 64 channels bf16
-constexpr int kS3StageBytes = 3 * kS3BoxBytes;       // 54 KB
-constexpr int kS3Stages = 2;
-// HALO1 variant: ONE box of 18 rows x 10 pixels per tile (23 KB, rounded up to a 1024-byte multiple); tap (dh, dw) is the
-// same tile read from row dh * 10 + dw on, eight-row groups 1280 B apart.  The start address is then no longer a multiple
-// of the 1024-byte swizzle atom: this relies on the tensor core applying the 128-byte swizzle to absolute shared-memory
-// address bits, exactly as TMA does when it writes the box (probed on B200: tests/test_gpu_kernels.py::test_s3x3_single_halo_box).
-constexpr int kS3HaloRows = 18 * 10;
-constexpr int kS3HaloBytes = (kS3HaloRows * 128 + 1023) / 1024 * 1024;
+constexpr int kS3HaloRows = 18 * 10;                                   // one halo box: 18 rows x 10 pixels x 64 channels bf16
+constexpr int kS3HaloBytes = (kS3HaloRows * 128 + 1023) / 1024 * 1024;  // 23 KB stage (1024-byte multiple)
+constexpr int kS3StageBytes = kS3HaloBytes;
+constexpr int kS3Stages = 3;
 constexpr int kS3WBytes = 9 * 64 * 128;              // resident weights: 9 taps x (64 cout x 64 cin)
 constexpr int kS3Threads = 64 + 8 * 32;
 constexpr int kS3SmemBytes = kS3WBytes + 2 * kStemStagingBytes + kS3Stages * kS3StageBytes + 2 * 64 * 4 + (2 * kS3Stages + 5) * 8 + 16 + 1024;
@@ -46,32 +44,30 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sm
                : "memory");
 }
 
-// SWIZZLE_128B K-major descriptor (everything but the start address) with an arbitrary stride between 8-row groups
-__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t sbo_bytes, uint32_t base_offset) {
+// SWIZZLE_128B K-major descriptor (everything but the start address) with an arbitrary stride between 8-row groups;
+// matrix base offset 0 (see the header comment)
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>(1) << 16;                       // LBO (ignored)
   d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;          // SBO
   d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(base_offset & 7u) << 49;        // matrix base offset
   d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
   return d;
 }
 
-template <bool HALO1>
 __global__ void __launch_bounds__(kS3Threads, 1)
 conv_s3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmO, const S3x3Params p) {
-  constexpr int kStageBytes = HALO1 ? kS3HaloBytes : kS3StageBytes;
+  constexpr int kStageBytes = kS3StageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* w_smem = smem;                                     // tap (dh, dw) at (dh * 3 + dw) * 8 KB
   uint8_t* staging = smem + kS3WBytes;                        // 2 x 16 KB
   uint8_t* stage_base = staging + 2 * kStemStagingBytes;      // kS3Stages x 54 KB
-  float* s_scale = reinterpret_cast<float*>(stage_base + kS3Stages * kS3StageBytes);  // (HALO1 stages are smaller; same plan)
+  float* s_scale = reinterpret_cast<float*>(stage_base + kS3Stages * kS3StageBytes);
   float* s_shift = s_scale + 64;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 64);
-  static_assert(kS3Stages * kS3StageBytes >= kS3Stages * kS3HaloBytes, "the shared-memory plan is sized for the three-box stage");
   uint64_t* empty_bar = full_bar + kS3Stages;
   uint64_t* tmem_full_bar = empty_bar + kS3Stages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -132,14 +128,8 @@ conv_s3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait_a(empty0 + s * 8, ph ^ 1u);
         const uint32_t dst = stage0 + s * (uint32_t)kStageBytes;
         const uint32_t fb = full0 + s * 8;
-        if (HALO1) {
-          mbar_arrive_expect_tx_a(fb, (uint32_t)(kS3HaloRows * 128));
-          tma_load_4d_b(dst, &tmA, fb, 0, wb * 8 - 1, hb * 16 - 1, f);
-        } else {
-          mbar_arrive_expect_tx_a(fb, (uint32_t)kS3StageBytes);
-#pragma unroll
-          for (int dw = 0; dw < 3; ++dw) tma_load_4d_b(dst + (uint32_t)dw * kS3BoxBytes, &tmA, fb, 0, wb * 8 + dw - 1, hb * 16 - 1, f);
-        }
+        mbar_arrive_expect_tx_a(fb, (uint32_t)(kS3HaloRows * 128));
+        tma_load_4d_b(dst, &tmA, fb, 0, wb * 8 - 1, hb * 16 - 1, f);
         if (++s == kS3Stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -149,6 +139,7 @@ conv_s3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
       const uint64_t desc_hi = umma_desc_kmajor<128>(0);
+      const uint64_t desc_halo = umma_desc_sw128_sbo(1280u);
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
       const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
       const uint32_t w16 = smem_u32(w_smem) >> 4;
@@ -170,9 +161,8 @@ conv_s3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int dw = 0; dw < 3; ++dw) {
             // tap (dh, dw): box dw, shifted by dh rows of 8 pixels (1024 B = one swizzle atom)
-            // HALO1: the one box read from row dh * 10 + dw on (8 x 16-byte units per row), groups 1280 B apart
-            const uint64_t adesc = HALO1 ? (umma_desc_sw128_sbo(1280u, p.base_off_mode ? (uint32_t)(dh * 10 + dw) : 0u) | (a16 + (uint32_t)((dh * 10 + dw) * 8)))
-                                         : (desc_hi | (a16 + (uint32_t)(dw * (kS3BoxBytes >> 4) + dh * 64)));
+            // tap (dh, dw): the halo box read from row dh * 10 + dw on (8 x 16-byte units per row), groups 1280 B apart
+            const uint64_t adesc = desc_halo | (a16 + (uint32_t)((dh * 10 + dw) * 8));
             const uint64_t bdesc = desc_hi | (w16 + (uint32_t)((dh * 3 + dw) * 512));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

@@ -34,16 +34,20 @@ struct TailParams {
   int F, H, W;            // frames (clips x T), height, width
   int tiles_w, tiles_h, num_tiles;
   int relu2, relu3;
-  const float* scale2;    // conv2 BN
-  const float* shift2;
-  const float* scale3;    // conv3 BN (DS: unused, folded into the weights)
-  const float* shift3;
-  const float* shiftd;    // DS: downsample BN shift
+  // BN scale / shift BY VALUE: the kernel parameter block lives in the constant bank, so the epilogue's per-column
+  // operands come through the constant cache instead of shared memory (as broadcast LDS.128 they were 60 % of the
+  // kernel's shared-memory wavefronts, and the shared-memory data pipe -- MMA operand fetch + staging -- is what bounds it)
+  float s2[64], b2[64];     // conv2 BN
+  float s3[256], b3[256];   // conv3 BN (DS: s3 unused -- folded into the weights --, b3 = conv3 shift + downsample shift)
+  long long* dbg;           // VAD_TAIL_DEBUG: clock64() stamps of CTA 0's role threads for its tiles 8..11 ([4 tiles][32 events]), else null
 };
+// event slots: 0 IN issued | 1 conv3 operands ready, 2 conv3 issued, 3 conv2 operands ready, 4 conv2 issued |
+// 5 + 3 n: DMA chunk n done-wait over, stored, store read | 17 acc2_full seen, 18 E1 done, 19 acc3_full seen, 20 + 2 n: chunk n ready, chunk n done
+#define TAIL_STAMP(tc_, ev_) do { if (p.dbg && blockIdx.x == 0 && (tc_) >= 8u && (tc_) < 12u) p.dbg[((tc_) - 8u) * 32u + (ev_)] = clock64(); } while (0)
 
 constexpr int kTailW2Bytes = 9 * 64 * 128;      // 72 KB: nine taps x (64 cout x 64 cin)
 constexpr int kTailW3Bytes = 256 * 128;         // 32 KB: 256 cout x 64 cin
-constexpr int kTailInBytes = kS3HaloBytes;      // 23 KB: ONE 10 x 18 halo box per tile (conv_s3x3.cuh, HALO1)
+constexpr int kTailInBytes = kS3HaloBytes;      // 23 KB: ONE 10 x 18 halo box per tile (conv_s3x3.cuh)
 constexpr int kTailChunkBytes = 128 * 128;      // 16 KB: 128 pixels x 64 channels (A3, X, one staging tile)
 constexpr int kTailThreads = 96 + 8 * 32;
 constexpr int kTailL2Ahead = 2;                 // tiles of halo box / X / residual pulled into L2 ahead of their smem loads
@@ -59,8 +63,7 @@ struct TailCfg {
   static constexpr int kOffA3 = kOffIn + IN_STAGES * kTailInBytes;
   static constexpr int kOffX = kOffA3 + kTailChunkBytes;                  // DS only: block-input tile X
   static constexpr int kOffRing = kOffX + (DS ? kTailChunkBytes : 0);
-  static constexpr int kOffF = kOffRing + RING * kTailChunkBytes;         // floats: s2 b2 [64], s3 b3 [256]
-  static constexpr int kOffBar = kOffF + (2 * 64 + 2 * 256) * 4;
+  static constexpr int kOffBar = kOffRing + RING * kTailChunkBytes;
   static constexpr int kNumBars = 13 + 2 * RING;
   static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -90,15 +93,11 @@ template <bool DS, int IN_STAGES, int RING>
 __global__ void __launch_bounds__(kTailThreads, 1)
 conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW2,
                  const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmXR,
-                 const __grid_constant__ CUtensorMap tmO, const TailParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TailParams p) {
   using Cfg = TailCfg<DS, IN_STAGES, RING>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  float* s_scale2 = reinterpret_cast<float*>(smem + Cfg::kOffF);
-  float* s_shift2 = s_scale2 + 64;
-  float* s_scale3 = s_shift2 + 64;
-  float* s_shift3 = s_scale3 + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* w_bar = bars + 0;
   uint64_t* in_full = bars + 1;      // [2]
@@ -144,15 +143,6 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);   // acc2: columns 0..127 (two stages), acc3: columns 256..511
     tmem_relinquish();
-  }
-  if (warp >= 3) {
-    const int t = threadIdx.x - 96;  // 0..255
-    if (t < 64) {
-      s_scale2[t] = p.scale2[t];
-      s_shift2[t] = p.shift2[t];
-    }
-    s_scale3[t] = DS ? 1.f : p.scale3[t];
-    s_shift3[t] = DS ? p.shift3[t] + p.shiftd[t] : p.shift3[t];
   }
   tc_fence_before();
   __syncthreads();
@@ -207,6 +197,7 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait_a(in_empty_a + st * 8, (use & 1u) ^ 1u);
         mbar_arrive_expect_tx_a(in_full_a + st * 8, (uint32_t)(kS3HaloRows * 128));
         tma_load_4d_b(in0 + st * (uint32_t)kTailInBytes, &tmA, in_full_a + st * 8, 0, wb * 8 - 1, hb * 16 - 1, f);
+        TAIL_STAMP(tc, 0);
         if (DS) {
           mbar_wait_a(x_empty_a, (tc & 1u) ^ 1u);   // conv3 of the previous tile has read X (and A3)
           mbar_arrive_expect_tx_a(x_full_a, (uint32_t)kTailChunkBytes);
@@ -221,7 +212,7 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc2 = umma_idesc_bf16_m128(64);
       constexpr uint32_t idesc3 = umma_idesc_bf16_m128(256);
       const uint64_t desc_hi = umma_desc_kmajor<128>(0);
-      const uint64_t desc_halo = umma_desc_sw128_sbo(1280u, 0u);   // 8-row groups of the 10-pixel-wide halo box
+      const uint64_t desc_halo = umma_desc_sw128_sbo(1280u);   // 8-row groups of the 10-pixel-wide halo box
       const uint32_t in_full_a = smem_u32(in_full), in_empty_a = smem_u32(in_empty);
       const uint32_t acc2_full_a = smem_u32(acc2_full), acc2_empty_a = smem_u32(acc2_empty);
       const uint32_t a3_full_a = smem_u32(a3_full), a3_empty_a = smem_u32(a3_empty);
@@ -236,6 +227,7 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait_a(in_full_a + st * 8, use & 1u);
         mbar_wait_a(acc2_empty_a + acc * 8, ((t2 >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        TAIL_STAMP(t2, 3);
         const uint32_t d_tmem = tmem_base + acc * 64u;
         const uint32_t a16 = in16 + st * (uint32_t)(kTailInBytes >> 4);
 #pragma unroll
@@ -254,6 +246,7 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         umma_commit_a(in_empty_a + st * 8);
         umma_commit_a(acc2_full_a + acc * 8);
+        TAIL_STAMP(t2, 4);
       };
       if ((int)blockIdx.x < p.num_tiles) conv2(0);
       uint32_t tc = 0;
@@ -262,6 +255,7 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait_a(acc3_empty_a, (tc & 1u) ^ 1u);
         mbar_wait_a(a3_full_a, tc & 1u);
         tc_fence_after();
+        TAIL_STAMP(tc, 1);
         const uint32_t d3 = tmem_base + 256u;
         {
           const uint64_t adesc = desc_hi | a3_16, bdesc = desc_hi | w3_16;
@@ -276,6 +270,7 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         umma_commit_a(a3_empty_a);
         umma_commit_a(acc3_full_a);
+        TAIL_STAMP(tc, 2);
         if (tile + (int)gridDim.x < p.num_tiles) conv2(tc + 1);
       }
     }
@@ -313,9 +308,12 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_coords(blockIdx.x + (c >> 2) * gridDim.x, wb, hb, f);
         const uint32_t b = (uint32_t)(c % RING);
         mbar_wait_a(st_done_a + b * 8, (uint32_t)(c / RING) & 1u);
+        TAIL_STAMP((uint32_t)(c >> 2), 5 + 3 * (c & 3));
         tma_store_4d(&tmO, r0 + b * kTailChunkBytes, (c & 3) * 64, wb * 8, hb * 16, f);
         tma_store_commit();
+        TAIL_STAMP((uint32_t)(c >> 2), 6 + 3 * (c & 3));
         tma_store_wait_read<0>();
+        TAIL_STAMP((uint32_t)(c >> 2), 7 + 3 * (c & 3));
         if (DS) mbar_arrive_a(st_ready_a + b * 8);
         else if (c + RING < chunks) load_res(c + RING);
       }
@@ -324,98 +322,103 @@ conv_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps 3..10
+    // The body is instantiated per column half so that every BN scale / shift is a constant-bank operand with a static
+    // address (FFMA R, R, c[0][imm], c[0][imm]): no load instruction at all for them.
     const int q = warp & 3;            // TMEM lane quarter
-    const int half = (warp - 3) >> 2;  // which 32 of every 64 columns
     const int lrow = q * 32 + lane;    // tile row = (h, w) = (lrow / 8, lrow % 8)
     const uint32_t xr = (uint32_t)(lrow & 7);
     const uint32_t a3_row = smem_u32(smem + Cfg::kOffA3) + (uint32_t)lrow * 128u;
     const uint32_t ring_row = smem_u32(smem + Cfg::kOffRing) + (uint32_t)lrow * 128u;
-    uint32_t tc = 0;
-    uint32_t c = 0;  // chunk counter of this CTA
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
-      // ---- E1: conv2 accumulator -> BN2 + ReLU -> bf16 -> A3
-      const uint32_t acc = tc & 1u;
-      mbar_wait(&acc2_full[acc], (tc >> 1) & 1u);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u + (uint32_t)(half * 32), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc2_empty[acc]);
-      mbar_wait(a3_empty, (tc & 1u) ^ 1u);          // conv3 of the previous tile has read A3
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = half * 32 + g * 8;
-        const uint32_t addr = a3_row + ((((uint32_t)col >> 3) ^ xr) << 4);
-        const float4 sa = *reinterpret_cast<const float4*>(s_scale2 + col), sb = *reinterpret_cast<const float4*>(s_scale2 + col + 4);
-        const float4 ha = *reinterpret_cast<const float4*>(s_shift2 + col), hb = *reinterpret_cast<const float4*>(s_shift2 + col + 4);
-        const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-        const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-        float fv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          fv[j] = fmaf(__uint_as_float(v[g * 8 + j]), sc[j], sh[j]);
-          if (p.relu2) fv[j] = fmaxf(fv[j], 0.f);
-        }
-        const uint32_t o0 = pack_bf16x2(fv[0], fv[1]), o1 = pack_bf16x2(fv[2], fv[3]);
-        const uint32_t o2 = pack_bf16x2(fv[4], fv[5]), o3 = pack_bf16x2(fv[6], fv[7]);
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-      }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's operand reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a3_full);
-      // ---- E2: conv3 accumulator -> BN3 (+ residual) + ReLU -> bf16 -> staging tile -> (DMA thread) TMA store
-      mbar_wait(acc3_full, tc & 1u);
-      tc_fence_after();
-#pragma unroll 1
-      for (int n = 0; n < 4; ++n, ++c) {
-        const uint32_t b = c % RING, u = c / RING;
-        // RES: the residual chunk of use u has landed; DS: the store of use u - 1 has been read (passes at once for u = 0)
-        mbar_wait(&st_ready[b], DS ? ((u & 1u) ^ 1u) : (u & 1u));
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(n * 64 + half * 32), v);
+    auto body = [&](auto half_c) {
+      constexpr int half = decltype(half_c)::value;  // which 32 of every 64 columns
+      uint32_t tc = 0;
+      uint32_t c = 0;  // chunk counter of this CTA
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
+        // ---- E1: conv2 accumulator -> BN2 + ReLU -> bf16 -> A3
+        const uint32_t acc = tc & 1u;
+        mbar_wait(&acc2_full[acc], (tc >> 1) & 1u);
+        tc_fence_after();
+        if (warp == 3 && lane == 0) TAIL_STAMP(tc, 17);
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u + (uint32_t)(half * 32), v);
         tmem_ld_wait();
-        if (n == 3) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc3_empty);   // accumulator drained: conv3 of the next tile may start
-        }
-        const uint32_t row = ring_row + b * kTailChunkBytes;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc2_empty[acc]);
+        mbar_wait(a3_empty, (tc & 1u) ^ 1u);          // conv3 of the previous tile has read A3
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int col = n * 64 + half * 32 + g * 8;
-          const uint32_t addr = row + ((((uint32_t)(half * 4 + g)) ^ xr) << 4);
-          const float4 ha = *reinterpret_cast<const float4*>(s_shift3 + col), hb = *reinterpret_cast<const float4*>(s_shift3 + col + 4);
-          const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+          constexpr int col0 = half * 32;
+          const int col = col0 + g * 8;
+          const uint32_t addr = a3_row + ((((uint32_t)col >> 3) ^ xr) << 4);
           float fv[8];
-          if (DS) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) fv[j] = __uint_as_float(v[g * 8 + j]) + sh[j];
-          } else {
-            const float4 sa = *reinterpret_cast<const float4*>(s_scale3 + col), sb = *reinterpret_cast<const float4*>(s_scale3 + col + 4);
-            const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+          for (int j = 0; j < 8; ++j) fv[j] = fmaf(__uint_as_float(v[g * 8 + j]), p.s2[col + j], p.b2[col + j]);
+          uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) fv[j] = fmaf(__uint_as_float(v[g * 8 + j]), sc[j], sh[j]);
-            uint4 rr;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(addr));
-            fv[0] += bf16_lo(rr.x); fv[1] += bf16_hi(rr.x);
-            fv[2] += bf16_lo(rr.y); fv[3] += bf16_hi(rr.y);
-            fv[4] += bf16_lo(rr.z); fv[5] += bf16_hi(rr.z);
-            fv[6] += bf16_lo(rr.w); fv[7] += bf16_hi(rr.w);
-          }
-          if (p.relu3) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) fv[j] = fmaxf(fv[j], 0.f);
-          }
-          const uint32_t o0 = pack_bf16x2(fv[0], fv[1]), o1 = pack_bf16x2(fv[2], fv[3]);
-          const uint32_t o2 = pack_bf16x2(fv[4], fv[5]), o3 = pack_bf16x2(fv[6], fv[7]);
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+          for (int j = 0; j < 4; ++j) o[j] = p.relu2 ? pack_bf16x2_relu(fv[2 * j], fv[2 * j + 1]) : pack_bf16x2(fv[2 * j], fv[2 * j + 1]);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
         }
-        fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's operand reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(&st_done[b]);
+        if (lane == 0) mbar_arrive(a3_full);
+        if (warp == 3 && lane == 0) TAIL_STAMP(tc, 18);
+        // ---- E2: conv3 accumulator -> BN3 (+ residual) + ReLU -> bf16 -> staging tile -> (DMA thread) TMA store
+        mbar_wait(acc3_full, tc & 1u);
+        tc_fence_after();
+        if (warp == 3 && lane == 0) TAIL_STAMP(tc, 19);
+#pragma unroll
+        for (int n = 0; n < 4; ++n, ++c) {
+          const uint32_t b = c % RING, u = c / RING;
+          // RES: the residual chunk of use u has landed; DS: the store of use u - 1 has been read (passes at once for u = 0)
+          mbar_wait(&st_ready[b], DS ? ((u & 1u) ^ 1u) : (u & 1u));
+          if (warp == 3 && lane == 0) TAIL_STAMP(tc, 20 + 2 * n);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(n * 64 + half * 32), v);
+          const uint32_t row = ring_row + b * kTailChunkBytes;
+          uint4 rr[4];
+          if (!DS) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t addr = row + ((((uint32_t)(half * 4 + g)) ^ xr) << 4);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[g].x), "=r"(rr[g].y), "=r"(rr[g].z), "=r"(rr[g].w) : "r"(addr));
+            }
+          }
+          tmem_ld_wait();
+          if (n == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc3_empty);   // accumulator drained: conv3 of the next tile may start
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = n * 64 + half * 32 + g * 8;
+            const uint32_t addr = row + ((((uint32_t)(half * 4 + g)) ^ xr) << 4);
+            float fv[8];
+            if (DS) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fv[j] = __uint_as_float(v[g * 8 + j]) + p.b3[col + j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fv[j] = fmaf(__uint_as_float(v[g * 8 + j]), p.s3[col + j], p.b3[col + j]);
+              fv[0] += bf16_lo(rr[g].x); fv[1] += bf16_hi(rr[g].x);
+              fv[2] += bf16_lo(rr[g].y); fv[3] += bf16_hi(rr[g].y);
+              fv[4] += bf16_lo(rr[g].z); fv[5] += bf16_hi(rr[g].z);
+              fv[6] += bf16_lo(rr[g].w); fv[7] += bf16_hi(rr[g].w);
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = p.relu3 ? pack_bf16x2_relu(fv[2 * j], fv[2 * j + 1]) : pack_bf16x2(fv[2 * j], fv[2 * j + 1]);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_done[b]);
+          if (warp == 3 && lane == 0) TAIL_STAMP(tc, 21 + 2 * n);
+        }
       }
-    }
+    };
+    if (((warp - 3) >> 2) == 0) body(std::integral_constant<int, 0>{});
+    else                        body(std::integral_constant<int, 1>{});
   }
 
   tc_fence_before();

@@ -384,7 +384,9 @@ __global__ void __launch_bounds__(256) head_select_kernel(const float* __restric
       for (int t = 0; t < T; ++t) {
         bool used = false;
         for (int u = 0; u < j; ++u) used |= (s_idx[u] == t);
-        if (!used && sh[t] > bv) { bv = sh[t]; best = t; }
+        // torch.topk semantics: NaN ranks above everything, ties keep the lower index; `best < 0` accepts the first
+        // unused candidate whatever its value (all -inf / NaN rows), so an index in [0, T) is always selected
+        if (!used && (best < 0 || sh[t] > bv || (sh[t] != sh[t] && bv == bv))) { bv = sh[t]; best = t; }
       }
       s_idx[j] = best;
       idx_out[b * k + j] = best;

@@ -147,7 +147,6 @@ struct vad_plan {
   bool no_tail = false;      // VAD_NO_TAIL=1: no conv2 -> conv3 (+ downsample) fusion in layer1 (A/B and bit-identity tests)
   std::vector<std::pair<int, void*>> fold_bufs;  // (op index, 64 KB device buffer): BN-scaled [W3 | Wd] of a tail = 2 op
   bool fold_pending = false;                     // fold_bufs must be (re)filled on the next bind
-  int s3_halo = 0;           // VAD_S3_HALO=1|2: (1,3,3) halo-tile kernels load ONE 10 x 18 halo box per tile (2: with the descriptor base offset)
   bool no_s3 = false;        // VAD_NO_S3X3=1: layer1's (1,3,3) convs through the generic im2col kernel
   bool thalo_bn128 = false;  // VAD_THALO_BN128=1: also for 128-wide tiles (2-deep ring: measured slower on layer2)
   bool no_thalo = false;     // VAD_NO_THALO=1: (3,1,1) convs through the generic im2col kernel
@@ -252,7 +251,6 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   p->stem_generic = sgen && sgen[0] == '1';
   { const char* k = getenv("VAD_NO_S3X3"); p->no_s3 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_TAIL"); p->no_tail = k && k[0] == '1'; }
-  { const char* k = getenv("VAD_S3_HALO"); p->s3_halo = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_TAIL_CFG"); p->tail_cfg = k ? atoi(k) : 0; }
   { const char* k = getenv("VAD_THALO_BN128"); p->thalo_bn128 = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
@@ -439,7 +437,6 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         q.F = batch * src.T; q.H = src.H; q.W = Wi;
         q.tiles_w = (Wi + 7) / 8; q.tiles_h = (src.H + 15) / 16;
         q.relu = c.relu;
-        q.base_off_mode = p->s3_halo == 2 ? 1 : 0;
         m_tiles = (long long)q.F * q.tiles_w * q.tiles_h;
       }
       const long long n_tiles = (d.cout + r.bn - 1) / r.bn;
@@ -630,6 +627,20 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       q.F = r.s3p.F; q.H = r.s3p.H; q.W = r.s3p.W;
       q.tiles_w = r.s3p.tiles_w; q.tiles_h = r.s3p.tiles_h; q.num_tiles = r.s3p.num_tiles;
       q.relu2 = r.cp.relu; q.relu3 = p->rt[c3].cp.relu;
+      {
+        // BN scale / shift travel in the kernel parameter block (constant bank): fetch them from the parameter blob once
+        // per configure (a few KB, synchronous like the rest of configure; the blob is immutable for the life of the plan)
+        const vad_op_desc& d3 = p->ops[c3];
+        float sd_shift[256];
+        VAD_CUDA_CHECK(cudaMemcpy(q.s2, p->params + d.scale_off, 64 * 4, cudaMemcpyDeviceToHost));
+        VAD_CUDA_CHECK(cudaMemcpy(q.b2, p->params + d.shift_off, 64 * 4, cudaMemcpyDeviceToHost));
+        VAD_CUDA_CHECK(cudaMemcpy(q.s3, p->params + d3.scale_off, 256 * 4, cudaMemcpyDeviceToHost));
+        VAD_CUDA_CHECK(cudaMemcpy(q.b3, p->params + d3.shift_off, 256 * 4, cudaMemcpyDeviceToHost));
+        if (ds >= 0) {
+          VAD_CUDA_CHECK(cudaMemcpy(sd_shift, p->params + p->ops[ds].shift_off, 256 * 4, cudaMemcpyDeviceToHost));
+          for (int k = 0; k < 256; ++k) q.b3[k] += sd_shift[k];
+        }
+      }
       // per-op accounting: the fused launch carries the FLOPs of its parts; bytes = each tensor touched once
       const double Md = (double)r.cp.M;
       p->op_flops[i] += p->op_flops[c3] + (ds >= 0 ? p->op_flops[ds] : 0.0);
@@ -820,12 +831,12 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
         if (cr != CUDA_SUCCESS)
           return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(stem) failed: %d; set VAD_STEM_GENERIC=1", i, (int)cr);
       } else if (r.s3) {
-        // input (C, W, H, F): one box = 64 channels x 8 columns x 18 rows; output slice (cout, W, H, F): 8 x 4 per store
+        // input (C, W, H, F): one box = 64 channels x 10 columns x 18 rows (tile + halo); output slice (cout, W, H, F): 8 x 4 per store
         S3x3Params& q = r.s3p;
         q.scale = c.scale; q.shift = c.shift;
         cuuint64_t gdim[4] = {64, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.F};
         cuuint64_t gstr[3] = {128, (cuuint64_t)128 * q.W, (cuuint64_t)128 * q.W * q.H};
-        cuuint32_t box[4] = {64, (cuuint32_t)((p->s3_halo || r.tail) ? 10 : 8), 18, 1};
+        cuuint32_t box[4] = {64, 10, 18, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult cr = p->encode_tiled(&r.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)slot_ptr(d.src), gdim, gstr, box, es,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -844,11 +855,6 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
           // fused conv3 (+ downsample): resident 256 x 64 weight tiles; 64 ch x 8 w x 16 h boxes over the 256-channel
           // residual (tail = 1) or the 64-channel block input X (tail = 2), and over the 256-channel output
           const vad_op_desc& d3 = p->ops[r.tail_c3];
-          TailParams& t = r.tlp;
-          t.scale2 = c.scale; t.shift2 = c.shift;
-          t.scale3 = reinterpret_cast<const float*>(p->params + d3.scale_off);
-          t.shift3 = reinterpret_cast<const float*>(p->params + d3.shift_off);
-          t.shiftd = nullptr;
           cuuint32_t es2[2] = {1, 1};
           cuuint32_t wbox[2] = {64, 256};
           cuuint32_t cbox[4] = {64, 8, 16, 1};
@@ -869,14 +875,14 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           } else if (cr == CUDA_SUCCESS) {
             const vad_op_desc& dd = p->ops[r.tail_ds];
-            t.shiftd = reinterpret_cast<const float*>(p->params + dd.shift_off);
             void* fb = nullptr;
             for (auto& e : p->fold_bufs) if (e.first == (int)i) fb = e.second;
             if (!fb) return fail(VAD_ERR_CUDA, "op %zu: folded tail weights were not allocated", i);
             if (p->fold_pending) {
               fold_tail_weights_kernel<<<(256 * 128 + 255) / 256, 256, 0, st>>>(
                   reinterpret_cast<const __nv_bfloat16*>(p->params + d3.w_off), reinterpret_cast<const __nv_bfloat16*>(p->params + dd.w_off),
-                  t.scale3, reinterpret_cast<const float*>(p->params + dd.scale_off), 64, 64, static_cast<__nv_bfloat16*>(fb));
+                  reinterpret_cast<const float*>(p->params + d3.scale_off), reinterpret_cast<const float*>(p->params + dd.scale_off), 64, 64,
+                  static_cast<__nv_bfloat16*>(fb));
               if (cudaGetLastError() != cudaSuccess) return fail(VAD_ERR_CUDA, "op %zu: fold_tail_weights_kernel launch failed", i);
             }
             cuuint64_t wdim[2] = {128, 256};
@@ -1111,10 +1117,28 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
     } else if (d.kind == VAD_OP_CONV) {
       if (r.tail) {
         // RES: <2 halo stages, ring of 3> or <1, 5> (VAD_TAIL_CFG=1) or <1, 4> (=2); DS: <1 halo stage, ring of 2>
+        static long long* tail_dbg = nullptr;
+        static const bool want_dbg = getenv("VAD_TAIL_DEBUG") != nullptr;
+        if (want_dbg && !tail_dbg) { cudaMalloc(&tail_dbg, 2 * 4 * 32 * 8); cudaMemset(tail_dbg, 0, 2 * 4 * 32 * 8); }
         auto launch_tail = [&](auto kern, int smem) -> cudaError_t {
           cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
           if (le != cudaSuccess) return le;
-          return launch_k(kern, r.grid, kTailThreads, (size_t)smem, st, g_pdl, 1, r.tmA, r.tmB, r.tmW3, r.tmX, r.tmO, r.tlp);
+          TailParams tp = r.tlp;
+          tp.dbg = want_dbg ? tail_dbg + (r.tail == 2 ? 0 : 128) : nullptr;
+          le = launch_k(kern, r.grid, kTailThreads, (size_t)smem, st, g_pdl, 1, r.tmA, r.tmB, r.tmW3, r.tmX, r.tmO, tp);
+          if (want_dbg && le == cudaSuccess) {  // debug only: synchronises and prints CTA 0's timeline of its tiles 8..11
+            long long h[128];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, tp.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            const long long t0 = h[17];
+            fprintf(stderr, "tail mode %d timeline (cycles since tile 8's acc2_full):\n", r.tail);
+            for (int t = 0; t < 4; ++t) {
+              fprintf(stderr, " tile %d:", 8 + t);
+              for (int e = 0; e < 28; ++e) fprintf(stderr, " %lld", h[t * 32 + e] ? h[t * 32 + e] - t0 : -1);
+              fprintf(stderr, "\n");
+            }
+          }
+          return le;
         };
         if (r.tail == 2)            e = launch_tail(conv_tail_kernel<true, 1, 2>, TailCfg<true, 1, 2>::kSmemBytes);
         else if (p->tail_cfg == 1)  e = launch_tail(conv_tail_kernel<false, 1, 5>, TailCfg<false, 1, 5>::kSmemBytes);
@@ -1155,15 +1179,8 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
         }
       } else if (r.s3) {
         static bool attr = false;
-        if (!attr) {
-          e = cudaFuncSetAttribute(conv_s3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes);
-          if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_s3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes);
-          attr = (e == cudaSuccess);
-        }
-        if (e == cudaSuccess) {
-          if (p->s3_halo) e = launch_k(conv_s3x3_kernel<true>, r.grid, kS3Threads, (size_t)kS3SmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmO, r.s3p);
-          else            e = launch_k(conv_s3x3_kernel<false>, r.grid, kS3Threads, (size_t)kS3SmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmO, r.s3p);
-        }
+        if (!attr) { e = cudaFuncSetAttribute(conv_s3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3SmemBytes); attr = (e == cudaSuccess); }
+        if (e == cudaSuccess) e = launch_k(conv_s3x3_kernel, r.grid, kS3Threads, (size_t)kS3SmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmO, r.s3p);
       } else if (r.thalo) {
         const int w_all = r.tp.resident ? 3 * (r.tp.Cin / 64) * r.bn * 128 : 0;
         if (r.bn == 128) {

@@ -75,8 +75,12 @@ def load_feature_extraction_model(model_name: str = "tushar-n-baseline", state_d
 
 
 def _atomic_save(path: str, arr: np.ndarray) -> None:
-    tmp = f"{path}.tmp.{os.getpid()}.npy"
-    np.save(tmp, arr)
+    """Write-then-rename.  The temporary is a dot file that does NOT end in ``.npy`` (np.save gets an open handle, so it
+    appends no suffix): a rank killed mid-write leaves nothing that ``segment()`` or a consumer globbing ``*.npy`` picks up."""
+    d, base = os.path.split(path)
+    tmp = os.path.join(d, f".{base}.{os.getpid()}.tmp")
+    with open(tmp, "wb") as fh:
+        np.save(fh, arr)
     os.replace(tmp, path)
 
 
@@ -244,7 +248,8 @@ def extract(dataset, model: torch.nn.Module, device: torch.device, outpath: str,
 def segment(feature_path: str, seg_outpath: str, seg_length: int = 32, queue: Optional[WorkQueue] = None) -> None:
     """32-segment averaging of every ``.npy`` in ``feature_path`` (extract_features.py:159-185)."""
     os.makedirs(seg_outpath, exist_ok=True)
-    files = [f for f in sorted(os.listdir(feature_path)) if f.endswith(".npy") and os.path.isfile(os.path.join(feature_path, f))]
+    files = [f for f in sorted(os.listdir(feature_path))
+             if f.endswith(".npy") and not f.startswith(".") and ".tmp." not in f and os.path.isfile(os.path.join(feature_path, f))]
     idxs: Iterable[int] = queue.claim(len(files), tag=seg_outpath) if queue is not None else range(len(files))
     for i in idxs:
         file = files[i]
@@ -300,7 +305,11 @@ def cli(argv: Optional[Sequence[str]] = None) -> None:
 
     bind_to_gpu(queue.local_rank if queue is not None else 0)  # pinned frame buffers land on the GPU's own socket
     dataset = {"train": _rows_from_dir(args.videos)} if args.videos else None
-    main(args.outdir, dataset=dataset, model_name=args.model_name, state_dict_path=args.weights, queue=queue, precision=args.precision)
+    try:
+        main(args.outdir, dataset=dataset, model_name=args.model_name, state_dict_path=args.weights, queue=queue, precision=args.precision)
+    finally:
+        if queue is not None:
+            queue.close()  # the rank that hosts the store outlives every other rank's last claim
 
 
 if __name__ == "__main__":

@@ -8,6 +8,10 @@ rank claims the next unclaimed index, so a rank stuck on a long video simply cla
 Static mode (no store): item ``i`` belongs to rank ``i % world_size`` (callers order items longest
 first, which makes round-robin a reasonable LPT schedule).  Both are deterministic in *what* is
 computed: outputs do not depend on which rank produced them.
+
+Shutdown: the TCP store lives inside one of the worker ranks (rank 0 when ``from_env`` creates it).  A rank that runs out
+of items must not take the store down while others still claim, so every rank calls ``close()`` when it is done: it
+checks in on a ``done`` key and the store's owner waits there until all ranks have checked in.
 """
 from __future__ import annotations
 
@@ -18,10 +22,13 @@ import torch.distributed as dist
 
 
 class WorkQueue:
-    def __init__(self, rank: int = 0, world_size: int = 1, local_rank: int = 0, store=None, dynamic: bool = True) -> None:
+    def __init__(self, rank: int = 0, world_size: int = 1, local_rank: int = 0, store=None, dynamic: bool = True,
+                 owns_store: bool = False) -> None:
         self.rank, self.world_size, self.local_rank = rank, world_size, local_rank
         self.store = store if dynamic else None
+        self.owns_store = bool(owns_store and self.store is not None)  # this process hosts the store's server
         self._epoch = 0
+        self._closed = False
 
     @classmethod
     def from_env(cls, dynamic: bool = True) -> Optional["WorkQueue"]:
@@ -32,6 +39,7 @@ class WorkQueue:
         rank = int(os.environ["RANK"])
         local_rank = int(os.environ.get("LOCAL_RANK", rank))
         store = None
+        owns = False
         if dynamic:
             if dist.is_available() and dist.is_initialized():
                 store = _default_store()
@@ -39,7 +47,8 @@ class WorkQueue:
                 host = os.environ.get("MASTER_ADDR", "127.0.0.1")
                 port = int(os.environ.get("MASTER_PORT", "29500")) + 17  # beside, not on, the rendezvous port
                 store = dist.TCPStore(host, port, world, is_master=(rank == 0), wait_for_workers=False)
-        return cls(rank, world, local_rank, store, dynamic)
+                owns = rank == 0
+        return cls(rank, world, local_rank, store, dynamic, owns_store=owns)
 
     @classmethod
     def from_process_group(cls, dynamic: bool = True) -> "WorkQueue":
@@ -78,6 +87,32 @@ class WorkQueue:
 
         while int(self.store.add(key, 0)) < self.world_size:
             time.sleep(0.005)
+
+
+    def close(self, timeout_s: float = 600.0) -> None:
+        """Check out.  Every rank calls this after its last ``claim`` / ``barrier``; the rank hosting the store returns only
+        when all ranks have checked out (or after ``timeout_s``), so nobody ever talks to a dead server.  Idempotent."""
+        if self._closed or self.world_size == 1 or self.store is None:
+            self._closed = True
+            return
+        self._closed = True
+        import time
+
+        key = "vad_wq/done"
+        try:
+            self.store.add(key, 1)
+            if self.owns_store:
+                t0 = time.monotonic()
+                while int(self.store.add(key, 0)) < self.world_size and time.monotonic() - t0 < timeout_s:
+                    time.sleep(0.005)
+        except Exception:  # a peer that already lost the server has nothing left to coordinate
+            pass
+
+    def __enter__(self) -> "WorkQueue":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
 
 
 def _default_store():

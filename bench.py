@@ -14,11 +14,16 @@ JSON keys beyond the base contract:
   value     clip-crops/s with the uint8 frames already resident in HBM
   e2e       same metric through the public API (TenCropVideoFrameDataset + extract_clip_features) from
             pinned HOST frames, H2D of the frames and D2H of the features inside the timed region
-  roofline  the tcgen05 conv kernel family: useful conv FLOPs / summed conv-kernel time, measured with
-            CUDA events around every launch inside the timed region, vs the measured bf16 peak
-  cpu_baseline  the reference's fp32 PyTorch forward (oracle port: same ATen ops, the reference source
-            itself cannot travel to the GPU box) timed on the host cores on a bounded sample
-`--impl reference` times that CPU path alone and prints the same line with "impl": "reference".
+  roofline  the WHOLE step against the tensor roofline: all conv FLOPs of the step (32.83 GFLOP per clip-crop) / the
+            device time of the K timed steps (preprocessing, pools, segment mean included), vs the measured sustained
+            bf16 peak; `per_kernel` underneath lists every layer group from a separate fully event-bracketed pass
+            (tensor fraction AND algorithmic-HBM fraction of each, the stem and the HBM-bound layer1 tail among them)
+  sustained the same step repeated for >= 10 s (power-capped clocks settle), reported beside the K-step `value`
+  smooth_video  the same step on a smooth (sinusoid + noise) video, SURVEY 8(d) config 2's second input
+  cpu_baseline  the reference's CPU path (PIL / torchvision preprocessing as src/gtransforms.py runs it + the fp32
+            I3Res50 forward, oracle port: the reference source itself cannot travel to the GPU box) timed on the host
+            cores on a bounded sample; `parity` = GPU features of the bench's own first clip vs that fp32 forward
+`--impl reference` times that CPU path alone and prints the same line (same `config`) with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -50,33 +55,75 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def bench_config(cpb: int, world: int) -> dict:
+    """The workload description both arms print (BASELINE.json configs[1])."""
+    return {"workload": WORKLOAD, "frames": N_FRAMES, "frame_hw": [SRC_H, SRC_W], "clips_per_video": CLIPS,
+            "crops": CROPS, "clips_per_batch": cpb, "videos_per_step_per_gpu": 1, "parallelism": f"dp{world}",
+            "flop_per_clip": FLOP_PER_CLIP, "weights": "random init under a fixed seed (constructor init, perturbed BatchNorm statistics)",
+            "cache": "inputs larger than L2 (461 MB of frames, >4 GB of activations per batch; no flush needed)"}
+
+
+def synthetic_frames(n: int, seed: int, kind: str = "noise"):
+    """[n, 240, 320, 3] uint8.  'noise': i.i.d. uniform bytes (maximises the +-1 LSB sensitivity of the resize);
+    'smooth': moving sinusoid gratings + mild noise (SURVEY 8(d) config 2's second variant, closer to real video)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, size=(n, SRC_H, SRC_W, 3), dtype=np.uint8)
+    t = np.arange(n, dtype=np.float32)[:, None, None, None]
+    y = np.arange(SRC_H, dtype=np.float32)[None, :, None, None]
+    x = np.arange(SRC_W, dtype=np.float32)[None, None, :, None]
+    ph = np.asarray([0.0, 2.1, 4.2], dtype=np.float32)[None, None, None, :]
+    out = np.empty((n, SRC_H, SRC_W, 3), dtype=np.uint8)
+    for lo in range(0, n, 100):   # bounded temporaries
+        tt = t[lo:lo + 100]
+        v = 127.5 + 70.0 * np.sin(0.031 * x + 0.017 * y + 0.05 * tt + ph) + 40.0 * np.sin(0.011 * x - 0.023 * y - 0.02 * tt + 1.3 * ph)
+        v += rng.normal(0.0, 4.0, size=v.shape).astype(np.float32)
+        out[lo:lo + 100] = np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    return out
+
+
 # ------------------------------------------------------------------------------------------ CPU arms
-def cpu_reference_run(steps: int, warmup: int, clips_per_step: int = 4):
-    """The reference's CPU path for this metric: I3Res50 fp32 forward, 10 serial per-crop forwards of a
-    batch of clips (extract_features.py:85-89), all host threads.  Returns (clips/s, details)."""
+def cpu_reference_run(steps: int, warmup: int, clips_per_step: int = 4, state_dict=None):
+    """The reference's CPU path for this metric on a bounded sample of the workload: per step `clips_per_step` clips of
+    the synthetic video go through the reference's transform chain (PIL resize / ten-crop / PILToTensor / per-channel
+    standardisation loops, src/gtransforms.py:9-73 via oracle.preprocess_pil) and then through 10 serial per-crop fp32
+    I3Res50 forwards of that batch (extract_features.py:83-89), all host threads.  Returns (clips/s, details)."""
     import torch
 
     from oracle import i3res50 as O
+    from oracle import preprocess_pil as Q
 
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = O.seeded_state_dict(0)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(clips_per_step, CROPS, 3, 16, 224, 224, generator=g).clamp_(-2.0, 2.4444)
+    sd = state_dict if state_dict is not None else O.seeded_state_dict(0)
+    n_clips = clips_per_step * (steps + warmup)
+    frames = synthetic_frames(min(N_FRAMES, 16 * n_clips), 1000)
+    images = Q.to_pil_list(frames)
+    tf = Q.RefClipTransform()
+    avail = len(images) // 16
+    t_pre = [0.0]
 
-    def step():
-        for c in range(CROPS):
-            O.forward(x[:, c], sd)
+    def step(i):
+        t0 = time.perf_counter()
+        batch = torch.stack([Q.clip_tensor_pil(images, (i * clips_per_step + j) % avail, tf) for j in range(clips_per_step)])
+        batch = batch.permute(0, 1, 3, 2, 4, 5)          # (B, 10, 3, 16, 224, 224), extract_features.py:83
+        t_pre[0] += time.perf_counter() - t0
+        with torch.no_grad():
+            for c in range(CROPS):
+                O.forward(batch[:, c], sd)
 
-    for _ in range(warmup):
-        step()
+    for i in range(warmup):
+        step(i)
+    t_pre[0] = 0.0
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
+    for i in range(steps):
+        step(warmup + i)
     dt = time.perf_counter() - t0
     units = steps * clips_per_step * CROPS
-    return units / dt, {"cores": torch.get_num_threads(), "seconds": dt, "clip_crops": units,
-                        "sample": f"{steps} steps x ({clips_per_step} clips x {CROPS} crops) fp32 I3Res50 forwards, "
-                                  f"batch {clips_per_step} per crop index like extract_features.py:85-89; preprocessing excluded"}
+    return units / dt, {"cores": torch.get_num_threads(), "seconds": dt, "clip_crops": units, "preprocess_seconds": t_pre[0],
+                        "sample": f"{steps} steps x ({clips_per_step} clips of the 2,000-frame video x {CROPS} crops): PIL/torchvision "
+                                  f"transform chain (src/gtransforms.py) + fp32 I3Res50 forwards, batch {clips_per_step} per crop index "
+                                  f"like extract_features.py:83-89"}
 
 
 def reference_arm(args):
@@ -84,18 +131,43 @@ def reference_arm(args):
     if rank != 0:
         return
     steps = max(1, args.steps)
+    # bounded: a step is 1 clip (10 clip-crop forwards, ~0.5 s on 16 cores) when many steps are asked for
     value, d = cpu_reference_run(steps, max(1, min(args.warmup, 1)), clips_per_step=1 if steps > 8 else 2)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": d["seconds"] / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU reference path (oracle port of src/i3d.py I3Res50.forward, fp32, "
-                                                 "oneDNN); each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": d["sample"]},
+        "config": bench_config(args.clips_per_batch, max(1, args.gpus)),
+        "note": "CPU reference path (the reference's PIL/torchvision preprocessing + oracle port of src/i3d.py I3Res50.forward, "
+                "fp32, oneDNN); each step is a bounded sample of the workload (cpu_baseline.sample)",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": d["sample"],
+                         "preprocess_share": d["preprocess_seconds"] / d["seconds"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def parity_stats(got, want) -> dict:
+    """Feature-parity statistics of `got` against the fp32 reference features `want` ([n, C] arrays): the vector-scale
+    metrics the tests gate on (north_star: 1e-2 / cosine 0.999 for bf16) and the floored element-wise relative error
+    |a - b| / max(|b|, 1e-3 max|b|) that SURVEY section 7 proposes, which bf16-stored activations cannot hold to 1e-2."""
+    import numpy as np
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    out = {"max_norm_err": 0.0, "rel_l2": 0.0, "cosine_min": 1.0, "elem_floored_max": 0.0, "elem_floored_p99": 0.0, "elem_frac_gt_1e-2": 0.0}
+    el = []
+    for a, b in zip(got, want):
+        mx = np.abs(b).max()
+        out["max_norm_err"] = max(out["max_norm_err"], float(np.abs(a - b).max() / mx))
+        out["rel_l2"] = max(out["rel_l2"], float(np.linalg.norm(a - b) / np.linalg.norm(b)))
+        out["cosine_min"] = min(out["cosine_min"], float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b))))
+        el.append(np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * mx))
+    el = np.concatenate(el)
+    out["elem_floored_max"] = float(el.max())
+    out["elem_floored_p99"] = float(np.quantile(el, 0.99))
+    out["elem_frac_gt_1e-2"] = float((el > 1e-2).mean())
+    return out
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -151,7 +223,10 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=160,
+                    help="timed steps (one 2,000-frame video each, ~60 ms); the default keeps the timed region at ~10 s")
+    ap.add_argument("--sustain-seconds", type=float, default=10.0,
+                    help="length of the extra sustained run reported as `sustained` when the K timed steps are shorter than this")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--clips-per-batch", type=int, default=16,
@@ -221,8 +296,7 @@ def main():
     model = seeded(I3Res50(), 1)
     model.eval().to(dev)
 
-    rng = np.random.default_rng(1000 + rank)
-    frames_host = torch.from_numpy(rng.integers(0, 256, size=(N_FRAMES, SRC_H, SRC_W, 3), dtype=np.uint8)).pin_memory()
+    frames_host = torch.from_numpy(synthetic_frames(N_FRAMES, 1000 + rank, "noise")).pin_memory()
     frames_dev = frames_host.to(dev)
     ds = TenCropVideoFrameDataset(frames_dev, device=dev)
     assert len(ds) == CLIPS
@@ -296,6 +370,49 @@ def main():
         prof_stem = plan.profile_end()
     except RuntimeError:
         prof_stem = []
+    # ---- sustained: the same resident step for >= --sustain-seconds (settled, power-capped clocks), own clock samples
+    sustained = None
+    if ms / 1e3 >= args.sustain_seconds:
+        sustained = {"seconds": ms / 1e3, "steps": K, "value": world * K * CLIPS * CROPS / (ms / 1e3), "note": "the timed region itself"}
+    elif args.sustain_seconds > 0:
+        n_s = max(K, int(args.sustain_seconds / (ms / K / 1e3)) + 1)
+        s_sampler = ClockSampler(local_rank)
+        if rank == 0:
+            s_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        for _ in range(n_s):
+            step_resident()
+        s1.record()
+        barrier()
+        ms_s = s0.elapsed_time(s1)
+        if world > 1:
+            ts = torch.tensor([ms_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            ms_s = float(ts[0])
+        sustained = {"seconds": ms_s / 1e3, "steps": n_s, "value": world * n_s * CLIPS * CROPS / (ms_s / 1e3),
+                     "clocks": s_sampler.stop() if rank == 0 else None}
+
+    # ---- the smooth (sinusoid + noise) video of SURVEY 8(d) config 2: same step, other pixel statistics
+    smooth = None
+    if rank == 0 and os.environ.get("VAD_BENCH_NO_SMOOTH") != "1":
+        fs = torch.from_numpy(synthetic_frames(N_FRAMES, 2000, "smooth")).to(dev)
+        ds_noise, ds = ds, TenCropVideoFrameDataset(fs, device=dev)
+        for _ in range(2):
+            step_resident()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_q = min(K, 10)
+        q0.record()
+        for _ in range(n_q):
+            seg_smooth = step_resident()
+        q1.record()
+        torch.cuda.synchronize(dev)
+        smooth = {"value": n_q * CLIPS * CROPS / (q0.elapsed_time(q1) / 1e3), "unit": UNIT, "steps": n_q, "n_gpus": 1,
+                  "segment_abs_mean": float(seg_smooth.abs().mean())}
+        ds = ds_noise
+        del fs
+    launches["n"] = 0
     prof = []
     if os.environ.get("VAD_BENCH_NO_PROFILE") != "1":
         plan = model.plan(dev)
@@ -441,58 +558,81 @@ def main():
         conv_ms = sum(p["ms"] for p in conv)
         conv_flops = sum(p["flops"] for p in conv)
         all_ms = sum(p["ms"] for p in prof) or 1.0
-        roofline = None
+        tflops_step = value * FLOP_PER_CLIP / 1e12 / world   # per GPU: every conv FLOP of the step / the whole step time
+        # per-kernel table (separate, fully event-bracketed pass of the same K steps): one row per layer group, each with
+        # its tensor fraction AND its algorithmic-HBM fraction, so an HBM-bound layer shows as such
+        def group_of(name):
+            if name == "conv1":
+                return "stem conv1 5x7x7/2 (+BN+ReLU+temporal max-pool)  [stem_umma_mf_kernel]"
+            if name.startswith("maxpool") or name == "avgpool":
+                return name
+            layer, _, rest = name.partition(".")
+            return f"{layer}.*.{rest.split('.', 1)[1]}" if "." in rest else name
+        groups = {}
+        for q in prof:
+            if not q["calls"] or q["ms"] <= 0:
+                continue
+            gname = group_of(q["name"])
+            a = groups.setdefault(gname, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            a["ms"] += q["ms"]; a["flops"] += q["flops"]; a["bytes"] += q["bytes"]; a["launches"] += q["calls"]
+        per_kernel = []
+        for gname, a in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+            tf = a["flops"] / (a["ms"] / 1e3) / 1e12
+            gb = a["bytes"] / (a["ms"] / 1e3) / 1e9
+            per_kernel.append({"layers": gname, "share_of_backbone_time": a["ms"] / all_ms, "ms_per_launch": a["ms"] / a["launches"],
+                               "launches": a["launches"], "tflops": tf, "frac_tensor_sustained": tf / peaks["bf16_sustained"],
+                               "hbm_gbs_algorithmic": gb, "frac_hbm": gb / peaks["hbm_gbs"]})
         family = None
         if conv_ms > 0:
             achieved = conv_flops / (conv_ms / 1e3) / 1e12
-            top = sorted(conv, key=lambda p: -p["ms"])[:6]
-            family = {
-                "bound": "tensor", "kernel": "stem_umma_kernel + conv_umma_kernel (53 launches per forward, aggregated)",
-                "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "frac_of_burst": achieved / peaks["bf16_burst"],
-                "conv_share_of_backbone_time": conv_ms / all_ms,
-                "launches_timed": int(sum(p["calls"] for p in conv)),
-                "top_layers": [{"name": p["name"], "ms_per_launch": p["ms"] / p["calls"],
-                                "tflops": p["flops"] / (p["ms"] / 1e3) / 1e12} for p in top],
-                "whole_step_frac_of_sustained": value * FLOP_PER_CLIP / 1e12 / peaks["bf16_sustained"] / world,
-            }
-            # the dominant single kernel: the stem (conv1), ~22% of the step.  Algorithmic FLOPs per launch =
-            # 9.443 GFLOP per clip-crop (4.721 GMAC) x the clip-crops of the launch; duration =
-            # CUDA events around every launch of it inside the timed region.
-            stem = [p for p in prof_stem if p["name"] == "conv1" and p["calls"]]
-            if stem:
-                st = stem[0]
-                s_ach = st["flops"] / (st["ms"] / 1e3) / 1e12
-                traffic = None
-                tpath = os.path.join(ROOT, "profiles", "stem_dram_traffic.json")
-                if os.path.exists(tpath):
-                    traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-                roofline = {
-                    "bound": "tensor", "kernel": "stem_umma_mf_kernel (conv1 5x7x7/2 + BN + ReLU + temporal max-pool)",
-                    "achieved": s_ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": s_ach / peaks["bf16_sustained"], "frac_of_burst": s_ach / peaks["bf16_burst"],
-                    "traffic": traffic,
-                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step); burst {peaks['bf16_burst']}",
-                    "avg_launch_ms": st["ms"] / st["calls"], "launches_timed": int(st["calls"]),
-                    "flops_per_launch_avg": st["flops"] / st["calls"],
-                    "share_of_backbone_time": st["ms"] / all_ms,
-                    "note": "useful FLOPs (K = 735); the tensor core executes K = 1120 (8 px x 4 ch windows) as N = 128/192 "
-                            "MMAs that feed 2-3 output frames from one input frame",
-                }
+            family = {"bound": "tensor", "kernel": "all conv launches of a forward (stem + 52 conv ops), event-bracketed pass",
+                      "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                      "frac": achieved / peaks["bf16_sustained"], "frac_of_burst": achieved / peaks["bf16_burst"],
+                      "conv_share_of_backbone_time": conv_ms / all_ms, "launches_timed": int(sum(p["calls"] for p in conv))}
+        stem = [q for q in prof_stem if q["name"] == "conv1" and q["calls"]]
+        # `roofline`: the whole step.  The path is 53 tensor-bound conv launches (96 % of the step) plus HBM-bound
+        # preprocessing / pools; no single launch dominates (the largest, the stem, is ~19 %), so the number that is
+        # graded is all conv FLOPs over the device time of the K timed steps -- everything else counts against it.
+        roofline = {
+            "bound": "tensor", "kernel": "whole step: preprocess + stem + 52 conv ops + pools + segment mean (conv FLOPs / step time)",
+            "achieved": tflops_step, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": tflops_step / peaks["bf16_sustained"], "frac_of_burst": tflops_step / peaks["bf16_burst"],
+            "traffic": None,
+            "peak_source": f"{peaks['source']} bf16 sustained (kernels timed inside a long step); burst {peaks['bf16_burst']}",
+            "flops_per_step": CLIPS * CROPS * FLOP_PER_CLIP, "avg_step_ms": ms / K,
+            "traffic_note": "per-kernel DRAM bytes of this build: profiles/ (ncu --set full captures); not a constant copied into the line",
+            "stem_in_timed_region": ({"avg_launch_ms": stem[0]["ms"] / stem[0]["calls"], "launches_timed": int(stem[0]["calls"]),
+                                      "tflops": stem[0]["flops"] / (stem[0]["ms"] / 1e3) / 1e12,
+                                      "frac": stem[0]["flops"] / (stem[0]["ms"] / 1e3) / 1e12 / peaks["bf16_sustained"]} if stem else None),
+            "per_kernel": per_kernel,
+        }
         cpu_baseline = None
         if not args.no_cpu_baseline:
             os.sched_setaffinity(0, cpus_at_start)  # the CPU baseline gets every core the box allows
-            v, d = cpu_reference_run(steps=8, warmup=1, clips_per_step=4)  # ~12 s of CPU work
+            v, d = cpu_reference_run(steps=6, warmup=1, clips_per_step=4)  # ~15-25 s of CPU work
             cpu_baseline = {"value": v, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": d["sample"],
-                            "seconds": d["seconds"]}
+                            "seconds": d["seconds"], "preprocess_share": d["preprocess_seconds"] / d["seconds"]}
+            # parity of THIS build on the bench's own data: clip 0 of the timed video, crops 0..2, GPU features against the
+            # fp32 CPU forward (the checker) of the bit-exact preprocessed clip, with the bench model's weights
+            try:
+                from oracle import i3res50 as O
+                from oracle import preprocess as P
+                clip0 = P.clip_tensor(frames_host[:16].numpy(), 0)[:3]                      # (3, 16, 3, 224, 224)
+                sd_cpu = {k: t.detach().cpu() for k, t in model.state_dict().items()}
+                with torch.no_grad():
+                    want, _ = O.forward(torch.from_numpy(clip0).permute(0, 2, 1, 3, 4).contiguous(), sd_cpu)
+                got = extract_clip_features(TenCropVideoFrameDataset(frames_dev[:16], device=dev), model, dev, strict_compat=False)
+                cpu_baseline["parity"] = parity_stats(got[0, :3], want.reshape(3, -1).numpy())
+                cpu_baseline["parity"]["note"] = ("bf16 operands + bf16-stored activations, fp32 accumulate; gate (tests): max_norm_err <= 1e-2, "
+                                                  "cosine >= 0.999; the floored element-wise statistic is reported, bounded in "
+                                                  "tests/test_gpu_backbone.py, and is what bf16 storage costs on near-zero features")
+            except Exception as exc:
+                cpu_baseline["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames": N_FRAMES, "frame_hw": [SRC_H, SRC_W], "clips_per_video": CLIPS,
-                       "crops": CROPS, "clips_per_batch": cpb, "videos_per_step_per_gpu": 1, "parallelism": f"dp{world}",
-                       "flop_per_clip": FLOP_PER_CLIP, "weights": "random init under a fixed seed (constructor init, perturbed BatchNorm statistics)",
-                       "cache": "inputs larger than L2 (461 MB of frames, >4 GB of activations per batch; no flush needed)"},
+            "config": bench_config(cpb, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames_host.numel()),
                     "d2h_bytes_per_step": int(f_host.numel() * 4 + s_host.numel() * 4), "ms_per_step": ms_e2e / K,
                     "wall_ms_per_step": wall_e2e / K,
@@ -504,6 +644,8 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "roofline_conv_family": family,
+            "sustained": sustained,
+            "smooth_video": smooth,
             "cpu_baseline": cpu_baseline,
             "head": head_info,
             "inception": inception_info,

@@ -5,7 +5,11 @@ Tolerance (bf16 operands + bf16 stored activations, fp32 accumulate; BASELINE.js
 "1e-2 max relative error and cosine >= 0.999"): relative error is measured against the feature
 vector's scale -- max|a-b| <= 1e-2 * max|b| and ||a-b|| <= 1e-2 * ||b|| per clip -- because
 post-ReLU pooled features contain values arbitrarily close to 0 for which an elementwise ratio is
-meaningless; the elementwise statistic is printed for the record.
+meaningless.  The literal element-wise reading of north_star, floored as SURVEY section 7 proposes --
+|a-b| / max(|b|, 1e-3 max|b|) -- is NOT held to 1e-2 by any pipeline that stores activations in bf16 (the
+oracle's own bf16 emulation shows the same gap on the CPU): it is measured here, printed, and pinned by the
+regression bounds ELEM_* below so that it cannot silently get worse; the TF32 mode (tests/test_gpu_tf32.py)
+is the mode that holds 1e-3.
 """
 import os
 
@@ -21,6 +25,10 @@ pytestmark = pytest.mark.gpu
 MAX_NORM_TOL = 1e-2
 REL_L2_TOL = 1e-2
 COS_MIN = 0.999
+# floored element-wise relative error (see the module docstring): regression bounds, ~1.5x what a B200 measures
+ELEM_P99_MAX = 0.25
+ELEM_FRAC_GT_1E2_MAX = 0.35
+ELEM_MAX_MAX = 2.0
 
 
 def check_features(got: np.ndarray, want: np.ndarray):
@@ -30,8 +38,12 @@ def check_features(got: np.ndarray, want: np.ndarray):
         max_norm = np.abs(a - r).max() / np.abs(r).max()
         rel_l2 = np.linalg.norm(a - r) / np.linalg.norm(r)
         cos = float(a @ r / (np.linalg.norm(a) * np.linalg.norm(r)))
-        print(f"clip {b}: max-normalised err {max_norm:.2e}, rel L2 {rel_l2:.2e}, cos {cos:.6f}")
+        el = np.abs(a - r) / np.maximum(np.abs(r), 1e-3 * np.abs(r).max())
+        el_max, el_p99, el_frac = float(el.max()), float(np.quantile(el, 0.99)), float((el > 1e-2).mean())
+        print(f"clip {b}: max-normalised err {max_norm:.2e}, rel L2 {rel_l2:.2e}, cos {cos:.6f}; floored element-wise: "
+              f"max {el_max:.3f}, p99 {el_p99:.3f}, fraction > 1e-2 {el_frac:.3f}")
         assert max_norm <= MAX_NORM_TOL and rel_l2 <= REL_L2_TOL and cos >= COS_MIN
+        assert el_p99 <= ELEM_P99_MAX and el_frac <= ELEM_FRAC_GT_1E2_MAX and el_max <= ELEM_MAX_MAX
 
 
 @pytest.fixture(scope="module")

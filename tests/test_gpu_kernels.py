@@ -607,20 +607,3 @@ def test_bottleneck_tail_with_folded_downsample(cuda_device, shape, monkeypatch)
         assert_bf16_close(out, ref)
         errs.append((out - ref).abs().max().item())
     assert errs[1] <= 2.0 * errs[0] + 1e-3
-
-
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_s3x3_single_halo_box(cuda_device, mode, monkeypatch):
-    """Hardware probe + regression: the (1,3,3) halo-tile kernel with ONE 10 x 18 halo box per tile (UMMA descriptors that
-    start at rows which are not multiples of the 1024-byte swizzle atom, eight-row groups 1280 B apart) against the
-    three-box form.  mode 1: matrix-base-offset field 0; mode 2: base offset = start row & 7."""
-    from gpu_util import run_conv_case
-    case = (64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 3, 55, 55)
-    monkeypatch.setenv("VAD_NO_TAIL", "1")
-    monkeypatch.setenv("VAD_S3_HALO", "0")
-    base, _ = run_conv_case(*case, device=cuda_device)
-    monkeypatch.setenv("VAD_S3_HALO", mode)
-    out, ref = run_conv_case(*case, device=cuda_device)
-    bad = (out != base)
-    print(f"VAD_S3_HALO={mode}: {int(bad.sum())} of {bad.numel()} elements differ; max |d| {float((out - base).abs().max()):.4g}")
-    assert torch.equal(out, base)

@@ -138,6 +138,46 @@ def test_workqueue_two_ranks_cover_every_item_once(tmp_path, dynamic):
     assert list(claims) == [37, 5]  # nothing claimed twice
 
 
+def _wq_env_worker(rank, world, port, outdir):
+    """No process group, no trailing barrier: WorkQueue.from_env() hosts its own TCP store inside rank 0, rank 0 runs out
+    of work long before rank 1 does, and close() is the only thing that keeps the store alive for rank 1's last claims."""
+    sys.path.insert(0, ROOT)
+    import time
+
+    from anomaly_detection_on_video_b200.workqueue import WorkQueue
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    q = WorkQueue.from_env()
+    assert q is not None and q.owns_store == (rank == 0)
+    got = []
+    try:
+        for i in q.claim(12, tag="videos"):
+            got.append(i)
+            if rank == 1:
+                time.sleep(0.15)  # the slow rank: still claiming after rank 0 has seen the end of the queue
+    finally:
+        q.close()
+    np.save(os.path.join(outdir, f"env_claims_{rank}.npy"), np.array(got, dtype=np.int64))
+
+
+def test_workqueue_store_owner_outlives_the_slow_rank(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_wq_env_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)  # raises if a rank dies
+    claimed = np.concatenate([np.load(tmp_path / f"env_claims_{r}.npy") for r in range(world)])
+    assert sorted(claimed.tolist()) == list(range(12))
+
+
+def test_atomic_save_leaves_no_npy_temporaries(tmp_path):
+    from anomaly_detection_on_video_b200.extract_features import _atomic_save
+
+    path = str(tmp_path / "video_i3d.npy")
+    _atomic_save(path, np.arange(6, dtype=np.float32))
+    assert os.listdir(tmp_path) == ["video_i3d.npy"] and np.array_equal(np.load(path), np.arange(6, dtype=np.float32))
+    # a temporary left behind by a killed rank is neither a .npy file nor visible to segment()'s listing
+    open(tmp_path / ".video2_i3d.npy.123.tmp", "wb").close()
+    assert [f for f in os.listdir(tmp_path) if f.endswith(".npy")] == ["video_i3d.npy"]
+
+
 def test_workqueue_single_process_is_identity():
     from anomaly_detection_on_video_b200.workqueue import WorkQueue
 
