@@ -32,6 +32,14 @@ EXPORTED_SYMBOLS = (
     "vad_plan_profile_select",
     "vad_plan_profile_end",
     "vad_plan_destroy",
+    "vad_head_train_create",
+    "vad_head_train_param_floats",
+    "vad_head_train_bn_floats",
+    "vad_head_train_workspace_bytes",
+    "vad_head_train_step",
+    "vad_head_train_num_launches",
+    "vad_head_train_destroy",
+    "vad_adam_step",
     "vad_ingest_ncthw_f32",
     "vad_preproc_create",
     "vad_preproc_info",
@@ -192,6 +200,24 @@ def load() -> ctypes.CDLL:
     lib.vad_head_flops.argtypes = [c_void_p, c_int32, c_int32]
     lib.vad_head_destroy.restype = None
     lib.vad_head_destroy.argtypes = [c_void_p]
+    lib.vad_head_train_create.restype = c_int32
+    lib.vad_head_train_create.argtypes = [POINTER(c_void_p), POINTER(HeadConfig), c_int32]
+    lib.vad_head_train_param_floats.restype = c_uint64
+    lib.vad_head_train_param_floats.argtypes = [c_void_p]
+    lib.vad_head_train_bn_floats.restype = c_uint64
+    lib.vad_head_train_bn_floats.argtypes = [c_void_p]
+    lib.vad_head_train_workspace_bytes.restype = c_int32
+    lib.vad_head_train_workspace_bytes.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(c_uint64)]
+    lib.vad_head_train_step.restype = c_int32
+    lib.vad_head_train_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                        c_void_p, POINTER(c_float), c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.vad_head_train_num_launches.restype = c_int32
+    lib.vad_head_train_num_launches.argtypes = [c_void_p]
+    lib.vad_head_train_destroy.restype = None
+    lib.vad_head_train_destroy.argtypes = [c_void_p]
+    lib.vad_adam_step.restype = c_int32
+    lib.vad_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_float, c_float, c_float, c_float, c_float,
+                                  c_int32, c_float, c_void_p]
     if lib.vad_abi_version() != 1:
         raise RuntimeError(f"{LIB_PATH}: ABI version {lib.vad_abi_version()} != 1; rebuild the library")
     _lib = lib

@@ -171,8 +171,9 @@ extern "C" double vad_head_flops(const vad_head_t* h, int32_t n_seq, int32_t t) 
 }
 
 // out[S*T, N] = act(conv1d_taps(A)[S*T, taps*Cin] . W[N, taps*Cin]^T + bias) (+ res)
+// (ldo / ldr: row pitches of out / res in floats, 0 = N;  the weight matrix is [N][taps * Cin])
 static int32_t head_gemm(vad_head* h, const float* A, int S, int T, int Cin, int taps, const float* W, int N, const float* bias,
-                         bool gelu, const float* res, float* out, cudaStream_t st) {
+                         bool gelu, const float* res, float* out, cudaStream_t st, int ldo = 0, int ldr = 0) {
   if (Cin % kHeadBK || N % 64) return fail(VAD_ERR_INVALID_ARGUMENT, "head gemm: Cin %% 32 / N %% 64 (Cin=%d, N=%d)", Cin, N);
   HeadGemmParams q;
   memset(&q, 0, sizeof(q));
@@ -181,7 +182,7 @@ static int32_t head_gemm(vad_head* h, const float* A, int S, int T, int Cin, int
   q.Sb = 128 / q.Tb;
   q.t_tiles = (T + q.Tb - 1) / q.Tb;
   q.N = N; q.Cin = Cin; q.taps = taps; q.gelu = gelu ? 1 : 0;
-  q.ldo = N; q.ldr = N; q.bias = bias; q.res = res; q.out = out;
+  q.ldo = ldo ? ldo : N; q.ldr = ldr ? ldr : N; q.bias = bias; q.res = res; q.out = out;
   const int bn = (N % 128 == 0) ? 128 : 64;
   CUtensorMap tmA, tmB;
   {

@@ -409,7 +409,8 @@ __global__ void __launch_bounds__(256) head_select_kernel(const float* __restric
 __global__ void __launch_bounds__(256) head_loss_kernel(const float* __restrict__ scores, const float* __restrict__ vid_score,
                                                         const float* __restrict__ labels, const float* __restrict__ sel_n,
                                                         const float* __restrict__ sel_a, int nn, int ncrops, int T, int C, int k,
-                                                        float* __restrict__ l1, float* __restrict__ out) {
+                                                        float* __restrict__ l1, float* __restrict__ out, float w_smooth = 8e-4f,
+                                                        float w_sparse = 8e-3f, float alpha = 0.001f, float margin = 200.f) {
   __shared__ float red[256];
   auto block_sum = [&](float v) -> float {
     red[threadIdx.x] = v;
@@ -438,10 +439,10 @@ __global__ void __launch_bounds__(256) head_loss_kernel(const float* __restrict_
     const float d = scores[b * T + t + 1] - scores[b * T + t];
     v = fmaf(d, d, v);
   }
-  const float smooth = 8e-4f * block_sum(v);
+  const float smooth = w_smooth * block_sum(v);
   v = 0.f;
   for (int e = threadIdx.x; e < nn * T; e += blockDim.x) v = fmaf(scores[e], scores[e], v);
-  const float sparsity = 8e-3f * sqrtf(block_sum(v));
+  const float sparsity = w_sparse * sqrtf(block_sum(v));
   v = 0.f;
   for (int e = threadIdx.x; e < bs; e += blockDim.x) {
     const float pr = vid_score[e], y = labels[e];
@@ -449,7 +450,6 @@ __global__ void __launch_bounds__(256) head_loss_kernel(const float* __restrict_
     v -= y * fmaxf(logf(pr), -100.f) + (1.f - y) * fmaxf(logf(1.f - pr), -100.f);
   }
   const float bce = block_sum(v) / (float)bs;
-  const float margin = 200.f;
   auto dist = [&](const float* a, const float* b) {  // torch.pairwise_distance: || a - b + 1e-6 ||_2 over k
     float s = 0.f;
     for (int j = 0; j < k; ++j) { const float d = a[j] - b[j] + 1e-6f; s = fmaf(d, d, s); }
@@ -472,7 +472,6 @@ __global__ void __launch_bounds__(256) head_loss_kernel(const float* __restrict_
   for (int e = threadIdx.x; e < (sep < rest ? sep : rest); e += blockDim.x) { const float d = dist(la + (sep + e) * k, la + e * k); v = fmaf(d, d, v); }
   const float con_a = block_sum(v) / (float)(sep < rest ? sep : rest);
   if (threadIdx.x == 0) {
-    const float alpha = 0.001f;
     const float mg = bce + alpha * (alpha * con + con_a + con_n);
     out[0] = mg + smooth + sparsity;
     out[1] = smooth; out[2] = sparsity; out[3] = bce; out[4] = con; out[5] = con_n; out[6] = con_a;

@@ -1486,6 +1486,7 @@ extern "C" int32_t vad_add_magnitude(const float* feats_dev, int64_t rows, int32
 
 // ------------------------------------------------------------------------------------ MGFN scoring head
 #include "head_api.cuh"
+#include "head_train_api.cuh"
 
 // ------------------------------------------------------------------------------------ TF32 precision mode
 #include "tf32_api.cuh"

@@ -257,6 +257,47 @@ double vad_head_flops(const vad_head_t* head, int32_t n_seq, int32_t t);
 void vad_head_destroy(vad_head_t* head);
 
 /* ------------------------------------------------------------------------------------------------
+ * MGFN training step: replaces MGFNRunner.training_step + loss.backward() + the Adam step Lightning drives from
+ * configure_optimizers (src/runner.py:29-39,53-59) over MGFNForVideoAnomalyDetection.forward in train() mode
+ * (modeling_mgfn.py:302-427: BatchNorm1d on batch statistics, dropout on the magnitude-selection mask) and the losses
+ * of src/loss/base.py:7-48, src/loss/mgfn.py:7-47.
+ *
+ * Parameters, gradients and the two Adam moments are flat fp32 blobs of vad_head_train_param_floats() floats in the
+ * layout of vad_head_create, except that a Focus block stores its raw to_v weight and BatchNorm1d affine terms:
+ *     focus     to_v W[inner][d]; norm weight[d], bias[d]; rel_pos w[heads][k], b[heads]; to_out ...
+ * The BatchNorm running statistics (not trained) live in a separate buffer of vad_head_train_bn_floats() floats:
+ * running_mean[d] | running_var[d] per Focus block, in block order; a step updates them with momentum 0.1.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vad_head_train vad_head_train_t;
+int32_t vad_head_train_create(vad_head_train_t** head, const vad_head_config* cfg, int32_t device);
+uint64_t vad_head_train_param_floats(const vad_head_train_t* head);
+uint64_t vad_head_train_bn_floats(const vad_head_train_t* head);
+int32_t vad_head_train_workspace_bytes(const vad_head_train_t* head, int32_t n_videos, int32_t ncrops, int32_t t,
+                                       uint64_t* bytes);
+/* Forward (train mode) + loss + backward for a batch whose first n_videos / 2 bags are normal and the rest abnormal
+ * (src/runner.py:31-33).  video_dev [n_videos, ncrops, t, channels + 1]; labels_dev [n_videos] (normal then abnormal);
+ * mask_dev [n_videos, t]: the dropout mask of the magnitude selection (0 or 1 / (1 - p); modeling_mgfn.py:341-344), drawn
+ * by the caller so that the step is reproducible, or NULL for none.  grads_dev is OVERWRITTEN with d loss / d params.
+ * loss_cfg_host: NULL for the reference's constants, else HOST floats {smoothness weight 8e-4, sparsity weight 8e-3,
+ * alpha 0.001, margin 200} (src/loss/base.py:9,24; src/loss/mgfn.py:9-11).
+ * loss_terms_dev[7] as vad_head_loss; scores_out_dev [n_videos, t] and idx_out_dev [n_videos, k] are optional.
+ * Every contraction (forward, input gradients, weight gradients) is a tcgen05 kind::tf32 GEMM; t <= 64, t % 4 == 0 and
+ * n_videos * ncrops * t % 32 == 0 (the training bags are 32 segments, configs/data/default.yaml). */
+int32_t vad_head_train_step(vad_head_train_t* head, const float* params_dev, float* grads_dev, float* bn_stats_dev,
+                            const float* video_dev, int32_t n_videos, int32_t ncrops, int32_t t,
+                            const float* labels_dev, const float* mask_dev, const float* loss_cfg_host,
+                            void* workspace_dev, uint64_t workspace_bytes, float* loss_terms_dev,
+                            float* scores_out_dev, int32_t* idx_out_dev, void* stream);
+int32_t vad_head_train_num_launches(const vad_head_train_t* head);
+void vad_head_train_destroy(vad_head_train_t* head);
+/* torch.optim.Adam semantics (configure_optimizers, src/runner.py:53-59: lr 1e-3, weight_decay 5e-4 added to the
+ * gradient) fused over flat blobs of n floats; `step` counts from 1; grads are multiplied by grad_scale first
+ * (1 / world_size after a sum all-reduce). */
+int32_t vad_adam_step(float* params_dev, const float* grads_dev, float* m_dev, float* v_dev, uint64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * TF32 precision mode of the backbone (BASELINE.json: "bf16 vs TF32 modes"; features within 1e-3 of the
  * reference's fp32 path).  Same op table and slot / channel-slice semantics as vad_plan_*, with
  *   - every slot a plain fp32 [batch, T, H, W, C] tensor (slot 0: the caller's input, C = in_channels,

@@ -25,10 +25,11 @@ pytestmark = pytest.mark.gpu
 MAX_NORM_TOL = 1e-2
 REL_L2_TOL = 1e-2
 COS_MIN = 0.999
-# floored element-wise relative error (see the module docstring): regression bounds, ~1.5x what a B200 measures
-ELEM_P99_MAX = 0.25
-ELEM_FRAC_GT_1E2_MAX = 0.35
-ELEM_MAX_MAX = 2.0
+# floored element-wise relative error (see the module docstring): regression bounds, ~1.5-2x what a B200 measures
+# (round 2: max 0.09-0.68, p99 0.04-0.12, fraction > 1e-2 0.14-0.19 over the golden cases)
+ELEM_P99_MAX = 0.20
+ELEM_FRAC_GT_1E2_MAX = 0.30
+ELEM_MAX_MAX = 1.5
 
 
 def check_features(got: np.ndarray, want: np.ndarray):
