@@ -173,7 +173,7 @@ extern "C" double vad_head_flops(const vad_head_t* h, int32_t n_seq, int32_t t) 
 // out[S*T, N] = act(conv1d_taps(A)[S*T, taps*Cin] . W[N, taps*Cin]^T + bias) (+ res)
 // (ldo / ldr: row pitches of out / res in floats, 0 = N;  the weight matrix is [N][taps * Cin])
 static int32_t head_gemm(vad_head* h, const float* A, int S, int T, int Cin, int taps, const float* W, int N, const float* bias,
-                         bool gelu, const float* res, float* out, cudaStream_t st, int ldo = 0, int ldr = 0) {
+                         bool gelu, const float* res, float* out, cudaStream_t st, int ldo = 0, int ldr = 0, bool split_k = false) {
   if (Cin % kHeadBK || N % 64) return fail(VAD_ERR_INVALID_ARGUMENT, "head gemm: Cin %% 32 / N %% 64 (Cin=%d, N=%d)", Cin, N);
   HeadGemmParams q;
   memset(&q, 0, sizeof(q));
@@ -205,6 +205,17 @@ static int32_t head_gemm(vad_head* h, const float* A, int S, int T, int Cin, int
   }
   const int s_tiles = (S + q.Sb - 1) / q.Sb;
   dim3 grid(s_tiles * q.t_tiles, N / bn);
+  if (split_k) {
+    // enough CTAs for two waves of the 148 SMs, at least 8 k-blocks each; `out` must be zero and there is no epilogue math
+    if (bias || gelu || res) return fail(VAD_ERR_INVALID_ARGUMENT, "head gemm: split-K takes no bias / GELU / residual");
+    const int total_kb = taps * Cin / kHeadBK;
+    int splits = (2 * 148 + (int)(grid.x * grid.y) - 1) / (int)(grid.x * grid.y);
+    if (splits > total_kb / 8) splits = total_kb / 8;
+    if (splits > 1) {
+      q.kb_per_split = (total_kb + splits - 1) / splits;
+      grid.z = (unsigned)((total_kb + q.kb_per_split - 1) / q.kb_per_split);
+    }
+  }
   cudaError_t e;
   if (bn == 128) {
     static bool attr = false;

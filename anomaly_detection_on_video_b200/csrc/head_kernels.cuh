@@ -24,6 +24,8 @@ struct HeadGemmParams {
   int N;             // output channels
   int Cin, taps;     // contraction = taps * Cin, tap offsets -(taps/2) .. +(taps/2)
   int gelu;
+  int kb_per_split;  // split-K (wgrad: K = all tokens, few output tiles): gridDim.z CTAs take kb_per_split k-blocks each and
+                     // red.add their partial tile into `out` (zeroed by the caller; no bias / GELU / residual); 0 = no split
   int ldo, ldr;      // row pitches (elements) of out / residual
   const float* bias;       // [N] or null
   const float* res;        // [S*T, ldr] or null
@@ -86,7 +88,9 @@ head_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int tt = blockIdx.x - st * p.t_tiles;
   const int s0 = st * p.Sb, t0 = tt * p.Tb;
   const int kb_per_tap = p.Cin / kHeadBK;
-  const int num_kb = p.taps * kb_per_tap;
+  const int total_kb = p.taps * kb_per_tap;
+  const int kb_first = p.kb_per_split ? (int)blockIdx.z * p.kb_per_split : 0;
+  const int num_kb = p.kb_per_split ? (total_kb - kb_first < p.kb_per_split ? total_kb - kb_first : p.kb_per_split) : total_kb;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -114,14 +118,14 @@ head_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (elect_one_sync()) {
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
       uint32_t s = 0, ph = 0;
-      int tap = 0, c0 = 0;
+      int tap = kb_first / kb_per_tap, c0 = (kb_first - tap * kb_per_tap) * kHeadBK;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_a(empty0 + s * 8, ph ^ 1u);
         const uint32_t a_dst = stage0 + s * Cfg::kStageBytes;
         const uint32_t fb = full0 + s * 8;
         mbar_arrive_expect_tx_a(fb, (uint32_t)Cfg::kStageBytes);
         tma_load_3d_a(a_dst, &tmA, fb, c0, t0 + tap - p.taps / 2, s0);
-        tma_load_2d_a(a_dst + Cfg::kABytes, &tmB, fb, kb * kHeadBK, n0);
+        tma_load_2d_a(a_dst + Cfg::kABytes, &tmB, fb, (kb_first + kb) * kHeadBK, n0);
         c0 += kHeadBK;
         if (c0 >= p.Cin) { c0 = 0; ++tap; }
         if (++s == kHeadStages) { s = 0; ph ^= 1u; }
@@ -174,6 +178,12 @@ head_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             f.y = __uint_as_float(v[g * 4 + 1]) + s_bias[c * 32 + g * 4 + 1];
             f.z = __uint_as_float(v[g * 4 + 2]) + s_bias[c * 32 + g * 4 + 2];
             f.w = __uint_as_float(v[g * 4 + 3]) + s_bias[c * 32 + g * 4 + 3];
+            if (p.kb_per_split) {  // partial tile of a split-K launch: accumulate (fp32 reductions in L2)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + g * 4), "f"(__uint_as_float(v[g * 4 + 0])),
+                           "f"(__uint_as_float(v[g * 4 + 1])), "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                           : "memory");
+              continue;
+            }
             if (p.gelu) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w); }
             if (rr) {
               const float4 a = *reinterpret_cast<const float4*>(rr + g * 4);

@@ -31,8 +31,8 @@ extern "C" int32_t vad_head_train_create(vad_head_train_t** out, const vad_head_
   if (!out || !cfg) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_head_train_create: null pointer");
   if (cfg->n_stages < 1 || cfg->n_stages > 4) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_head_train_create: n_stages must be 1..4");
   if (cfg->dim_head != 64) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_head_train_create: dim_head must be 64");
-  if (cfg->channels % 64 || cfg->k < 1 || cfg->k > 8 || cfg->local_aggr_kernel < 1 || !(cfg->local_aggr_kernel & 1) || cfg->ff_repe < 1)
-    return fail(VAD_ERR_INVALID_ARGUMENT, "vad_head_train_create: bad config (channels %% 64, 1 <= k <= 8, odd local_aggr_kernel)");
+  if (cfg->channels % 64 || cfg->k < 1 || cfg->k > 8 || cfg->local_aggr_kernel < 1 || cfg->local_aggr_kernel > 7 || !(cfg->local_aggr_kernel & 1) || cfg->ff_repe < 1)
+    return fail(VAD_ERR_INVALID_ARGUMENT, "vad_head_train_create: bad config (channels %% 64, 1 <= k <= 8, odd local_aggr_kernel <= 7)");
   int32_t rc = require_sm100(device);
   if (rc != VAD_OK) return rc;
   vad_head_train* h = new vad_head_train();
@@ -239,6 +239,8 @@ extern "C" int32_t vad_head_train_step(vad_head_train_t* h, const float* params_
   const int dl = c.dims[c.n_stages - 1];
   auto ew_grid = [](long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g)); };
   auto warp_grid = [](long long tokens) { return (int)((tokens * 32 + 255) / 256); };
+  // column reductions over all tokens: enough token chunks for ~4 blocks per SM whatever the channel count
+  auto red_chunks = [&](int channels) { int g = (148 * 4) / ((channels + 31) / 32); long long mx = (ntok + 63) / 64; if (g > mx) g = (int)mx; return g < 1 ? 1 : g; };
   auto ln_grid = [](long long tokens) { long long g = (tokens + 7) / 8; return (int)(g > 148 * 4 ? 148 * 4 : (g < 1 ? 1 : g)); };
   VAD_CUDA_CHECK(cudaMemsetAsync(D, 0, h->total_floats * sizeof(float), st));
 
@@ -268,7 +270,10 @@ extern "C" int32_t vad_head_train_step(vad_head_train_t* h, const float* params_
         TRAIN_LAUNCHED();
       } else {
         float* rm = bn_stats_dev + k.bn_stat;
-        head_bn_reduce_kernel<<<(d + 31) / 32, dim3(32, 8), 0, st>>>(q.x1, nullptr, ntok, d, 1e-5f, 0.1f, 0, q.bn_mean, q.bn_invstd, rm, rm + d, nullptr, nullptr);
+        VAD_CUDA_CHECK(cudaMemsetAsync(q.bn_s1, 0, 2 * (size_t)((d * 4 + 1023) / 1024 * 1024), st));   // bn_s1 | bn_s2 are adjacent arena granules
+        head_bn_reduce_kernel<<<dim3((d + 31) / 32, red_chunks(d)), dim3(32, 8), 0, st>>>(q.x1, nullptr, ntok, d, 0, nullptr, nullptr, q.bn_s1, q.bn_s2);
+        TRAIN_LAUNCHED();
+        head_bn_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(q.bn_s1, q.bn_s2, ntok, d, 1e-5f, 0.1f, q.bn_mean, q.bn_invstd, rm, rm + d);
         TRAIN_LAUNCHED();
         head_bn_apply_kernel<<<ew_grid(ntok * d), 256, 0, st>>>(q.x1, q.bn_mean, q.bn_invstd, P + k.bn_g, P + k.bn_b, ntok, d, q.xb);
         TRAIN_LAUNCHED();
@@ -324,7 +329,7 @@ extern "C" int32_t vad_head_train_step(vad_head_train_t* h, const float* params_
     HEAD_TRY(transpose(dOut, N, ntok, N, T, 0, B.t1, ntok, has_bias ? D + b_off : nullptr));               // dOutT [N, ntok] (+ bias gradient)
     for (int tap = 0; tap < taps; ++tap) {
       HEAD_TRY(transpose(A, Cin, ntok, Cin, T, tap - taps / 2, B.t2, ntok, nullptr));                       // (A shifted by the tap)T [Cin, ntok]
-      HEAD_TRY(head_gemm(G, B.t1, 1, N, (int)ntok, 1, B.t2, Cin, nullptr, false, nullptr, D + w_off + (size_t)tap * Cin, st, taps * Cin));
+      HEAD_TRY(head_gemm(G, B.t1, 1, N, (int)ntok, 1, B.t2, Cin, nullptr, false, nullptr, D + w_off + (size_t)tap * Cin, st, taps * Cin, 0, true));
     }
     if (dA_out) {
       for (int tp = 0; tp < taps; ++tp)                                                                      // WT[cin][tp][n] = W[n][taps - 1 - tp][cin]
@@ -386,12 +391,11 @@ extern "C" int32_t vad_head_train_step(vad_head_train_t* h, const float* params_
       } else {
         head_relpos_bwd_data_kernel<<<ew_grid(ntok * k.inner), 256, 0, st>>>(B.gw0, P + k.rp_w, B.gw1, S, T, k.inner, k.heads, c.local_aggr_kernel);
         TRAIN_LAUNCHED();                                                                                    // gw1 = d v
-        head_relpos_bwd_weight_kernel<<<k.heads * c.local_aggr_kernel + k.heads, 256, 0, st>>>(B.gw0, q.v, D + k.rp_w, D + k.rp_b, S, T, k.inner, k.heads,
-                                                                                              c.local_aggr_kernel);
+        head_relpos_bwd_weight_kernel<<<dim3((k.inner + 31) / 32, red_chunks(k.inner)), dim3(32, 8), 0, st>>>(B.gw0, q.v, D + k.rp_w, D + k.rp_b, S, T, k.inner,
+                                                                                                              k.heads, c.local_aggr_kernel);
         TRAIN_LAUNCHED();
         HEAD_TRY(gemm_bwd(B.gw1, q.xb, k.v_w, 0, false, 1, d, k.inner, ga, nullptr));                         // ga = d xb
-        head_bn_reduce_kernel<<<(d + 31) / 32, dim3(32, 8), 0, st>>>(q.x1, ga, ntok, d, 1e-5f, 0.f, 1, q.bn_mean, q.bn_invstd, nullptr, nullptr,
-                                                                    D + k.bn_b, D + k.bn_g);
+        head_bn_reduce_kernel<<<dim3((d + 31) / 32, red_chunks(d)), dim3(32, 8), 0, st>>>(q.x1, ga, ntok, d, 1, q.bn_mean, q.bn_invstd, D + k.bn_b, D + k.bn_g);
         TRAIN_LAUNCHED();                                                                                    // d beta = sum dy, d gamma = sum dy xhat
         head_bn_bwd_apply_kernel<<<ew_grid(ntok * d), 256, 0, st>>>(q.x1, ga, q.bn_mean, q.bn_invstd, P + k.bn_g, D + k.bn_b, D + k.bn_g, gb, ntok, d, gx);
         TRAIN_LAUNCHED();                                                                                    // gx = d x1

@@ -206,91 +206,97 @@ __global__ void head_relpos_bwd_data_kernel(const float* __restrict__ du, const 
     dv[i] = a;
   }
 }
-// ... weight / bias gradient: one block per (head, tap) and one per head for the bias (blockIdx.x >= heads * k):
-//   dw[h][j] = sum_{tok, c % heads == h} du[tok, c] * v[tok + j - half, c],   db[h] = sum du[tok, c]
+// ... weight / bias gradient:  dw[h][j] += sum_{tok, c % heads == h} du[tok, c] * v[tok + j - half, c],  db[h] += sum du[tok, c]
+// (dw / db zeroed by the caller).  grid (C / 32, token chunks), block (32, 8): a thread owns one channel over a slice of
+// the tokens and keeps k + 1 partial sums; block reduction per channel, then one atomicAdd per (channel, tap).  k <= 7.
 __global__ void __launch_bounds__(256) head_relpos_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ v, float* __restrict__ dw,
                                                                      float* __restrict__ db, int S, int T, int C, int heads, int k) {
-  __shared__ float red[256];
+  __shared__ float red[8][8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
   const int half = k / 2;
-  const bool bias = (int)blockIdx.x >= heads * k;
-  const int h = bias ? (int)blockIdx.x - heads * k : (int)blockIdx.x / k;
-  const int j = bias ? 0 : (int)blockIdx.x % k;
-  const int per = C / heads;
-  const long long total = (long long)S * T * per;
-  float a = 0.f;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int m = (int)(i % per);
-    const long long tok = i / per;
-    const int c = h + heads * m;
-    const float g = du[tok * C + c];
-    if (bias) {
-      a += g;
-    } else {
-      const int ts = (int)(tok % T) + j - half;
-      if (ts >= 0 && ts < T) a = fmaf(g, v[(tok + j - half) * C + c], a);
+  const long long ntok = (long long)S * T;
+  const long long per = (ntok + gridDim.y - 1) / gridDim.y;
+  const long long lo = (long long)blockIdx.y * per, hi = lo + per < ntok ? lo + per : ntok;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (c < C) {
+    for (long long tok = lo + ty; tok < hi; tok += 8) {
+      const int t = (int)(tok % T);
+      const float g = du[tok * C + c];
+      a[7] += g;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int ts = t + j - half;
+        if (j < k && ts >= 0 && ts < T) a[j] = fmaf(g, v[(tok + j - half) * C + c], a[j]);
+      }
     }
   }
-  red[threadIdx.x] = a;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[j][ty][tx] = a[j];
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    if (bias) db[h] = red[0];
-    else dw[h * k + j] = red[0];
+  if (ty == 0 && c < C) {
+    const int h = c % heads;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += red[j][i][tx];
+      if (j == 7) atomicAdd(db + h, sum);
+      else if (j < k) atomicAdd(dw + h * k + j, sum);
+    }
   }
 }
 
 // BatchNorm1d in train mode (FocusAttention.norm, modeling_mgfn.py:178): per-channel statistics over all tokens.
-// One block per 32 channels, block (32, 8).  mode 0: batch mean / invstd (+ running-statistics update, momentum, unbiased
-// variance as torch does);  mode 1: backward sums  s1[c] = sum dy, s2[c] = sum dy * xhat.
-__global__ void __launch_bounds__(256) head_bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long ntok, int C, float eps,
-                                                             float momentum, int mode, float* __restrict__ mean, float* __restrict__ invstd,
-                                                             float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ s1,
-                                                             float* __restrict__ s2) {
+// grid (C / 32, token chunks), block (32, 8); partial sums are atomically added into zeroed [C] accumulators:
+//   mode 0: acc1 += sum x,  acc2 += sum x^2          (head_bn_finalize_kernel turns them into mean / invstd)
+//   mode 1: acc1 += sum dy, acc2 += sum dy * xhat    (d beta, d gamma)
+__global__ void __launch_bounds__(256) head_bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long ntok, int C, int mode,
+                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                             float* __restrict__ acc1, float* __restrict__ acc2) {
   __shared__ float ra[8][33], rb[8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
-  const bool ok = c < C;
-  auto reduce2 = [&](float a, float b, float& oa, float& ob) {
-    ra[ty][tx] = a; rb[ty][tx] = b;
-    __syncthreads();
-    float sa = 0.f, sb = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { sa += ra[i][tx]; sb += rb[i][tx]; }
-    __syncthreads();
-    oa = sa; ob = sb;
-  };
-  if (mode == 0) {
-    float a = 0.f, dummy = 0.f, tot, t2;
-    if (ok) for (long long r = ty; r < ntok; r += 8) a += x[r * C + c];
-    reduce2(a, dummy, tot, t2);
-    const float mu = tot / (float)ntok;
-    a = 0.f;
-    if (ok) for (long long r = ty; r < ntok; r += 8) { const float d = x[r * C + c] - mu; a = fmaf(d, d, a); }
-    reduce2(a, dummy, tot, t2);
-    if (ok && ty == 0) {
-      const float var = tot / (float)ntok;
-      mean[c] = mu;
-      invstd[c] = rsqrtf(var + eps);
-      if (run_mean) {
-        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mu;
-        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (ntok > 1 ? tot / (float)(ntok - 1) : var);
-      }
-    }
-  } else {
-    float a = 0.f, b = 0.f, ta, tb;
-    if (ok) {
+  const long long per = (ntok + gridDim.y - 1) / gridDim.y;
+  const long long lo = (long long)blockIdx.y * per, hi = lo + per < ntok ? lo + per : ntok;
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    if (mode == 0) {
+      for (long long r = lo + ty; r < hi; r += 8) { const float v = x[r * C + c]; a += v; b = fmaf(v, v, b); }
+    } else {
       const float mu = mean[c], is = invstd[c];
-      for (long long r = ty; r < ntok; r += 8) {
+      for (long long r = lo + ty; r < hi; r += 8) {
         const float g = dy[r * C + c];
         a += g;
         b = fmaf(g, (x[r * C + c] - mu) * is, b);
       }
     }
-    reduce2(a, b, ta, tb);
-    if (ok && ty == 0) { s1[c] = ta; s2[c] = tb; }
+  }
+  ra[ty][tx] = a; rb[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa += ra[i][tx]; sb += rb[i][tx]; }
+    atomicAdd(acc1 + c, sa);
+    atomicAdd(acc2 + c, sb);
+  }
+}
+// sums -> batch mean / invstd (biased variance) and the running-statistics update (momentum, unbiased variance, as torch)
+__global__ void head_bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long ntok, int C, float eps, float momentum,
+                                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mu = sum[c] / (float)ntok;
+  float var = sumsq[c] / (float)ntok - mu * mu;
+  var = var > 0.f ? var : 0.f;
+  mean[c] = mu;
+  invstd[c] = rsqrtf(var + eps);
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mu;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (ntok > 1 ? var * (float)ntok / (float)(ntok - 1) : var);
   }
 }
 // y = (x - mean) * invstd * g + b

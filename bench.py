@@ -509,7 +509,44 @@ def main():
                      "tflops_tf32": flops / (head_ms / 1e3) / 1e12, "launches": head.num_launches + 3,
                      "loss": float(out.loss), "nccl_gather_ms": gather_ms,
                      "gather_bytes": int(seg_local.numel() * 4 * world),
-                     "note": "eval-mode forward + selection + loss (no backward kernels: training is not built)"}
+                     "note": "eval-mode forward + selection + loss"}
+        # ---- BASELINE config 5: one MIL training step on the gathered bags (src/runner.py:29-39,53-59): train-mode forward
+        # (BatchNorm batch statistics, dropout 0.7 on the selection mask), loss, backward (tcgen05 tf32 dgrad / wgrad GEMMs),
+        # NCCL all-reduce of the flat gradient blob across the ranks, fused Adam (lr 1e-3, weight_decay 5e-4)
+        from anomaly_detection_on_video_b200.mgfn import NativeAdam
+        head.train()
+        opt = NativeAdam(head, lr=1e-3, weight_decay=5e-4)
+        def train_step():
+            opt.zero_grad()
+            o = head(video, abnormal_labels=al, normal_labels=nl)
+            opt.step()
+            return o
+        for _ in range(2):
+            o = train_step()
+        n_tr = max(3, min(K, 10))
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        r0.record()
+        for _ in range(n_tr):
+            o = train_step()
+        r1.record()
+        barrier()
+        train_ms = r0.elapsed_time(r1) / n_tr
+        ar_ms = None
+        if world > 1:
+            gflat = head._train["grad"]
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            dist.all_reduce(gflat)
+            a1.record()
+            torch.cuda.synchronize(dev)
+            ar_ms = a0.elapsed_time(a1)
+        head_info.update({"train_step_ms": train_ms, "train_bags_per_s": bags / (train_ms / 1e3), "train_launches": head.train_launches + 1,
+                          "train_tflops_tf32": 3.0 * flops / (train_ms / 1e3) / 1e12, "train_loss": float(o.loss.detach()),
+                          "grad_allreduce_ms": ar_ms, "grad_bytes": int(head._train["grad"].numel() * 4),
+                          "train_note": "forward + loss + backward + gradient all-reduce (N > 1) + fused Adam; every rank steps on the same "
+                                        "32 gathered bags (16 normal + 16 abnormal, 10 crops x 32 segments x 2049)"})
+        head.eval()
     except Exception as exc:  # the head is reported beside the metric; it must never take the bench line down
         head_info = {"error": f"{type(exc).__name__}: {exc}"}
 
