@@ -445,8 +445,11 @@ __global__ void __launch_bounds__(256) maxpool3d_k3s1_kernel(const PoolParams p)
 // global average pool: in [B, P, C] bf16 -> out [B, C] fp32.  A warp covers 64 channels: lane =
 // pg*8 + cv reads 16 B of channel vector cv at positions pg, pg+4, ... (4 x 128 B contiguous per
 // step), then the four position groups are combined with warp shuffles.
+// kt_win > 0: AvgPool3d((kt_win, H, W), stride 1) followed by a global mean over the T - kt_win + 1 windows (the head the
+// reference puts on pytorchvideo's I3D-R50, src/i3d.py:21-57): frame t of the P = T * HW positions is weighted by the number
+// of windows that cover it.
 __global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int P, int C,
-                                                      float* __restrict__ out) {
+                                                      float* __restrict__ out, int HW = 0, int kt_win = 0) {
   const int warps_per_clip = C >> 6;
   const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -456,6 +459,19 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __res
   const int pg = lane >> 3;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const __nv_bfloat16* base = in + (long long)b * P * C + c0;
+  if (kt_win > 0) {
+    const int T = P / HW, last = T - kt_win;
+    for (int pos = pg; pos < P; pos += 4) {
+      const int t = pos / HW;
+      const int lo = t - kt_win + 1 > 0 ? t - kt_win + 1 : 0, hi = t < last ? t : last;
+      const float w = (float)(hi - lo + 1);
+      const uint4 x = *reinterpret_cast<const uint4*>(base + (long long)pos * C);
+      acc[0] = fmaf(w, bf16_lo(x.x), acc[0]); acc[1] = fmaf(w, bf16_hi(x.x), acc[1]);
+      acc[2] = fmaf(w, bf16_lo(x.y), acc[2]); acc[3] = fmaf(w, bf16_hi(x.y), acc[3]);
+      acc[4] = fmaf(w, bf16_lo(x.z), acc[4]); acc[5] = fmaf(w, bf16_hi(x.z), acc[5]);
+      acc[6] = fmaf(w, bf16_lo(x.w), acc[6]); acc[7] = fmaf(w, bf16_hi(x.w), acc[7]);
+    }
+  } else
   for (int pos = pg; pos < P; pos += 4) {
     const uint4 x = *reinterpret_cast<const uint4*>(base + (long long)pos * C);
     acc[0] += bf16_lo(x.x); acc[1] += bf16_hi(x.x);
@@ -469,7 +485,7 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __res
     acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
   }
   if (pg == 0) {
-    const float inv = 1.f / (float)P;
+    const float inv = kt_win > 0 ? 1.f / ((float)HW * (float)kt_win * (float)(P / HW - kt_win + 1)) : 1.f / (float)P;
     float4* o = reinterpret_cast<float4*>(out + (long long)b * C + c0);
     o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
     o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);

@@ -124,7 +124,7 @@ struct OpRuntime {
   bool skip = false;               // this op runs inside an earlier op's launch
   TailParams tlp;
   CUtensorMap tmW3, tmX;
-  int avg_P = 0, avg_C = 0;
+  int avg_P = 0, avg_C = 0, avg_HW = 0, avg_kt = 0;
   // for tensor-map encoding
   int Ci = 0, Ti = 0, Hi = 0, Wi = 0;
   int K_pad = 0;
@@ -569,6 +569,12 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       if (src.C % 64) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: avg-pool needs C %% 64 == 0", i);
       r.avg_P = src.T * src.H * src.W;
       r.avg_C = src.C;
+      // kt > 0: AvgPool3d((kt, H, W), stride 1) + global mean over the windows (kh / kw, when given, must cover the map)
+      if (d.kt > 1 && d.kt < src.T) {
+        if ((d.kh && d.kh != src.H) || (d.kw && d.kw != src.W)) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: windowed avg-pool must span the whole %dx%d map", i, src.H, src.W);
+        r.avg_HW = src.H * src.W;
+        r.avg_kt = d.kt;
+      }
       p->feat_c = src.C;
       p->op_bytes[i] = 2.0 * batch * (double)r.avg_P * src.C + 4.0 * batch * src.C;
       continue;
@@ -1230,7 +1236,7 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
                                       : static_cast<const uint8_t*>(workspace_dev) + p->slots[d.src].offset;
       const long long warps = (long long)p->batch * (r.avg_C / 64);
       avgpool_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), p->batch,
-                                                                     r.avg_P, r.avg_C, feat_out_dev);
+                                                                     r.avg_P, r.avg_C, feat_out_dev, r.avg_HW, r.avg_kt);
       e = cudaGetLastError();
     }
     if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "op %zu launch failed: %s", i, cudaGetErrorString(e));

@@ -53,7 +53,8 @@ def load_ucf_crime_dataset(repo_id: str = DEFAULT_REPO_ID, cache_dir: str = DEFA
 def load_feature_extraction_model(model_name: str = "tushar-n-baseline", state_dict_path: Optional[str] = None,
                                   device: Optional[torch.device] = None, precision: str = "bf16") -> Tuple[torch.nn.Module, torch.device]:
     """extract_features.py:34-40.  The default is the reference *factory's* default backbone (I3Res50);
-    the reference CLI's own default, pytorchvideo's ``i3d_8x8_r50``, is third-party and not built.
+    the reference CLI's own default, pytorchvideo's ``i3d_8x8_r50``, is built from its published architecture (third-party,
+    parity unpinned: ``ptv_resnet.I3D8x8R50``).
     ``model_name="inception-i3d"`` builds the InceptionV1-3D backbone BASELINE.json names (1024-d features; not part of
     the reference).  ``precision``: "bf16" (production) or "tf32" (fp32 activations, features within 1e-3)."""
     if precision not in ("bf16", "tf32"):

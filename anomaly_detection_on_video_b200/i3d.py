@@ -250,13 +250,17 @@ def build_i3d_feature_extractor(model_name: str = "tushar-n-baseline", check_mod
 
     The reference downloads the checkpoint from the HF hub; this environment has no network, so
     weights come from ``state_dict_path`` (or stay at the constructor's random init).
-    ``i3d_8x8_r50`` is pytorchvideo's third-party backbone, which the reference does not vendor.
+    ``i3d_8x8_r50`` (the CLI's default in the reference) is pytorchvideo's third-party backbone: built from its published
+    architecture (``ptv_resnet.I3D8x8R50``), parity unpinned.
     """
     if model_name == "tushar-n-baseline":
         model = I3Res50(use_nl=False)
     elif model_name == "i3d_8x8_r50":
-        raise NotImplementedError("i3d_8x8_r50 is pytorchvideo's create_resnet (third-party, un-vendored, version "
-                                  "unpinned in the reference); only 'tushar-n-baseline' (I3Res50) is built")
+        # pytorchvideo's create_resnet with the reference's arguments (src/i3d.py:339-350) as an op table over the native
+        # kernels; third-party architecture, parity unpinned (oracle/i3d_r50_ptv.py restates it)
+        from .ptv_resnet import I3D8x8R50
+
+        model = I3D8x8R50()
     else:
         raise AttributeError(model_name)
     if state_dict_path is not None:

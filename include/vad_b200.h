@@ -60,6 +60,9 @@ int32_t vad_abi_version(void);
  * ---------------------------------------------------------------------------------------------- */
 
 enum { VAD_OP_CONV = 0, VAD_OP_MAXPOOL = 1, VAD_OP_AVGPOOL = 2 };
+/* AVGPOOL: global mean over (T, H, W) of the src slot -> fp32 features.  With 1 < kt < T it is AvgPool3d((kt, H, W), stride 1)
+ * followed by a global mean over the T - kt + 1 windows (the head the reference puts on pytorchvideo's I3D-R50,
+ * src/i3d.py:21-57): frame t is weighted by the number of windows covering it. */
 
 /* vad_op_desc.flags */
 enum {

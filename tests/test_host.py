@@ -87,9 +87,27 @@ def test_param_packer_layout():
     assert torch.count_nonzero(wf[:, :, :, 7]) == 0 and torch.count_nonzero(wf[..., 3]) == 0
 
 
-def test_factory_signature_and_unbuilt_backbone():
-    with pytest.raises(NotImplementedError, match="pytorchvideo"):
-        build_i3d_feature_extractor("i3d_8x8_r50", check_model_size=False)
+def test_factory_builds_the_cli_default_backbone_with_pytorchvideo_names():
+    """a16: ``i3d_8x8_r50`` (extract_features.py:34,46; src/i3d.py:339-350).  pytorchvideo is absent, so parity is unpinned; what
+    can be held on the CPU: the parameter names / shapes a hub checkpoint carries, and the op table's MAC count."""
+    from anomaly_detection_on_video_b200 import _lib
+    from anomaly_detection_on_video_b200.ptv_resnet import I3D8x8R50
+    from oracle import i3d_r50_ptv as R
+
+    m = build_i3d_feature_extractor("i3d_8x8_r50", check_model_size=False)
+    assert isinstance(m, I3D8x8R50) and m.feature_dim == 2048
+    want = R.seeded_state_dict(0)
+    got = m.state_dict()
+    assert set(got) == set(want)
+    assert all(tuple(got[k].shape) == tuple(want[k].shape) for k in want)
+    m.load_state_dict(want, strict=True)
+    ops = m.op_table()
+    convs = [o for o in ops if o.kind == _lib.VAD_OP_CONV]
+    assert len(convs) == 1 + 3 * 16 + 4 and ops[-1].kind == _lib.VAD_OP_AVGPOOL and ops[-1].kernel[0] == 4
+    assert R.conv_macs() == 56_813_682_688
+
+
+def test_factory_signature():
     with pytest.raises(AttributeError):
         build_i3d_feature_extractor("nope")
     m = build_i3d_feature_extractor("tushar-n-baseline", check_model_size=False)
