@@ -223,6 +223,145 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocParams p) 
   }
 }
 
+// K1, stem layout only, resampling kernels of at most KH x KV taps (Pillow's bilinear filter has 3 taps when it
+// enlarges -- the 240 x 320 UCF-Crime frames --, 5 up to a 2 x reduction).  Same arithmetic as preprocess_kernel, far
+// fewer instructions (that kernel is issue bound at 0.38 of the HBM write rate: 5.6 k instructions per thread):
+//   * one thread owns one resized COLUMN: its horizontal taps and coefficients stay in registers for all source rows
+//     (no index division, no per-pixel table loads);
+//   * the horizontal result never goes to shared memory: the thread walks the staged source rows once and keeps the
+//     last KV horizontally resampled pixels in a register window.  Row y's vertical taps are source rows
+//     [ymin, ymin + ycnt) and ymin + ycnt never decreases with y, so when the window has just absorbed row
+//     ymin + ycnt - 1 the taps are its LAST ycnt entries: the coefficients are stored right-aligned (zeros in front)
+//     and every output is a fixed KV-term sum over statically indexed registers;
+//   * crops: groups of per_crop threads (one 16-byte store = two pixels each) take (row, crop) pairs; the thread's
+//     pad / range predicates and its mirrored source index are loop invariants.
+// blockDim.x = the resized width rounded up to a warp (352 for 341 columns).
+template <int KH, int KV, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 384 ? 4 : 2) preprocess_stem_kernel(const PreprocParams p) {
+  extern __shared__ __align__(16) uint8_t s_mem[];
+  const int R = p.rows_per_block;
+  const int src_row_bytes = p.W * 3;
+  const int src_pitch = (src_row_bytes + 15) & ~15;
+  unsigned short* lut_h = reinterpret_cast<unsigned short*>(s_mem);          // 256 bf16 bit patterns
+  int* s_kv = reinterpret_cast<int*>(s_mem + 512);                           // [R][KV] right-aligned vertical coefficients
+  int* s_rend = s_kv + R * KV;                                               // [R] one past the last staged source row of output row yy
+  uint2* s_px = reinterpret_cast<uint2*>(s_mem + p.off_px);                  // R x rw standardised bf16 pixels (r, g, b, 0)
+  uint8_t* s_src = s_mem + p.off_src;                                        // staged source rows, pitch src_pitch (+ tap slack)
+
+  const int y0 = blockIdx.x * R;
+  const int ny = (p.rh - y0) < R ? (p.rh - y0) : R;
+  const int slot = blockIdx.y;
+  const int clip_local = slot / p.fpc;
+  const int t = slot - clip_local * p.fpc;
+  const int clip = p.clip_start + clip_local;
+  int L = p.n_frames - clip * p.fpc;      // real frames in this clip (LoopPad, gtransforms.py:115-132)
+  L = L > p.fpc ? p.fpc : L;
+  const int src_frame = clip * p.fpc + (t % L);
+  const uint8_t* frame = p.frames + (long long)src_frame * p.H * p.W * 3;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  if (tid < 256) {
+    // GroupStandardizationTenCrop: t.sub_(114.75).div_(57.375), two fp32 roundings, then the stem's bf16
+    const float v = __fdiv_rn(__fsub_rn((float)tid, 114.75f), 57.375f);
+    lut_h[tid] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
+  const int ymin0 = p.bounds_v[2 * y0];
+  if (tid < ny) {
+    const int y = y0 + tid;
+    const int ymin = p.bounds_v[2 * y], ycnt = p.bounds_v[2 * y + 1];
+    s_rend[tid] = ymin + ycnt - ymin0;
+#pragma unroll
+    for (int q = 0; q < KV; ++q) {
+      const int j = q - (KV - ycnt);
+      s_kv[tid * KV + q] = j >= 0 ? p.coef_v[y * p.ksize_v + j] : 0;
+    }
+  }
+  const int nsrc = p.bounds_v[2 * (y0 + ny - 1)] + p.bounds_v[2 * (y0 + ny - 1) + 1] - ymin0;
+  {
+    const uint8_t* g0 = frame + (long long)ymin0 * src_row_bytes;
+    const bool vec = ((src_row_bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(g0) & 15) == 0);
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+    if (vec) {
+      const int per_row = src_row_bytes >> 4;
+      for (int r = warp; r < nsrc; r += nwarp)
+        for (int c = lane; c < per_row; c += 32)
+          reinterpret_cast<uint4*>(s_src + r * src_pitch)[c] = __ldg(reinterpret_cast<const uint4*>(g0 + (long long)r * src_row_bytes) + c);
+    } else {
+      for (int r = warp; r < nsrc; r += nwarp)
+        for (int c = lane; c < src_row_bytes; c += 32) s_src[r * src_pitch + c] = g0[(long long)r * src_row_bytes + c];
+    }
+  }
+  __syncthreads();
+
+  for (int x = tid; x < p.rw; x += nthr) {
+    const int xmin = p.bounds_h[2 * x];
+    int kh[KH];
+#pragma unroll
+    for (int j = 0; j < KH; ++j) kh[j] = j < p.ksize_h ? p.coef_h[x * p.ksize_h + j] : 0;   // zero beyond the tap count
+    const uint8_t* col = s_src + xmin * 3;
+    int win[KV][3];
+#pragma unroll
+    for (int q = 0; q < KV; ++q) win[q][0] = win[q][1] = win[q][2] = 0;
+    int next_r = 0;
+    for (int yy = 0; yy < ny; ++yy) {
+      const int rend = s_rend[yy];
+      while (next_r < rend) {
+#pragma unroll
+        for (int q = 0; q + 1 < KV; ++q) { win[q][0] = win[q + 1][0]; win[q][1] = win[q + 1][1]; win[q][2] = win[q + 1][2]; }
+        const uint8_t* src = col + next_r * src_pitch;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+#pragma unroll
+        for (int j = 0; j < KH; ++j) {
+          a0 += (int)src[3 * j] * kh[j];
+          a1 += (int)src[3 * j + 1] * kh[j];
+          a2 += (int)src[3 * j + 2] * kh[j];
+        }
+        win[KV - 1][0] = clip8_q22(a0); win[KV - 1][1] = clip8_q22(a1); win[KV - 1][2] = clip8_q22(a2);
+        ++next_r;
+      }
+      int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+#pragma unroll
+      for (int q = 0; q < KV; ++q) {
+        const int k = s_kv[yy * KV + q];
+        a0 += win[q][0] * k; a1 += win[q][1] * k; a2 += win[q][2] * k;
+      }
+      const uint32_t cr = lut_h[clip8_q22(a0)], cg = lut_h[clip8_q22(a1)], cb = lut_h[clip8_q22(a2)];
+      s_px[yy * p.rw + x] = make_uint2(cr | (cg << 16), cb);
+    }
+  }
+  __syncthreads();
+
+  // stem layout [clipcrop, t, crop, crop + 8, 4] bf16; one work item = two pixels (16 B).  (row, crop) pairs are walked
+  // row-major in steps of `groups` without a division; everything that depends only on the thread is hoisted.
+  const int crop = p.crop;
+  const int per_crop = (crop + 8) >> 1;
+  const int groups = nthr / per_crop;
+  const int g = tid / per_crop;
+  if (g >= groups) return;
+  const int i = tid - g * per_crop;
+  const int xa = 2 * i - p.pad_left, xb = xa + 1;
+  const bool pa = xa >= 0 && xa < crop, pb = xb >= 0 && xb < crop;
+  const int fa = crop - 1 - xa, fb = crop - 1 - xb;                 // source columns in a mirrored crop
+  const int ncrops = p.ncrops;
+  const unsigned k_stride = (unsigned)(p.fpc * crop * per_crop);    // uint4 between two crops of a clip
+  uint4* const outp = reinterpret_cast<uint4*>(p.out) + ((long long)clip_local * ncrops * p.fpc + t) * (long long)(crop * per_crop) + i;
+  int yy = 0, k = g;
+  for (;;) {
+    while (k >= ncrops) { k -= ncrops; ++yy; }
+    if (yy >= ny) break;
+    const int yo = y0 + yy - p.tops[k];
+    if ((unsigned)yo < (unsigned)crop) {
+      const uint2* row = s_px + yy * p.rw + p.lefts[k];
+      const bool flip = p.flips[k] != 0;
+      uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+      if (pa) a = row[flip ? fa : xa];
+      if (pb) b = row[flip ? fb : xb];
+      outp[(unsigned)k * k_stride + (unsigned)(yo * per_crop)] = make_uint4(a.x, a.y, b.x, b.y);
+    }
+    k += groups;
+  }
+}
+
 // ------------------------------------------------------------------------------------------- K3
 struct PoolParams {
   const __nv_bfloat16* in;

@@ -37,7 +37,7 @@ enum AMode : int {
 struct ConvParams {
   int M, N, num_kb;
   int n_tiles, num_tiles;
-  int mc_items;          // MC kernels: work items = ceil(m_tiles / 2) * n_tiles (a cluster of two CTAs per item)
+  int mc_items;          // CTA-pair kernels: work items = ceil(m_tiles / 2) * n_tiles (a cluster of two CTAs per item)
   int pair_split;        // conv_pair_kernel<256>: items [0, pair_split) are 256 x 256 tiles; item pair_split + h is the
   int pair_total;        //   (h & 1)-th 128-column half of m-pair pair_split + h / 2 (tail round at half width); total items
   int pair_box_rows;     //   rows of one weight box (128, or 64 when there are half-width items)
@@ -48,7 +48,6 @@ struct ConvParams {
   int ntaps;
   long long sN, sT, sH, sW;  // input strides in elements
   int a_mode;
-  int l2_ahead;          // staged epilogue: TMA-prefetch the residual tile of the tile this CTA runs l2_ahead iterations later into L2 (0: off)
   int pool_tp;           // 1: M tiles are (all 4 frames x 32 pixels) and the staged epilogue max-reduces frame pairs (maxpool2 fused)
   int tp_tiles_per_clip; // ceil(H * W / 32) when pool_tp
   int relu;
@@ -142,23 +141,18 @@ __device__ __forceinline__ void tma_store_4d_b(const CUtensorMap* map, uint32_t 
                : "memory");
 }
 
-// MC: launched as clusters of two CTAs that run the m tiles (2j, 2j+1) of the same n tile in lock step; each CTA
-// loads its own A tile and HALF of the shared B (weight) tile, multicast into both CTAs' shared memory (tmR carries the
-// half-height weight map), and releases a ring slot in both CTAs, so the weights cross L2 -> SM once per 256 rows.
-template <int BN, int BK, int KPS, bool GATHER, bool EPI, bool MC = false>
+template <int BN, int BK, int KPS, bool GATHER, bool EPI>
 __global__ void __launch_bounds__(ConvCfg<BN, BK, KPS, GATHER, EPI>::kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvParams p) {
   using Cfg = ConvCfg<BN, BK, KPS, GATHER, EPI>;
   constexpr int STAGES = Cfg::kStages;
-  static_assert(!MC || (!GATHER && !EPI && KPS == 1 && BK == 64), "multicast: TMA operands, direct epilogue");
-  // work distribution: item w -> (n tile, m tile); MC pairs m tiles inside a cluster
-  const int crank = MC ? (int)cluster_ctarank() : 0;
-  const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int w_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int w_total = MC ? p.mc_items : p.num_tiles;
-  auto m_tile_of = [&](int w) { return MC ? 2 * (w / p.n_tiles) + crank : w / p.n_tiles; };
+  // work distribution: item w -> (n tile, m tile), n fastest
+  const int w_first = (int)blockIdx.x;
+  const int w_step = (int)gridDim.x;
+  const int w_total = p.num_tiles;
+  auto m_tile_of = [&](int w) { return w / p.n_tiles; };
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -185,7 +179,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (!GATHER) tma_prefetch_desc(&tmA);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], GATHER ? (1 + 128) : 1);
-      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: released by the MMA threads of both CTAs
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -207,7 +201,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch_dependents();  // the next kernel of the stream may begin its own prologue as SMs free up
@@ -225,7 +218,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = w_first; tile < w_total; tile += w_step) {
         const int n0 = (tile % p.n_tiles) * BN;
         const int m0 = m_tile_of(tile) * kBlockM;
-        const bool valid = !MC || m0 < p.M;  // MC: the odd CTA of the last pair may have no rows; it still loads its B half
         int tp_clip = 0, tp_p0 = 0;  // pool_tp: tile = (clip, 32 pixels) x all 4 frames
         if (EPI && p.pool_tp) {
           const int mt = tile / p.n_tiles;
@@ -250,11 +242,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_dst = stage0 + s * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + KPS * Cfg::kABytes;
           const uint32_t fb = full0 + s * 8;
-          mbar_arrive_expect_tx_a(fb, (uint32_t)nk * (GATHER ? Cfg::kBBytes : Cfg::kKbBytes) - ((MC && !valid) ? (uint32_t)Cfg::kABytes : 0u));
+          mbar_arrive_expect_tx_a(fb, (uint32_t)nk * (GATHER ? Cfg::kBBytes : Cfg::kKbBytes));
 #pragma unroll
           for (int j = 0; j < KPS; ++j) {
             if (j < nk) {
-              if (!GATHER && valid) {
+              if (!GATHER) {
                 if (EPI && p.pool_tp) {
                   tma_load_4d_b(a_dst + j * Cfg::kABytes, &tmA, fb, (kb + j) * BK, tp_p0, 0, tp_clip);
                 } else if (p.a_mode == A_TMA_2D) {
@@ -269,10 +261,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   }
                 }
               }
-              if (MC)  // my half of the weight rows, into both CTAs
-                tma_load_2d_mc(b_dst + (uint32_t)crank * (Cfg::kBBytes / 2), &tmR, fb, kb * BK, n0 + crank * (BN / 2), (uint16_t)3);
-              else
-                tma_load_2d_a(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * BK, n0);
+              tma_load_2d_a(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * BK, n0);
             }
           }
           if (EPI && kb == 0 && p.res != nullptr) {
@@ -290,16 +279,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_2d_a(epi0 + rb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes, &tmR, res_full0 + rb * 8, n0 + 64 * j, m0);
             }
             if (++rb == NB) { rb = 0; rph ^= 1u; }
-            if (p.l2_ahead && !p.pool_tp) {
-              // the residual comes from HBM; its smem load is only issued two tiles ahead (buffer depth), which is less
-              // than the DRAM round trip for short tiles: pull the lines of a later tile into L2 now
-              const long long ft = (long long)tile + (long long)p.l2_ahead * gridDim.x;
-              if (ft < p.num_tiles) {
-                const int fn0 = (int)(ft % p.n_tiles) * BN, fm0 = (int)(ft / p.n_tiles) * kBlockM;
-                for (int j = 0; j < BN / 64; ++j)
-                  if (fn0 + 64 * j < p.N) tma_prefetch_l2_2d(&tmR, fn0 + 64 * j, fm0);
-              }
-            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -320,17 +299,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int tc = 0;
       mbar_wait_a(full0, 0);
       for (int tile = w_first; tile < w_total; tile += w_step) {
-        const bool valid = !MC || m_tile_of(tile) * kBlockM < p.M;
-        if (MC && !valid) {
-          // no rows for this CTA: keep the ring in lock step with the peer (its B halves still land here)
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait_a(full0 + s * 8, ph);
-            umma_commit_mc(empty0 + s * 8, (uint16_t)3);
-            if (++s == STAGES) { s = 0; ph ^= 1u; }
-          }
-          if (tile + w_step < w_total) mbar_wait_a(full0 + s * 8, ph);
-          continue;
-        }
         const uint32_t acc = (uint32_t)tc & 1u;
         mbar_wait_a(tempty0 + acc * 8, (((uint32_t)tc >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -373,8 +341,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           };
           call_with_nk<KPS>(nk, issue);
-          if (MC) umma_commit_mc(empty0 + s * 8, (uint16_t)3);  // frees the slot in both CTAs of the pair
-          else    umma_commit_a(empty0 + s * 8);               // frees the smem stage once these MMAs have read it
+          umma_commit_a(empty0 + s * 8);               // frees the smem stage once these MMAs have read it
           if (last_stage) { umma_commit_a(tfull0 + acc * 8); ++tc; }  // accumulator complete
           if (!ready) {
             mbar_wait_a(full0 + ns * 8, nph);
@@ -399,7 +366,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = w_first; tile < w_total; tile += w_step) {
       const int n0 = (tile % p.n_tiles) * BN;
       const int m0 = m_tile_of(tile) * kBlockM;
-      if (MC && m0 >= p.M) continue;  // the MMA thread skipped this item too
       const int tc_this = tc++;
       const int acc = tc_this & 1;
       const uint32_t aph = (tc_this >> 1) & 1;
@@ -642,7 +608,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (EPI && warp >= 2 && warp < 2 + Cfg::kEpiWarps && lane == 0) tma_store_wait<0>();  // bulk stores fully complete
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -127,7 +127,7 @@ struct TrainArena {
 };
 
 struct TrainBlockBufs {
-  float *x1, *y1, *qkv, *u, *xb, *v, *bn_mean, *bn_invstd, *bn_s1, *bn_s2, *x2, *y2, *zp, *z, *x3;
+  float *x1, *y1, *qkv, *u, *xb, *v, *bn_mean, *bn_invstd, *x2, *y2, *zp, *z, *x3;
 };
 struct TrainBufs {
   float *feat, *mag, *x0;
@@ -137,6 +137,7 @@ struct TrainBufs {
   int* idx;
   float *g0, *g1, *g2, *gw0, *gw1;     // gradient ping-pong [ntok, max_dim] x3, [ntok, max_wide] x2
   float *t1, *t2, *wt;                 // transposes: [max_wide or max rows, ntok], [max cols, ntok]; transformed weights
+  float *bn_part;                      // BatchNorm column-reduction partials [chunks][2][C] (chunks * C <= 592 * 32)
 };
 
 static void head_train_layout(const vad_head_train* h, int n_videos, int ncrops, int T, TrainArena& a, TrainBufs& b) {
@@ -158,7 +159,7 @@ static void head_train_layout(const vad_head_train* h, int n_videos, int ncrops,
     } else {
       q.xb = a.take(ntok * d);
       q.v = a.take(ntok * k.inner);
-      q.bn_mean = a.take(d); q.bn_invstd = a.take(d); q.bn_s1 = a.take(d); q.bn_s2 = a.take(d);
+      q.bn_mean = a.take(d); q.bn_invstd = a.take(d);
     }
     q.u = a.take(ntok * k.inner);
     q.x2 = a.take(ntok * d);
@@ -195,6 +196,7 @@ static void head_train_layout(const vad_head_train* h, int n_videos, int ncrops,
   b.t1 = a.take(rows * (size_t)ntok);
   b.t2 = a.take(rows * (size_t)ntok);
   b.wt = a.take(h->max_weight);
+  b.bn_part = a.take((size_t)2 * 592 * 32);
 }
 
 extern "C" int32_t vad_head_train_workspace_bytes(const vad_head_train_t* h, int32_t n_videos, int32_t ncrops, int32_t t, uint64_t* bytes) {
@@ -270,10 +272,10 @@ extern "C" int32_t vad_head_train_step(vad_head_train_t* h, const float* params_
         TRAIN_LAUNCHED();
       } else {
         float* rm = bn_stats_dev + k.bn_stat;
-        VAD_CUDA_CHECK(cudaMemsetAsync(q.bn_s1, 0, 2 * (size_t)((d * 4 + 1023) / 1024 * 1024), st));   // bn_s1 | bn_s2 are adjacent arena granules
-        head_bn_reduce_kernel<<<dim3((d + 31) / 32, red_chunks(d)), dim3(32, 8), 0, st>>>(q.x1, nullptr, ntok, d, 0, nullptr, nullptr, q.bn_s1, q.bn_s2);
+        const int bn_chunks = red_chunks(d);
+        head_bn_reduce_kernel<<<dim3((d + 31) / 32, bn_chunks), dim3(32, 8), 0, st>>>(q.x1, nullptr, ntok, d, 0, nullptr, nullptr, B.bn_part);
         TRAIN_LAUNCHED();
-        head_bn_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(q.bn_s1, q.bn_s2, ntok, d, 1e-5f, 0.1f, q.bn_mean, q.bn_invstd, rm, rm + d);
+        head_bn_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(B.bn_part, bn_chunks, ntok, d, 1e-5f, 0.1f, q.bn_mean, q.bn_invstd, rm, rm + d);
         TRAIN_LAUNCHED();
         head_bn_apply_kernel<<<ew_grid(ntok * d), 256, 0, st>>>(q.x1, q.bn_mean, q.bn_invstd, P + k.bn_g, P + k.bn_b, ntok, d, q.xb);
         TRAIN_LAUNCHED();
@@ -395,7 +397,10 @@ extern "C" int32_t vad_head_train_step(vad_head_train_t* h, const float* params_
                                                                                                               k.heads, c.local_aggr_kernel);
         TRAIN_LAUNCHED();
         HEAD_TRY(gemm_bwd(B.gw1, q.xb, k.v_w, 0, false, 1, d, k.inner, ga, nullptr));                         // ga = d xb
-        head_bn_reduce_kernel<<<dim3((d + 31) / 32, red_chunks(d)), dim3(32, 8), 0, st>>>(q.x1, ga, ntok, d, 1, q.bn_mean, q.bn_invstd, D + k.bn_b, D + k.bn_g);
+        const int bn_chunks = red_chunks(d);
+        head_bn_reduce_kernel<<<dim3((d + 31) / 32, bn_chunks), dim3(32, 8), 0, st>>>(q.x1, ga, ntok, d, 1, q.bn_mean, q.bn_invstd, B.bn_part);
+        TRAIN_LAUNCHED();
+        head_bn_grad_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(B.bn_part, bn_chunks, d, D + k.bn_b, D + k.bn_g);
         TRAIN_LAUNCHED();                                                                                    // d beta = sum dy, d gamma = sum dy xhat
         head_bn_bwd_apply_kernel<<<ew_grid(ntok * d), 256, 0, st>>>(q.x1, ga, q.bn_mean, q.bn_invstd, P + k.bn_g, D + k.bn_b, D + k.bn_g, gb, ntok, d, gx);
         TRAIN_LAUNCHED();                                                                                    // gx = d x1

@@ -250,12 +250,15 @@ __global__ void __launch_bounds__(256) head_relpos_bwd_weight_kernel(const float
 }
 
 // BatchNorm1d in train mode (FocusAttention.norm, modeling_mgfn.py:178): per-channel statistics over all tokens.
-// grid (C / 32, token chunks), block (32, 8); partial sums are atomically added into zeroed [C] accumulators:
-//   mode 0: acc1 += sum x,  acc2 += sum x^2          (head_bn_finalize_kernel turns them into mean / invstd)
-//   mode 1: acc1 += sum dy, acc2 += sum dy * xhat    (d beta, d gamma)
+// grid (C / 32, token chunks), block (32, 8); every block writes its two partial sums to part[chunk][2][C] and a second
+// kernel adds the chunks in a fixed order in double precision -- no atomics: the batch statistics (and with them the whole
+// train-mode forward and the loss) are bit-reproducible run to run, and E[x^2] - E[x]^2 does not amplify summation-order
+// noise (with fp32 atomics the loss terms moved by 1e-3 between two runs on the same input).
+//   mode 0: sum x,  sum x^2          (head_bn_finalize_kernel turns them into mean / invstd)
+//   mode 1: sum dy, sum dy * xhat    (d beta, d gamma: head_bn_grad_finalize_kernel)
 __global__ void __launch_bounds__(256) head_bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long ntok, int C, int mode,
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                             float* __restrict__ acc1, float* __restrict__ acc2) {
+                                                             float* __restrict__ part) {
   __shared__ float ra[8][33], rb[8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
@@ -280,24 +283,36 @@ __global__ void __launch_bounds__(256) head_bn_reduce_kernel(const float* __rest
     float sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sa += ra[i][tx]; sb += rb[i][tx]; }
-    atomicAdd(acc1 + c, sa);
-    atomicAdd(acc2 + c, sb);
+    part[((size_t)blockIdx.y * 2 + 0) * C + c] = sa;
+    part[((size_t)blockIdx.y * 2 + 1) * C + c] = sb;
   }
 }
-// sums -> batch mean / invstd (biased variance) and the running-statistics update (momentum, unbiased variance, as torch)
-__global__ void head_bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long ntok, int C, float eps, float momentum,
+// chunk partials -> batch mean / invstd (biased variance) and the running-statistics update (momentum, unbiased variance, as torch)
+__global__ void head_bn_finalize_kernel(const float* __restrict__ part, int chunks, long long ntok, int C, float eps, float momentum,
                                         float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float mu = sum[c] / (float)ntok;
-  float var = sumsq[c] / (float)ntok - mu * mu;
-  var = var > 0.f ? var : 0.f;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < chunks; ++k) { s += (double)part[((size_t)k * 2) * C + c]; ss += (double)part[((size_t)k * 2 + 1) * C + c]; }
+  const double mud = s / (double)ntok;
+  double vard = ss / (double)ntok - mud * mud;
+  vard = vard > 0.0 ? vard : 0.0;
+  const float mu = (float)mud, var = (float)vard;
   mean[c] = mu;
   invstd[c] = rsqrtf(var + eps);
   if (run_mean) {
     run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mu;
     run_var[c] = (1.f - momentum) * run_var[c] + momentum * (ntok > 1 ? var * (float)ntok / (float)(ntok - 1) : var);
   }
+}
+// chunk partials of mode 1 -> s1 = sum dy (= d beta), s2 = sum dy * xhat (= d gamma), fixed summation order
+__global__ void head_bn_grad_finalize_kernel(const float* __restrict__ part, int chunks, int C, float* __restrict__ s1, float* __restrict__ s2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int k = 0; k < chunks; ++k) { a += part[((size_t)k * 2) * C + c]; b += part[((size_t)k * 2 + 1) * C + c]; }
+  s1[c] = a;
+  s2[c] = b;
 }
 // y = (x - mean) * invstd * g + b
 __global__ void head_bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,

@@ -106,11 +106,6 @@ __device__ __forceinline__ void tma_load_im2col_5d(void* smem_dst, const CUtenso
       "r"(h), "r"(d), "r"(n), "h"(off_w), "h"(off_h), "h"(off_d)
       : "memory");
 }
-// TMA prefetch into L2 only (no shared-memory destination, no barrier): warms the lines a later tile will load
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -192,7 +187,7 @@ __device__ __forceinline__ void tma_load_im2col_5d_a(uint32_t dst, const CUtenso
       : "memory");
 }
 
-// ---- thread-block clusters (TMA multicast of a shared operand tile across the CTAs of a cluster)
+// ---- thread-block clusters (CTA pairs, conv_pair.cuh)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -201,22 +196,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// the box lands at the same CTA-relative shared-memory offset in every CTA of cta_mask and signals the mbarrier at the
-// same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-// arrive on the mbarrier at this offset in every CTA of cta_mask once the previously issued MMAs have completed
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
-}
-
 // ---- programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
 // (barrier init, TMEM allocation, loads of constant weights) while its predecessor in the stream is still draining;
 // griddep_wait() blocks until the predecessor grid has completed and its writes are visible.  Both are no-ops for a

