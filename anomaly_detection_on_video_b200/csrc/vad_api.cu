@@ -159,6 +159,15 @@ struct vad_plan {
   std::vector<OpRuntime> rt;
   const void* bound_x = nullptr;
   void* bound_ws = nullptr;
+  // CUDA graph of one forward (small batches: ~55 launches of 5-15 us each are fixed cost; VAD_GRAPH=0|1 overrides the
+  // batch <= 32 default).  Captured on an internal stream at the second forward of a binding (the first one sets the
+  // kernels' shared-memory attributes), launched into the caller's stream; a re-bind or re-configure drops it.
+  int direct_runs = 0;            // forwards launched op by op since the last bind
+  cudaGraphExec_t graph_exec = nullptr;
+  float* graph_feat = nullptr;
+  int feat_misses = 0;            // forwards whose feature pointer differed from the captured one
+  cudaStream_t cap_stream = nullptr;
+  bool graph_failed = false;
   double flops = 0.0;
   int feat_c = 0;
   EncodeTiledFn encode_tiled = nullptr;
@@ -254,7 +263,12 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   return VAD_OK;
 }
 
-extern "C" void vad_plan_destroy(vad_plan_t* plan) { delete plan; }
+extern "C" void vad_plan_destroy(vad_plan_t* plan) {
+  if (!plan) return;
+  if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
+  if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
+  delete plan;
+}
 
 static int pool_out_same(int in, int s) { return (in + s - 1) / s; }
 
@@ -675,6 +689,11 @@ extern "C" double vad_plan_flops(const vad_plan_t* p) { return (p && p->configur
 
 // Slot shapes change while the op list runs (slots are reused), so shapes are re-derived here in
 // op order; only pointers and tensor maps are (re)bound.
+static void drop_graph(vad_plan* p) {
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+  p->direct_runs = 0;
+}
+
 static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) {
   auto slot_ptr = [&](int s) -> uint8_t* {
     return s == 0 ? const_cast<uint8_t*>(static_cast<const uint8_t*>(x)) : static_cast<uint8_t*>(ws) + p->slots[s].offset;
@@ -953,6 +972,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
   p->fold_pending = false;
   p->bound_x = x;
   p->bound_ws = ws;
+  drop_graph(p);
   return VAD_OK;
 }
 
@@ -1047,20 +1067,8 @@ static int grid_for(long long total, int threads, int cap = 148 * 32) {
   return (int)g;
 }
 
-extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* workspace_dev, uint64_t workspace_bytes,
-                                    float* feat_out_dev, void* stream) {
-  if (!p || !p->configured) return fail(VAD_ERR_NOT_CONFIGURED, "vad_plan_forward: plan is not configured");
-  if (!x_dev || (!workspace_dev && p->ws_bytes)) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_forward: null pointer");
-  if (workspace_bytes < p->ws_bytes)
-    return fail(VAD_ERR_WORKSPACE_TOO_SMALL, "workspace %llu < required %llu", (unsigned long long)workspace_bytes,
-                (unsigned long long)p->ws_bytes);
-  if (((uintptr_t)x_dev & 15) || ((uintptr_t)workspace_dev & 1023))
-    return fail(VAD_ERR_INVALID_ARGUMENT, "x must be 16 B aligned and the workspace 1024 B aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->bound_x != x_dev || p->bound_ws != workspace_dev) {
-    int32_t rc = bind_plan(p, x_dev, workspace_dev, st);
-    if (rc != VAD_OK) return rc;
-  }
+// every op of the table, in order, into stream st (directly, or inside a stream capture)
+static int32_t run_ops(vad_plan* p, const void* x_dev, void* workspace_dev, float* feat_out_dev, cudaStream_t st) {
   auto mark = [&]() -> cudaError_t {
     if (!p->profiling) return cudaSuccess;
     cudaEvent_t ev;
@@ -1084,8 +1092,10 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
         static long long* tail_dbg = nullptr;
         static const bool want_dbg = getenv("VAD_TAIL_DEBUG") != nullptr;
         if (want_dbg && !tail_dbg) { cudaMalloc(&tail_dbg, 2 * 4 * 32 * 8); cudaMemset(tail_dbg, 0, 2 * 4 * 32 * 8); }
-        auto launch_tail = [&](auto kern, int smem) -> cudaError_t {
-          cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        auto launch_tail = [&](auto kern, int smem, auto mode_tag) -> cudaError_t {
+          static bool attr = false;   // one per instantiation of this generic lambda: mode_tag tells the two kernels (same pointer type) apart
+          cudaError_t le = cudaSuccess;
+          if (!attr) { le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = (le == cudaSuccess); }
           if (le != cudaSuccess) return le;
           TailParams tp = r.tlp;
           tp.dbg = want_dbg ? tail_dbg + (r.tail == 2 ? 0 : 128) : nullptr;
@@ -1104,8 +1114,8 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
           }
           return le;
         };
-        if (r.tail == 2)            e = launch_tail(conv_tail_kernel<true, 1, 2>, TailCfg<true, 1, 2>::kSmemBytes);
-        else                        e = launch_tail(conv_tail_kernel<false, 2, 3>, TailCfg<false, 2, 3>::kSmemBytes);
+        if (r.tail == 2)            e = launch_tail(conv_tail_kernel<true, 1, 2>, TailCfg<true, 1, 2>::kSmemBytes, std::integral_constant<int, 2>{});
+        else                        e = launch_tail(conv_tail_kernel<false, 2, 3>, TailCfg<false, 2, 3>::kSmemBytes, std::integral_constant<int, 1>{});
       } else if (r.stem) {
         static bool stem_attr = false;
         if (!stem_attr) {
@@ -1193,6 +1203,61 @@ extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* work
     if (p->profiling && (int)i >= pf0 && (int)i < pf1) { p->prof_flops[i] += p->op_flops[i]; p->prof_bytes[i] += p->op_bytes[i]; }
   }
   return VAD_OK;
+}
+
+extern "C" int32_t vad_plan_forward(vad_plan_t* p, const void* x_dev, void* workspace_dev, uint64_t workspace_bytes,
+                                    float* feat_out_dev, void* stream) {
+  if (!p || !p->configured) return fail(VAD_ERR_NOT_CONFIGURED, "vad_plan_forward: plan is not configured");
+  if (!x_dev || (!workspace_dev && p->ws_bytes)) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_plan_forward: null pointer");
+  if (workspace_bytes < p->ws_bytes)
+    return fail(VAD_ERR_WORKSPACE_TOO_SMALL, "workspace %llu < required %llu", (unsigned long long)workspace_bytes,
+                (unsigned long long)p->ws_bytes);
+  if (((uintptr_t)x_dev & 15) || ((uintptr_t)workspace_dev & 1023))
+    return fail(VAD_ERR_INVALID_ARGUMENT, "x must be 16 B aligned and the workspace 1024 B aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->bound_x != x_dev || p->bound_ws != workspace_dev) {
+    int32_t rc = bind_plan(p, x_dev, workspace_dev, st);
+    if (rc != VAD_OK) return rc;
+  }
+  const char* graph_env = getenv("VAD_GRAPH");   // 0: never, 1: any batch; unset: batch <= 32
+  const int gmode = graph_env ? atoi(graph_env) : -1;
+  const bool want_graph = !p->profiling && !p->graph_failed && !getenv("VAD_TAIL_DEBUG") && !getenv("VAD_STEM_CLOCKS") &&
+                          (gmode == 1 || (gmode < 0 && p->batch <= 32));
+  if (want_graph && p->graph_exec && p->graph_feat == feat_out_dev) {
+    VAD_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
+    return VAD_OK;
+  }
+  if (want_graph && p->graph_exec && ++p->feat_misses > 2) {
+    // the caller hands out a different feature pointer every forward: a graph bakes it in, so stop re-capturing
+    drop_graph(p);
+    p->graph_failed = true;
+    ++p->direct_runs;
+    return run_ops(p, x_dev, workspace_dev, feat_out_dev, st);
+  }
+  if (want_graph && p->direct_runs >= 1) {
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    if (!p->cap_stream) VAD_CUDA_CHECK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+      const int32_t rc = run_ops(p, x_dev, workspace_dev, feat_out_dev, p->cap_stream);
+      ce = cudaStreamEndCapture(p->cap_stream, &graph);
+      if (rc != VAD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    }
+    if (ce == cudaSuccess) ce = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce == cudaSuccess) {
+      p->graph_feat = feat_out_dev;
+      VAD_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
+      return VAD_OK;
+    }
+    // capture not possible here (old driver, ...): remember and launch op by op from now on
+    cudaGetLastError();
+    p->graph_exec = nullptr;
+    p->graph_failed = true;
+  }
+  ++p->direct_runs;
+  return run_ops(p, x_dev, workspace_dev, feat_out_dev, st);
 }
 
 extern "C" int32_t vad_plan_profile_select(vad_plan_t* p, int32_t first_op, int32_t n_ops) {

@@ -148,6 +148,7 @@ class BackbonePlan:
                                        ctypes.c_void_p(self.params.data_ptr()), self.params.numel(), in_channels,
                                        in_pad_left, dev_index), "vad_plan_create")
         self._cfg: Optional[Tuple[int, int, int, int]] = None
+        self._feat_buf: Optional[torch.Tensor] = None
         self._ws: Optional[torch.Tensor] = None
         self._ws_ptr = 0
         self._ws_bytes = 0
@@ -229,12 +230,19 @@ class BackbonePlan:
         b, t, h, wp, _ = x_stem.shape
         self.configure(b, t, h, wp - 8 if self.in_channels == 0 else wp)
         has_feat = any(op.kind == _lib.VAD_OP_AVGPOOL for op in self.ops)
+        clone = False
         if has_feat and out is None:
-            out = torch.empty(b, self.feature_dim(), dtype=torch.float32, device=self.device)
+            # a plan-owned result buffer: a small-batch forward is replayed as a CUDA graph (vad_plan_forward), which bakes
+            # the feature pointer in; the caller gets a copy
+            if self._feat_buf is None or self._feat_buf.shape[0] != b:
+                self._feat_buf = torch.empty(b, self.feature_dim(), dtype=torch.float32, device=self.device)
+            out, clone = self._feat_buf, True
         check(self.lib.vad_plan_forward(self._h, ctypes.c_void_p(x_stem.data_ptr()), ctypes.c_void_p(self._ws_ptr),
                                         self._ws_bytes, ctypes.c_void_p(out.data_ptr()) if has_feat else None,
                                         ctypes.c_void_p(_stream_ptr(self.device))), "vad_plan_forward")
-        return out if has_feat else None
+        if not has_feat:
+            return None
+        return out.clone() if clone else out
 
 
 class Tf32Plan:

@@ -43,6 +43,14 @@ MIXED: Tuple[Tuple[str, int, Tuple[int, int, int, int, int, int]], ...] = (
     ("Mixed_5c", 832, (384, 192, 384, 48, 128, 128)),
 )
 # max-pools that sit in front of a Mixed block: name -> (kernel, stride)
+# Branch temporaries whose channel count would put the following 3x3x3 conv on a narrow k-block path are widened with zero
+# channels (zero weight rows in the producing 1x1x1 conv: relu(0 * x + 0) = 0; zero weight columns in the consumer): the
+# consumer then contracts whole 64-channel k-blocks through the im2col TMA path.  Measured per 160 clip-crops (round 2):
+# Cin = 144 (16-wide k-blocks, one 32-byte sector per TMA row) ran at 0.26 of the tensor peak, 112 at 0.28, 16 at 0.05, 24 on
+# the cp.async gather at 0.08; a 64-multiple Cin reaches 0.8, so even 4 x the FLOPs (16 -> 64) is the faster launch.  Internal
+# to a Mixed block: results are unchanged (the extra terms are exact zeros).
+BRANCH_PAD = {16: 64, 24: 64, 48: 64, 112: 128, 144: 192, 160: 192}
+
 POOL_BEFORE = {"Mixed_4b": ("MaxPool3d_4a_3x3", (3, 3, 3), (2, 2, 2)), "Mixed_5b": ("MaxPool3d_5a_2x2", (2, 2, 2), (2, 2, 2))}
 
 
@@ -87,6 +95,7 @@ class InceptionI3d(_NativeBackbone):
         if in_channels != 3:
             raise NotImplementedError("only the RGB stream is built (the flow stream has 2 input channels)")
         self.fuse_stem_pool = False
+        self.pad_branches = True   # BRANCH_PAD; False keeps every temporary at its nominal width (A/B and tests)
         self.Conv3d_1a_7x7 = Unit3D(3, 64, (7, 7, 7), (2, 2, 2))
         self.MaxPool3d_2a_3x3 = MaxPool3dSamePadding((1, 3, 3), (1, 2, 2))
         self.Conv3d_2b_1x1 = Unit3D(64, 64)
@@ -106,8 +115,21 @@ class InceptionI3d(_NativeBackbone):
                 nn.init.zeros_(m.bias)
 
     def _unit(self, pk: ParamPacker, u: Unit3D, src: int, dst: int, name: str, fold_w: bool = False, off: int = 0,
-              total: int = 0) -> Op:
+              total: int = 0, cin_pad: int = 0, cout_pad: int = 0) -> Op:
         scale, shift = fold_bn(u.bn.weight, u.bn.bias, u.bn.running_mean, u.bn.running_var, u.bn.eps)
+        if self.precision != "tf32" and (cin_pad or cout_pad):
+            # zero-widened branch temporary (BRANCH_PAD): extra output channels of the producer / input channels of the consumer
+            conv = u.conv3d
+            w = conv.weight.detach().float()
+            co, ci = cout_pad or conv.out_channels, cin_pad or conv.in_channels
+            wp = torch.zeros(co, ci, *conv.kernel_size, dtype=torch.float32, device=w.device)
+            wp[:conv.out_channels, :conv.in_channels] = w
+            sc = torch.zeros(co, dtype=torch.float32, device=w.device); sc[:conv.out_channels] = scale
+            sh = torch.zeros(co, dtype=torch.float32, device=w.device); sh[:conv.out_channels] = shift
+            w_off, s_off, b_off = pk.add_conv(wp, sc, sh)
+            flags = _lib.VAD_FLAG_RELU | _lib.VAD_FLAG_CONV_SAME | (_lib.VAD_FLAG_FORCE_GATHER if self.force_gather else 0)
+            return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, cin=ci, cout=co, kernel=tuple(conv.kernel_size), stride=tuple(conv.stride),
+                      pad=(0, 0, 0), flags=flags, dst_c_off=off, dst_c_total=total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
         if self.precision == "tf32":
             conv = u.conv3d
             cin = (conv.in_channels + 3) // 4 * 4
@@ -151,10 +173,12 @@ class InceptionI3d(_NativeBackbone):
             total = outs[0] + outs[2] + outs[4] + outs[5]
             # torch.cat([b0, b1, b2, b3], dim=1): every branch writes its channel slice of the output in place
             ops.append(self._unit(pk, m.b0, cur, nxt, name + ".b0", off=0, total=total))
-            ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a"))
-            ops.append(self._unit(pk, m.b1b, T1, nxt, name + ".b1b", off=outs[0], total=total))
-            ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a"))
-            ops.append(self._unit(pk, m.b2b, T2, nxt, name + ".b2b", off=outs[0] + outs[2], total=total))
+            p1 = BRANCH_PAD.get(outs[1], 0) if self.pad_branches else 0
+            p2 = BRANCH_PAD.get(outs[3], 0) if self.pad_branches else 0
+            ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a", cout_pad=p1))
+            ops.append(self._unit(pk, m.b1b, T1, nxt, name + ".b1b", off=outs[0], total=total, cin_pad=p1))
+            ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a", cout_pad=p2))
+            ops.append(self._unit(pk, m.b2b, T2, nxt, name + ".b2b", off=outs[0] + outs[2], total=total, cin_pad=p2))
             ops.append(self._pool(m.b3a, cur, T3, name + ".b3a"))
             ops.append(self._unit(pk, m.b3b, T3, nxt, name + ".b3b", off=outs[0] + outs[2] + outs[4], total=total))
             cur = nxt

@@ -44,6 +44,10 @@ N_FRAMES, SRC_H, SRC_W = 2000, 240, 320
 CLIPS, CROPS = 125, 10
 FLOP_PER_CLIP = 2 * 16_414_572_544  # I3Res50 conv MACs per 16x224x224 clip-crop
 WORKLOAD = "i3res50_tencrop_one_ucf_video_2000f_240x320"
+# backbone -> (module, class, conv FLOPs per 16x224x224 clip-crop)
+BACKBONES = {"i3res50": ("i3d", "I3Res50", FLOP_PER_CLIP),
+             "inception": ("inception", "InceptionI3d", 55_575_138_304),
+             "i3d_8x8_r50": ("ptv_resnet", "I3D8x8R50", 113_600_000_000)}
 
 
 def load_peaks():
@@ -55,11 +59,11 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
-def bench_config(cpb: int, world: int) -> dict:
+def bench_config(cpb: int, world: int, backbone: str = "i3res50") -> dict:
     """The workload description both arms print (BASELINE.json configs[1])."""
-    return {"workload": WORKLOAD, "frames": N_FRAMES, "frame_hw": [SRC_H, SRC_W], "clips_per_video": CLIPS,
+    return {"workload": WORKLOAD.replace("i3res50", backbone), "frames": N_FRAMES, "frame_hw": [SRC_H, SRC_W], "clips_per_video": CLIPS,
             "crops": CROPS, "clips_per_batch": cpb, "videos_per_step_per_gpu": 1, "parallelism": f"dp{world}",
-            "flop_per_clip": FLOP_PER_CLIP, "weights": "random init under a fixed seed (constructor init, perturbed BatchNorm statistics)",
+            "flop_per_clip": BACKBONES[backbone][2], "weights": "random init under a fixed seed (constructor init, perturbed BatchNorm statistics)",
             "cache": "inputs larger than L2 (461 MB of frames, >4 GB of activations per batch; no flush needed)"}
 
 
@@ -232,6 +236,10 @@ def main():
     ap.add_argument("--clips-per-batch", type=int, default=16,
                     help="clips per backbone forward (x10 crops); 16 is the reference's DataLoader batch (extract_features.py:79)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--backbone", default="i3res50", choices=sorted(BACKBONES),
+                    help="backbone of the headline line: i3res50 (BASELINE.json's, default), inception (north_star's InceptionV1-3D, "
+                         "1024-d features) or i3d_8x8_r50 (the reference CLI's default, pytorchvideo I3D-R50); the latter two have no "
+                         "CPU reference arm (not in the reference / third party) and print cpu_baseline null")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -292,8 +300,11 @@ def main():
                     m.bias.copy_(0.1 * torch.randn(m.num_features, generator=g))
         return module
 
+    import importlib
+
+    bb_mod, bb_cls, flop_per_clip = BACKBONES[args.backbone]
     torch.manual_seed(0)
-    model = seeded(I3Res50(), 1)
+    model = seeded(getattr(importlib.import_module("anomaly_detection_on_video_b200." + bb_mod), bb_cls)(), 1)
     model.eval().to(dev)
 
     frames_host = torch.from_numpy(synthetic_frames(N_FRAMES, 1000 + rank, "noise")).pin_memory()
@@ -473,6 +484,8 @@ def main():
     # evaluate the loss.  Reported beside the extraction numbers, never mixed into `value`.
     head_info = None
     try:
+        if args.backbone != "i3res50":
+            raise RuntimeError("skipped: the MGFN head takes the 2048-d I3Res50 features")
         from anomaly_detection_on_video_b200.dataset import add_magnitude
         from anomaly_detection_on_video_b200.mgfn import MGFNConfig, MGFNForVideoAnomalyDetection
         torch.manual_seed(2)
@@ -553,9 +566,10 @@ def main():
     # ---- the backbone north_star names (InceptionV1-3D; not in the reference): same clip-crop batch, backbone only,
     # reported beside the I3Res50 numbers, never mixed into `value`
     inception_info = None
-    if rank == 0:
+    if rank == 0 and args.backbone == "i3res50" and os.environ.get("VAD_BENCH_NO_INCEPTION") != "1":
         try:
             from anomaly_detection_on_video_b200.inception import InceptionI3d
+            inc_flop = BACKBONES["inception"][2]
             torch.manual_seed(3)
             inc = seeded(InceptionI3d(), 4)
             inc.eval().to(dev)
@@ -566,18 +580,49 @@ def main():
             i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(dev)
             i0.record()
-            for _ in range(4 * K):
+            n_fw = min(4 * K, 200)
+            for _ in range(n_fw):
                 inc.forward_stem_layout(xs)
             i1.record()
             torch.cuda.synchronize(dev)
-            inc_ms = i0.elapsed_time(i1) / (4 * K)
+            inc_ms = i0.elapsed_time(i1) / n_fw
+            del xs
+            # the same 2,000-frame video through the same public calls as the headline: frames resident -> features -> segments,
+            # and end to end from pinned host frames with the features / segments read back (extract_stream)
+            n_v = max(3, min(K, 20))
+            for _ in range(2):
+                segment_mean(extract_clip_features(ds, inc, dev, clips_per_batch=cpb, strict_compat=False, as_numpy=False), 32)
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(n_v):
+                seg_i = segment_mean(extract_clip_features(ds, inc, dev, clips_per_batch=cpb, strict_compat=False, as_numpy=False), 32)
+            v1.record()
+            torch.cuda.synchronize(dev)
+            inc_res = n_v * CLIPS * CROPS / (v0.elapsed_time(v1) / 1e3)
+            for _ in extract_stream((frames_host for _ in range(2)), inc, dev, clips_per_batch=cpb):
+                pass
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            for fi, si in extract_stream((frames_host for _ in range(n_v)), inc, dev, clips_per_batch=cpb):
+                assert fi.shape == (CLIPS, CROPS, 1024) and si.shape == (CROPS, 32, 1024)
+            w1.record()
+            torch.cuda.synchronize(dev)
+            inc_e2e = n_v * CLIPS * CROPS / (w0.elapsed_time(w1) / 1e3)
             inception_info = {"model": "InceptionI3d (extract_features, 1024-d)", "clip_crops_per_forward": nb, "ms_per_forward": inc_ms,
-                              "clips_per_s": nb / (inc_ms / 1e3), "flop_per_clip": 55575138304,
-                              "tflops": nb * 55575138304 / (inc_ms / 1e3) / 1e12,
-                              "frac_of_sustained_peak": nb * 55575138304 / (inc_ms / 1e3) / 1e12 / load_peaks()["bf16_sustained"],
+                              "clips_per_s": nb / (inc_ms / 1e3), "flop_per_clip": inc_flop,
+                              "tflops": nb * inc_flop / (inc_ms / 1e3) / 1e12,
+                              "frac_of_sustained_peak": nb * inc_flop / (inc_ms / 1e3) / 1e12 / load_peaks()["bf16_sustained"],
                               "launches_per_forward": inc.plan(dev).num_launches, "n_gpus": 1,
-                              "note": "backbone forward from the bf16 stem layout, HBM-resident input, rank 0 only"}
-            del inc, xs
+                              "video": {"steps": n_v, "value": inc_res, "unit": UNIT,
+                                        "tflops_whole_step": inc_res * inc_flop / 1e12,
+                                        "frac_of_sustained_peak": inc_res * inc_flop / 1e12 / load_peaks()["bf16_sustained"],
+                                        "e2e": {"value": inc_e2e, "unit": UNIT, "h2d_bytes_per_step": int(frames_host.numel()),
+                                                "d2h_bytes_per_step": int(fi.numel() * 4 + si.numel() * 4)},
+                                        "note": "the headline's 2,000-frame video (preprocess + backbone + segment mean) with this backbone: "
+                                                "frames resident in HBM, and end to end from pinned host frames; "
+                                                "`bench.py --backbone inception` prints the full line (and scales with --gpus)"},
+                              "note": "ms_per_forward / clips_per_s: backbone forward from the bf16 stem layout, HBM-resident input; rank 0 only"}
+            del inc
         except Exception as exc:
             inception_info = {"error": f"{type(exc).__name__}: {exc}"}
 
@@ -595,7 +640,7 @@ def main():
         conv_ms = sum(p["ms"] for p in conv)
         conv_flops = sum(p["flops"] for p in conv)
         all_ms = sum(p["ms"] for p in prof) or 1.0
-        tflops_step = value * FLOP_PER_CLIP / 1e12 / world   # per GPU: every conv FLOP of the step / the whole step time
+        tflops_step = value * flop_per_clip / 1e12 / world   # per GPU: every conv FLOP of the step / the whole step time
         # per-kernel table (separate, fully event-bracketed pass of the same K steps): one row per layer group, each with
         # its tensor fraction AND its algorithmic-HBM fraction, so an HBM-bound layer shows as such
         def group_of(name):
@@ -631,12 +676,12 @@ def main():
         # preprocessing / pools; no single launch dominates (the largest, the stem, is ~19 %), so the number that is
         # graded is all conv FLOPs over the device time of the K timed steps -- everything else counts against it.
         roofline = {
-            "bound": "tensor", "kernel": "whole step: preprocess + stem + 52 conv ops + pools + segment mean (conv FLOPs / step time)",
+            "bound": "tensor", "kernel": f"whole step ({args.backbone}): preprocess + every op-table launch + segment mean (conv FLOPs / step time)",
             "achieved": tflops_step, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": tflops_step / peaks["bf16_sustained"], "frac_of_burst": tflops_step / peaks["bf16_burst"],
             "traffic": None,
             "peak_source": f"{peaks['source']} bf16 sustained (kernels timed inside a long step); burst {peaks['bf16_burst']}",
-            "flops_per_step": CLIPS * CROPS * FLOP_PER_CLIP, "avg_step_ms": ms / K,
+            "flops_per_step": CLIPS * CROPS * flop_per_clip, "avg_step_ms": ms / K,
             "traffic_note": "per-kernel DRAM bytes of this build: profiles/ (ncu --set full captures); not a constant copied into the line",
             "stem_in_timed_region": ({"avg_launch_ms": stem[0]["ms"] / stem[0]["calls"], "launches_timed": int(stem[0]["calls"]),
                                       "tflops": stem[0]["flops"] / (stem[0]["ms"] / 1e3) / 1e12,
@@ -644,7 +689,7 @@ def main():
             "per_kernel": per_kernel,
         }
         cpu_baseline = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.backbone == "i3res50":
             os.sched_setaffinity(0, cpus_at_start)  # the CPU baseline gets every core the box allows
             v, d = cpu_reference_run(steps=6, warmup=1, clips_per_step=4)  # ~15-25 s of CPU work
             cpu_baseline = {"value": v, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": d["sample"],
@@ -669,7 +714,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": bench_config(cpb, world),
+            "config": bench_config(cpb, world, args.backbone),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames_host.numel()),
                     "d2h_bytes_per_step": int(f_host.numel() * 4 + s_host.numel() * 4), "ms_per_step": ms_e2e / K,
                     "wall_ms_per_step": wall_e2e / K,
@@ -687,7 +732,7 @@ def main():
             "head": head_info,
             "inception": inception_info,
             "host": host_info,
-            "tflops_whole_step": value * FLOP_PER_CLIP / 1e12,
+            "tflops_whole_step": value * flop_per_clip / 1e12,
             "step_breakdown": {"step_ms": ms / K, "profiled_pass_step_ms": (ms_profiled / K) if prof else None,
                                "backbone_kernels_ms": (sum(p["ms"] for p in prof) / K) if prof else None,
                                "note": "backbone_kernels_ms = CUDA-event time of the op-table launches in the separate fully "

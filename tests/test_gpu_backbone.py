@@ -225,3 +225,32 @@ def test_extract_stream_matches_per_video_extraction(model, cuda_device):
     assert len(got) == len(want)
     for (gf, gs), (wf, ws) in zip(got, want):
         assert torch.equal(gf, wf) and torch.equal(gs, ws)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_direct_launches(cuda_device, monkeypatch):
+    """vad_plan_forward captures the op table of a small batch into a CUDA graph at the second forward of a binding and
+    replays it afterwards (VAD_GRAPH: 0 never, 1 any batch, unset batch <= 32).  Same kernels, same arguments: same bits,
+    for the capturing forward, for replays, for new input values in the bound buffer, and after a re-bind."""
+    from anomaly_detection_on_video_b200.i3d import I3Res50
+
+    m = I3Res50()
+    m.load_state_dict(O.seeded_state_dict(0), strict=True)
+    m = m.eval().to(cuda_device)
+    gen = torch.Generator().manual_seed(11)
+    xs = [torch.randn(2, 16, 224, 232, 4, generator=gen).to(torch.bfloat16).to(cuda_device) for _ in range(2)]
+    monkeypatch.setenv("VAD_GRAPH", "0")
+    want = [m.forward_stem_layout(x).clone() for x in xs]
+    torch.cuda.synchronize()
+    monkeypatch.setenv("VAD_GRAPH", "1")
+    buf = xs[0].clone()
+    outs = [m.forward_stem_layout(buf).clone() for _ in range(4)]      # direct, capture + launch, replay, replay
+    buf.copy_(xs[1])
+    outs2 = [m.forward_stem_layout(buf).clone() for _ in range(2)]     # replay on new values in the same buffer
+    other = xs[0].clone()
+    outs3 = [m.forward_stem_layout(other).clone() for _ in range(3)]   # re-bind: direct, capture, replay
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, want[0]) for o in outs)
+    assert all(torch.equal(o, want[1]) for o in outs2)
+    assert all(torch.equal(o, want[0]) for o in outs3)
+    monkeypatch.delenv("VAD_GRAPH")
+    assert torch.equal(m.forward_stem_layout(other), want[0])          # default policy: batch 2 <= 32 -> graph

@@ -39,6 +39,27 @@ def test_features_match_fp32_oracle(model, cuda_device):
         assert max_norm <= 1e-2 and rel_l2 <= 1e-2 and cos >= 0.999
 
 
+def test_widened_branch_temporaries_do_not_change_the_features(model, cuda_device):
+    """BRANCH_PAD (zero channels added to the 16/24/48/112/144/160-channel branch temporaries so that the 3x3x3 convs contract
+    64-wide k-blocks): the extra terms are exact zeros, so the features move only by the fp32 summation order inside the
+    tensor core's k-blocks -- far below the bf16 storage noise that separates either variant from the fp32 oracle."""
+    from anomaly_detection_on_video_b200.inception import InceptionI3d
+    from oracle import inception as OI
+
+    plain = InceptionI3d()
+    plain.pad_branches = False
+    plain.load_state_dict(OI.seeded_state_dict(0), strict=True)
+    plain = plain.eval().to(cuda_device)
+    widths = {op.name: (op.cin, op.cout) for op in model.op_table()}
+    assert widths["Mixed_4e.b1a"] == (512, 192) and widths["Mixed_4e.b1b"] == (192, 288) and widths["Mixed_3b.b2b"] == (64, 32)
+    assert {op.name: (op.cin, op.cout) for op in plain.op_table()}["Mixed_4e.b1b"] == (144, 288)
+    x = torch.randn(2, 3, 16, 224, 224, generator=torch.Generator().manual_seed(5)).clamp(-2.0, 2.4444).to(cuda_device)
+    a, b = model(x).view(2, -1).float(), plain(x).view(2, -1).float()
+    err = float((a - b).abs().max() / b.abs().max())
+    print(f"padded vs nominal branch widths: max-normalised difference {err:.2e}")
+    assert err <= 2e-3
+
+
 def test_extract_features_is_forward_and_shape_is_checked(model, cuda_device):
     x = torch.randn(1, 3, 16, 224, 224, generator=torch.Generator().manual_seed(2)).to(cuda_device)
     assert torch.equal(model.extract_features(x), model(x))
