@@ -1178,14 +1178,23 @@ static int32_t run_ops(vad_plan* p, const void* x_dev, void* workspace_dev, floa
       else if (inb && q.kt == 1 && q.kh == 1 && q.kw == 1)
         maxpool3d_fixed_kernel<1, 1, 1><<<g, 256, 0, st>>>(q);   // strided copy
       else if (q.kt == 3 && q.kh == 3 && q.kw == 3 && q.st == 1 && q.sh == 1 && q.sw == 1 && q.pt == 1 && q.ph == 1 && q.pw == 1 &&
-               q.To == q.Ti && q.Ho == q.Hi && q.Wo == q.Wi)            // Inception branch pools
+               q.To == q.Ti && q.Ho == q.Hi && q.Wo == q.Wi) {          // Inception branch pools
         maxpool3d_k3s1_kernel<<<grid_for((long long)q.B * q.Hi * q.Wi * (q.C / 8), 256, 148 * 64), 256, 0, st>>>(q);
-      else if (q.kt == 1 && q.kh == 3 && q.kw == 3)
-        maxpool3d_checked_kernel<1, 3, 3><<<g, 256, 0, st>>>(q);  // MaxPool3d_2a / 3a (SAME padding)
-      else if (q.kt == 3 && q.kh == 3 && q.kw == 3)
-        maxpool3d_checked_kernel<3, 3, 3><<<g, 256, 0, st>>>(q);  // MaxPool3d_4a
-      else if (q.kt == 2 && q.kh == 2 && q.kw == 2)
-        maxpool3d_checked_kernel<2, 2, 2><<<g, 256, 0, st>>>(q);  // MaxPool3d_5a
+      } else if ((q.kt == 1 || q.kt == 3) && q.kh == 3 && q.kw == 3 || (q.kt == 2 && q.kh == 2 && q.kw == 2)) {
+        // MaxPool3d_2a / 3a ((1,3,3) / (1,2,2)), 4a ((3,3,3) / 2), 5a ((2,2,2) / 2), SAME padding: one block per output row
+        const int items = q.Wo * (q.C / 8);
+        const int iters = (items + 511) / 512;
+        const int threads = ((items + iters - 1) / iters + 31) / 32 * 32;
+        const long long rows = (long long)q.B * q.To * q.Ho;
+        if (rows > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "max-pool: too many output rows for one launch");
+        if (q.C < 128 || getenv("VAD_POOL_OLD")) {
+          if (q.kt == 1)      maxpool3d_checked_kernel<1, 3, 3><<<g, 256, 0, st>>>(q);
+          else if (q.kt == 3) maxpool3d_checked_kernel<3, 3, 3><<<g, 256, 0, st>>>(q);
+          else                maxpool3d_checked_kernel<2, 2, 2><<<g, 256, 0, st>>>(q);
+        } else if (q.kt == 1) maxpool3d_rows_kernel<1, 3, 3><<<(int)rows, threads, 0, st>>>(q);
+        else if (q.kt == 3)   maxpool3d_rows_kernel<3, 3, 3><<<(int)rows, threads, 0, st>>>(q);
+        else                  maxpool3d_rows_kernel<2, 2, 2><<<(int)rows, threads, 0, st>>>(q);
+      }
       else
         maxpool3d_kernel<<<g, 256, 0, st>>>(q);
       e = cudaGetLastError();
