@@ -73,6 +73,17 @@ __device__ __forceinline__ void umma_f16_pair_acc(uint32_t tmem_d, uint64_t ades
                "l"(adesc), "l"(bdesc), "r"(idesc)
                : "memory");
 }
+// kind::tf32: fp32 operands read from shared memory (128-byte rows = 32 floats per k-block, 8 per MMA), fp32 accumulate
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the mbarrier at this offset in both CTAs once the previously issued pair MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -82,6 +93,17 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 256 (two CTAs x 128 rows)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_m256(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+}
+
+// instruction descriptor: tf32 x tf32 -> fp32, both operands K-major, M = 256
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_m256(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+}
+// TF32 rounding of a stored activation (ties away from zero): see tf32_kernels.cuh
+__device__ __forceinline__ float pair_tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
 }
 
 template <int BN, int KPS, bool EPI = false>
@@ -114,13 +136,19 @@ struct PairCfg {
 // tmB: weight map with (64 x BN/2) boxes.  Work item w -> (n tile = w % n_tiles, pair of m tiles = w / n_tiles); the
 // cluster (blockIdx.x >> 1) walks items with stride gridDim.x / 2; CTA rank r of the pair owns rows (2 * pair + r) * 128.
 // A pair whose odd CTA has no rows (odd number of m tiles) still loads: the boxes are out of bounds and arrive as zeros.
-template <int BN, int KPS, bool EPI>
+//
+// F32 = true is the TF32 precision mode (tf32_api.cuh): the tensor maps carry fp32 elements, a k-block is 32 floats -- the
+// same 128-byte rows, so stages, descriptors and barriers are unchanged --, the MMAs are kind::tf32, and the direct epilogue
+// reads an fp32 residual and writes TF32-rounded fp32 activations (p.res / p.out then point at floats).
+template <int BN, int KPS, bool EPI, bool F32 = false>
 __global__ void __launch_bounds__(PairCfg<BN, KPS, EPI>::kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = PairCfg<BN, KPS, EPI>;
+  static_assert(!(F32 && EPI), "the TF32 mode uses the direct epilogue");
   constexpr int STAGES = Cfg::kStages;
   constexpr int NB = Cfg::kEpiBufs;
+  constexpr int KBE = F32 ? 32 : 64;   // elements of one k-block (one 128-byte row)
   const int crank = (int)cluster_ctarank();
   // SPLIT (BN = 256, direct epilogue, one n tile): the items of the last, partly filled round run as two 128-column halves
   // each, so 3.3 rounds of work take 3.5 rounds instead of 4 (wave quantisation of the 74 CTA pairs)
@@ -217,20 +245,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < KPS; ++j) {
             if (j < nk) {
               if (p.a_mode == A_TMA_2D) {
-                tma_load_2d_pair(a_dst + j * Cfg::kABytes, &tmA, fb, (kb + j) * 64, m0);
+                tma_load_2d_pair(a_dst + j * Cfg::kABytes, &tmA, fb, (kb + j) * KBE, m0);
               } else {
                 tma_load_im2col_5d_pair(a_dst + j * Cfg::kABytes, &tmA, fb, c0, wq, hq, dq, nq, (uint16_t)dw, (uint16_t)dh, (uint16_t)dt);
-                c0 += 64;
+                c0 += KBE;
                 if (c0 >= p.cin_eff) {
                   c0 = 0;
                   if (++dw == p.kw) { dw = 0; if (++dh == p.kh) { dh = 0; ++dt; } }
                 }
               }
               if (SPLIT && p.pair_box_rows == 64) {  // 64-row weight boxes: two for a full-width item, one for a half
-                tma_load_2d_pair(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * 64, n0);
-                if (!half) tma_load_2d_pair(b_dst + j * Cfg::kBBytes + 64 * 128, &tmB, fb, (kb + j) * 64, n0 + 64);
+                tma_load_2d_pair(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * KBE, n0);
+                if (!half) tma_load_2d_pair(b_dst + j * Cfg::kBBytes + 64 * 128, &tmB, fb, (kb + j) * KBE, n0 + 64);
               } else {
-                tma_load_2d_pair(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * 64, n0);
+                tma_load_2d_pair(b_dst + j * Cfg::kBBytes, &tmB, fb, (kb + j) * KBE, n0);
               }
             }
           }
@@ -242,7 +270,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (crank == 0 && elect_one_sync()) {
-      constexpr uint32_t idesc_full = umma_idesc_bf16_m256(BN), idesc_half = umma_idesc_bf16_m256(BN / 2);
+      constexpr uint32_t idesc_full = F32 ? umma_idesc_tf32_m256(BN) : umma_idesc_bf16_m256(BN);
+      constexpr uint32_t idesc_half = F32 ? umma_idesc_tf32_m256(BN / 2) : umma_idesc_bf16_m256(BN / 2);
       const uint64_t desc_hi = umma_desc_kmajor<128>(0);
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
       const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
@@ -274,7 +303,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t bdesc = desc_hi | (b_lo + j * (Cfg::kBBytes >> 4));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (j == 0 && k == 0) umma_f16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
+                if constexpr (F32) umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | j | k) ? 1u : 0u);
+                else if (j == 0 && k == 0) umma_f16_pair(d_tmem, adesc, bdesc, idesc, kb ? 1u : 0u);
                 else                  umma_f16_pair_acc(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
                 if (j * 4 + k == WAIT_IDX && do_wait) {
                   if (last_stage) {
@@ -403,6 +433,40 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         continue;
       }
       const bool row_ok = row < p.M;
+      if constexpr (F32) {
+        float* out_row = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0 + col0_i;
+        const float* res_row = p.res ? reinterpret_cast<const float*>(p.res) + (long long)row * p.ldr + n0 + col0_i : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < cpw_i / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int col = c * 32 + g * 4;
+              if (n0 + col0_i + col < p.N) {
+                float4 f;
+                f.x = fmaf(__uint_as_float(v[g * 4 + 0]), s_scale[col0_i + col + 0], s_shift[col0_i + col + 0]);
+                f.y = fmaf(__uint_as_float(v[g * 4 + 1]), s_scale[col0_i + col + 1], s_shift[col0_i + col + 1]);
+                f.z = fmaf(__uint_as_float(v[g * 4 + 2]), s_scale[col0_i + col + 2], s_shift[col0_i + col + 2]);
+                f.w = fmaf(__uint_as_float(v[g * 4 + 3]), s_scale[col0_i + col + 3], s_shift[col0_i + col + 3]);
+                if (res_row) {
+                  const float4 r = *reinterpret_cast<const float4*>(res_row + col);
+                  f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
+                }
+                if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+                f.x = pair_tf32_rna(f.x); f.y = pair_tf32_rna(f.y); f.z = pair_tf32_rna(f.z); f.w = pair_tf32_rna(f.w);
+                *reinterpret_cast<float4*>(out_row + col) = f;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ltempty0 + acc * 8);
+        continue;
+      }
       __nv_bfloat16* out_row = p.out + (long long)row * p.ldo + n0 + col0_i;
 #pragma unroll 1
       for (int c = 0; c < cpw_i / 32; ++c) {

@@ -12,6 +12,8 @@ struct Tf32Op {
   vad::Tf32ConvParams cp;
   vad::PoolF32Params pp;
   CUtensorMap tmA, tmB;
+  vad::ConvParams pc;    // CTA-pair form (conv_pair_kernel<.., F32 = true>): the bf16 kernel's parameter block, fp32 pointers
+  bool pair = false;     // 256 x BN tiles on CTA pairs: Cout >= 128 layers with a TMA activation tile
   bool tma_a = false;  // activation tile through a rank-5 fp32 im2col map (Cin % 32 == 0, TMA-expressible geometry)
   int pb[3] = {0, 0, 0};  // back padding (t, h, w)
   int Ci = 0, Ti = 0, Hi = 0, Wi = 0;
@@ -37,6 +39,7 @@ struct vad_tf32_plan {
   EncodeIm2colFn encode_im2col = nullptr;
   int driver_version = 0;
   bool no_tma_a = false;           // VAD_TF32_GATHER=1: every layer through the gather producer
+  bool no_pair = false;            // VAD_TF32_NO_PAIR=1: no CTA-pair kernel (A/B and bit-identity tests)
   const void* bound_x = nullptr;   // pointers the activation maps were encoded for
   const void* bound_ws = nullptr;
 };
@@ -82,6 +85,7 @@ extern "C" int32_t vad_tf32_plan_create(vad_tf32_plan_t** plan, const vad_op_des
   p->encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
   cudaDriverGetVersion(&p->driver_version);
   { const char* k = getenv("VAD_TF32_GATHER"); p->no_tma_a = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_TF32_NO_PAIR"); p->no_pair = k && k[0] == '1'; }
   cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (p->sm_count <= 0) p->sm_count = 148;
   *plan = p;
@@ -161,11 +165,33 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
       if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
       c.n_tiles = (int)n_tiles; c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;
+      // A 128 x 128 tile of 4-byte operands pulls 32 KB through L2 per 1 MFLOP k-block -- twice the bf16 kernel's bytes per
+      // FLOP at half the tensor rate, i.e. the L2 -> shared-memory path binds at a quarter of the tensor peak.  Layers with
+      // Cout >= 128 therefore run 256 x BN tiles on CTA pairs (tcgen05 cta_group::2, conv_pair.cuh): each CTA loads its 128
+      // activation rows and half of the weight rows.
+      r.pair = r.tma_a && d.cout >= 128 && !p->no_pair && (p->sm_count & 1) == 0;
+      if (r.pair) {
+        r.bn = d.cout % 256 == 0 ? 256 : 128;
+        vad::ConvParams& q = r.pc;
+        memset(&q, 0, sizeof(q));
+        const long long nt = (d.cout + r.bn - 1) / r.bn;
+        q.M = c.M; q.N = c.N; q.num_kb = c.num_kb; q.n_tiles = (int)nt; q.num_tiles = (int)(m_tiles * nt);
+        q.mc_items = (int)(((m_tiles + 1) / 2) * nt);
+        q.pair_split = q.pair_total = q.mc_items;
+        q.pair_box_rows = r.bn / 2;
+        q.To = To; q.Ho = Ho; q.Wo = Wo; q.Ti = src.T; q.Hi = src.H; q.Wi = src.W;
+        q.kt = d.kt; q.kh = d.kh; q.kw = d.kw; q.st = d.st; q.sh = d.sh; q.sw = d.sw; q.pt = pf[0]; q.ph = pf[1]; q.pw = pf[2];
+        q.cin_eff = d.cin; q.ntaps = c.ntaps;
+        q.a_mode = vad::A_TMA_IM2COL;
+        q.relu = c.relu; q.ldo = c.ldo;
+        r.grid = 2 * q.mc_items < p->sm_count ? 2 * q.mc_items : p->sm_count;
+      }
       if (d.res >= 0) {
         const SlotInfo& rs = p->slots[d.res];
         if (!rs.defined || rs.T != To || rs.H != Ho || rs.W != Wo || rs.C < d.cout)
           return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: residual slot %d does not match the output", i, d.res);
         c.ldr = rs.C;
+        r.pc.ldr = rs.C;
       }
       p->flops += 2.0 * (double)M * d.cout * c.ntaps * d.cin;  // useful FLOPs (the folded window's zero taps excluded)
     } else if (d.kind == VAD_OP_MAXPOOL) {
@@ -222,7 +248,7 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
       if (d.res > 0) r.res_off = p->slots[d.res].offset;
       cuuint64_t gdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
       cuuint64_t gstr[1] = {(cuuint64_t)r.K_pad * 4};
-      cuuint32_t box[2] = {32, (cuuint32_t)r.bn};
+      cuuint32_t box[2] = {32, (cuuint32_t)(r.pair ? r.bn / 2 : r.bn)};
       cuuint32_t es[2] = {1, 1};
       CUresult cr = p->encode_tiled(&r.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(p->params + d.w_off), gdim, gstr, box, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -230,6 +256,8 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
       if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(fp32 weights) failed: %d", i, (int)cr);
       r.cp.scale = reinterpret_cast<const float*>(p->params + d.scale_off);
       r.cp.shift = reinterpret_cast<const float*>(p->params + d.shift_off);
+      r.pc.scale = r.cp.scale;
+      r.pc.shift = r.cp.shift;
     }
   }
   p->bound_x = p->bound_ws = nullptr;
@@ -282,6 +310,19 @@ static int32_t bind_tf32(vad_tf32_plan* p, const void* x, void* ws) {
   return VAD_OK;
 }
 
+template <int BN, int KPS>
+static cudaError_t launch_conv_tf32_pair(const Tf32Op& r, const vad::ConvParams& c, cudaStream_t st) {
+  using Cfg = vad::PairCfg<BN, KPS, false>;
+  auto kern = vad::conv_pair_kernel<BN, KPS, false, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, false, 2, r.tmA, r.tmB, r.tmA, r.tmA, c);
+}
+
 template <int BN, bool TMA_A>
 static cudaError_t launch_conv_tf32(const Tf32Op& r, const vad::Tf32ConvParams& c, cudaStream_t st) {
   using Cfg = vad::Tf32Cfg<BN>;
@@ -318,7 +359,12 @@ extern "C" int32_t vad_tf32_plan_forward(vad_tf32_plan_t* p, const void* x_dev, 
       c.in = reinterpret_cast<const float*>(src);
       c.out = reinterpret_cast<float*>(ws + r.out_off);
       c.res = d.res > 0 ? reinterpret_cast<const float*>(ws + r.res_off) : nullptr;
-      if (r.tma_a) e = r.bn == 128 ? launch_conv_tf32<128, true>(r, c, st) : launch_conv_tf32<64, true>(r, c, st);
+      if (r.pair) {
+        vad::ConvParams q = r.pc;
+        q.out = reinterpret_cast<__nv_bfloat16*>(c.out);        // fp32 behind the bf16 kernel's pointer types (F32 instantiation)
+        q.res = reinterpret_cast<const __nv_bfloat16*>(c.res);
+        e = r.bn == 256 ? launch_conv_tf32_pair<256, 1>(r, q, st) : launch_conv_tf32_pair<128, 2>(r, q, st);
+      } else if (r.tma_a) e = r.bn == 128 ? launch_conv_tf32<128, true>(r, c, st) : launch_conv_tf32<64, true>(r, c, st);
       else         e = r.bn == 128 ? launch_conv_tf32<128, false>(r, c, st) : launch_conv_tf32<64, false>(r, c, st);
     } else if (d.kind == VAD_OP_MAXPOOL) {
       vad::PoolF32Params q = r.pp;

@@ -37,13 +37,19 @@ CONV_CASES = [
     ("1x1 stride 2 256->512 ds, linear", 256, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, 2, 14, 14, False, False),
     ("3x3x3 24->40 (cin % 32 != 0, N tail)", 24, 40, (3, 3, 3), (1, 1, 1), (1, 1, 1), 2, 3, 6, 5, False, True),
     ("1x1 2048->512 long K", 2048, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, 2, 7, 7, False, True),
+    # CTA-pair form (Cout >= 128 with a TMA activation tile): odd number of m tiles (the odd CTA of the last pair has no rows),
+    # N tail inside a 128-wide pair tile, more items than CTA pairs, residual on a two-n-tile layer
+    ("1x1 256->192 odd m tiles, N tail", 256, 192, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 1, 13, 13, False, True),
+    ("3x3x3 64->128 many pair items", 64, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), 4, 8, 28, 28, False, True),
+    ("1x1 128->512 +res, 490 m tiles", 512, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 4, 4, 28, 28, True, True),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_tf32_matches_fp32_conv3d(cuda_device, case, monkeypatch):
-    """Every case runs twice: activation tile by TMA im2col where Cin % 32 == 0 (the default) and by the cp.async gather
-    (VAD_TF32_GATHER=1); same k order per accumulator, so the two must agree bit for bit."""
+    """Every case runs three times: the default (activation tile by TMA im2col where Cin % 32 == 0; 256 x BN tiles on CTA pairs,
+    conv_pair_kernel<.., F32>, where also Cout >= 128), the single-CTA TMA kernel (VAD_TF32_NO_PAIR=1) and the cp.async gather
+    (VAD_TF32_GATHER=1); same k order per accumulator, so all three must agree bit for bit."""
     from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
 
     _, cin, cout, k, s, p, B, T, H, W, res, relu = case
@@ -64,14 +70,15 @@ def test_conv_tf32_matches_fp32_conv3d(cuda_device, case, monkeypatch):
     ops.append(eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=2, res=1 if res else -1, cin=cin, cout=cout, kernel=k, stride=s, pad=p,
                       flags=lib.VAD_FLAG_RELU if relu else 0, w_off=w_off, scale_off=s_off, shift_off=b_off))
     outs = []
-    for gather in ("0", "1"):
+    for gather, no_pair in (("0", "0"), ("0", "1"), ("1", "0")):
         monkeypatch.setenv("VAD_TF32_GATHER", gather)
+        monkeypatch.setenv("VAD_TF32_NO_PAIR", no_pair)
         plan = eng.Tf32Plan(ops, pk.blob(), 3, cuda_device, in_channels=cin)
         plan.forward(x.permute(0, 2, 3, 4, 1).contiguous().to(cuda_device))
         torch.cuda.synchronize()
         outs.append(plan.slot_tensor(2).cpu().permute(0, 4, 1, 2, 3).clone())
     close_tf32(outs[0], ref)
-    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 @pytest.mark.parametrize("cin,cout,k,s,T,H,W", [(64, 64, (3, 3, 3), (2, 2, 2), 6, 15, 20), (64, 128, (7, 7, 7), (2, 2, 2), 8, 16, 16),
