@@ -260,10 +260,10 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 384 ? 4 : 2) preprocess_stem_ker
   const uint8_t* frame = p.frames + (long long)src_frame * p.H * p.W * 3;
   const int tid = threadIdx.x, nthr = blockDim.x;
 
-  if (tid < 256) {
+  for (int i = tid; i < 256; i += nthr) {   // (narrow resized frames run fewer than 256 threads)
     // GroupStandardizationTenCrop: t.sub_(114.75).div_(57.375), two fp32 roundings, then the stem's bf16
-    const float v = __fdiv_rn(__fsub_rn((float)tid, 114.75f), 57.375f);
-    lut_h[tid] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    const float v = __fdiv_rn(__fsub_rn((float)i, 114.75f), 57.375f);
+    lut_h[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
   const int ymin0 = p.bounds_v[2 * y0];
   if (tid < ny) {

@@ -345,20 +345,24 @@ def test_preprocess_stem_layout_and_center_crop(cuda_device):
     assert torch.equal(one[1][0], ds[1][4]), "center crop == TenCrop index 4"
 
 
-@pytest.mark.parametrize("n,h,w", [(21, 240, 320), (17, 360, 480), (16, 300, 256), (19, 480, 854), (16, 256, 341), (5, 600, 800)],
-                         ids=["ucf_240x320", "down_360x480", "portrait_300x256", "down_480x854", "identity_256x341", "generic_600x800"])
-def test_preprocess_stem_kernel_equals_the_dataset_path(cuda_device, n, h, w, monkeypatch):
+@pytest.mark.parametrize("n,h,w,resize,crop", [(21, 240, 320, 256, 224), (17, 360, 480, 256, 224), (16, 300, 256, 256, 224),
+                                               (19, 480, 854, 256, 224), (16, 256, 341, 256, 224), (5, 600, 800, 256, 224),
+                                               (20, 60, 80, 64, 56), (9, 40, 30, 24, 16)],
+                         ids=["ucf_240x320", "down_360x480", "portrait_300x256", "down_480x854", "identity_256x341", "generic_600x800",
+                              "smoke_60x80_to_64_crop56", "tiny_40x30_to_24_crop16"])
+def test_preprocess_stem_kernel_equals_the_dataset_path(cuda_device, n, h, w, resize, crop, monkeypatch):
     """The column-per-thread stem-layout kernel (3- and 5-tap resampling filters; 600 x 800 falls back to the generic kernel)
     == the fp32 dataset path -- pinned by the reference digests above -- rounded to bf16 and re-laid out, bit for bit,
     including the LoopPad tail clip, the zero pad columns and the zero fourth channel."""
     from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
 
     frames = _frames(h * 7 + w, n, h, w)
-    ds = TenCropVideoFrameDataset(frames, device=cuda_device)
-    stem = ds.clips_stem(0, len(ds))                                  # (clips * 10, 16, 224, 232, 4) bf16
-    f32 = ds.clips_f32(0, len(ds))                                    # (clips, 10, 16, 3, 224, 224) fp32
+    ds = TenCropVideoFrameDataset(frames, resize=resize, cropsize=crop, device=cuda_device)
+    stem = ds.clips_stem(0, len(ds))                                  # (clips * 10, 16, crop, crop + 8, 4) bf16
+    f32 = ds.clips_f32(0, len(ds))                                    # (clips, 10, 16, 3, crop, crop) fp32
+    assert tuple(stem.shape) == (len(ds) * 10, 16, crop, crop + 8, 4)
     want = torch.zeros(stem.shape, dtype=torch.bfloat16, device=cuda_device)
-    want[:, :, :, 3:3 + 224, :3] = f32.reshape(-1, 16, 3, 224, 224).permute(0, 1, 3, 4, 2).to(torch.bfloat16)
+    want[:, :, :, 3:3 + crop, :3] = f32.reshape(-1, 16, 3, crop, crop).permute(0, 1, 3, 4, 2).to(torch.bfloat16)
     assert torch.equal(stem, want)
     monkeypatch.setenv("VAD_K1_GENERIC", "1")
     assert torch.equal(ds.clips_stem(0, len(ds)), want)
