@@ -4,10 +4,11 @@
 # Run under gpurun; one GPU.
 set -u
 TAG=${1:-r01}
-python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_plain.log 2>&1 || { echo "plain bench failed"; exit 1; }
+export VAD_BENCH_NO_INCEPTION=1 VAD_BENCH_NO_SMOOTH=1
+python bench.py --steps 1 --warmup 3 --sustain-seconds 0 --no-cpu-baseline > gpurun_out/${TAG}_bench_plain.log 2>&1 || { echo "plain bench failed"; exit 1; }
 python tools/ncu_target.py > gpurun_out/${TAG}_target_plain.log 2>&1 || { echo "plain target failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+    python bench.py --steps 1 --warmup 3 --sustain-seconds 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 echo "launch list rc=$?"
 full() {  # name, kernel regex, skip, count
   ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/${TAG}_$1 -f \
@@ -19,7 +20,7 @@ full() {  # name, kernel regex, skip, count
   if [ "$sz" -gt 12000000 ]; then rm -f gpurun_out/${TAG}_$1.ncu-rep; fi
 }
 full stem 'stem_umma' 0 1
-full conv_l1 'conv_umma|conv_thalo|conv_s3x3|conv_pair' 0 8
-full conv_l3 'conv_umma|conv_thalo|conv_s3x3|conv_pair' 27 4
+full conv_l1 'conv_umma|conv_thalo|conv_s3x3|conv_pair|conv_tail' 0 8
+full conv_l3 'conv_umma|conv_thalo|conv_s3x3|conv_pair|conv_tail' 23 4
 full aux 'maxpool|preprocess|avgpool|segment' 0 5
 du -sh gpurun_out
