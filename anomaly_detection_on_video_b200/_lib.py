@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 VAD_OP_CONV, VAD_OP_MAXPOOL, VAD_OP_AVGPOOL = 0, 1, 2
 VAD_FLAG_RELU, VAD_FLAG_STEM_FOLD_W, VAD_FLAG_POOL_SAME, VAD_FLAG_FORCE_GATHER, VAD_FLAG_POOL_T2, VAD_FLAG_CONV_SAME = 1, 2, 4, 8, 16, 32
+VAD_FLAG_STEM_PLANES = 64
 VAD_OUT_DATASET_F32, VAD_OUT_STEM_BF16 = 0, 1
 
 # every symbol include/vad_b200.h declares (tests check the .so exports exactly these)
@@ -63,6 +64,7 @@ EXPORTED_SYMBOLS = (
     "vad_tf32_plan_flops",
     "vad_tf32_plan_destroy",
     "vad_tf32_ingest_ncthw",
+    "vad_tf32_ingest_ncthw_planes",
 )
 
 
@@ -194,6 +196,8 @@ def load() -> ctypes.CDLL:
     lib.vad_tf32_plan_destroy.argtypes = [c_void_p]
     lib.vad_tf32_ingest_ncthw.restype = c_int32
     lib.vad_tf32_ingest_ncthw.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.vad_tf32_ingest_ncthw_planes.restype = c_int32
+    lib.vad_tf32_ingest_ncthw_planes.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.vad_head_num_launches.restype = c_int32
     lib.vad_head_num_launches.argtypes = [c_void_p]
     lib.vad_head_flops.restype = c_double

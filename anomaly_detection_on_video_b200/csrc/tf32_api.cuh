@@ -15,6 +15,10 @@ struct Tf32Op {
   vad::ConvParams pc;    // CTA-pair form (conv_pair_kernel<.., F32 = true>): the bf16 kernel's parameter block, fp32 pointers
   bool pair = false;     // 256 x BN tiles on CTA pairs: Cout >= 128 layers with a TMA activation tile
   bool tma_a = false;  // activation tile through a rank-5 fp32 im2col map (Cin % 32 == 0, TMA-expressible geometry)
+  bool stem = false;   // VAD_FLAG_STEM_PLANES: dedicated stem kernel on the column-parity plane input
+  vad::StemTf32Params sp;
+  CUtensorMap tmE, tmOdd, tmW, tmSO;
+  int stem_smem = 0;
   int pb[3] = {0, 0, 0};  // back padding (t, h, w)
   int Ci = 0, Ti = 0, Hi = 0, Wi = 0;
   int bn = 128;
@@ -40,6 +44,7 @@ struct vad_tf32_plan {
   int driver_version = 0;
   bool no_tma_a = false;           // VAD_TF32_GATHER=1: every layer through the gather producer
   bool no_pair = false;            // VAD_TF32_NO_PAIR=1: no CTA-pair kernel (A/B and bit-identity tests)
+  bool planes_in = false;          // slot 0 is the column-parity plane layout (the stem op carries VAD_FLAG_STEM_PLANES)
   const void* bound_x = nullptr;   // pointers the activation maps were encoded for
   const void* bound_ws = nullptr;
 };
@@ -58,6 +63,14 @@ extern "C" int32_t vad_tf32_plan_create(vad_tf32_plan_t** plan, const vad_op_des
       return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad dst slot %d", i, d.dst);
     if (d.flags & VAD_FLAG_POOL_T2)
       return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: the TF32 mode takes the unfused op table (no POOL_T2)", i);
+    if (d.flags & VAD_FLAG_STEM_PLANES) {
+      if (i != 0 || d.kind != VAD_OP_CONV || !(d.flags & VAD_FLAG_STEM_FOLD_W) || d.src != 0 || d.cin != 4 || d.cout != 64 || d.sh != 2 ||
+          d.sw != 2 || d.pw != 3 || d.kw > 8 || d.kh < 2 || d.kt * d.kh > 36 || d.res >= 0 || (d.flags & VAD_FLAG_CONV_SAME) || in_channels != 4)
+        return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_PLANES needs the first op to be a folded RGB stem conv with stride 2 in h and w, "
+                    "64 output channels, pw = 3, kw <= 8, 2 <= kh, kt * kh <= 36, symmetric padding and no residual", i);
+      for (int j = 1; j < n_ops; ++j)
+        if (ops[j].src == 0 || ops[j].res == 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: only the stem may read the plane-layout input", j);
+    }
     if ((d.flags & VAD_FLAG_STEM_FOLD_W) && (d.kind != VAD_OP_CONV || d.cin != 4 || d.kw > 8 || d.src != 0 || in_channels != 4))
       return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: STEM_FOLD_W needs a conv on the 4-channel input with kw <= 8", i);
     if (d.kind == VAD_OP_CONV) {
@@ -75,6 +88,7 @@ extern "C" int32_t vad_tf32_plan_create(vad_tf32_plan_t** plan, const vad_op_des
   p->params = static_cast<const uint8_t*>(params_dev);
   p->params_bytes = params_bytes;
   p->in_channels = in_channels;
+  p->planes_in = (ops[0].flags & VAD_FLAG_STEM_PLANES) != 0;
   p->device = device;
   void* fn = nullptr;
   rc = driver_symbol("cuTensorMapEncodeTiled", &fn);
@@ -105,7 +119,8 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
   p->batch = batch;
   SlotInfo& s0 = p->slots[0];
   s0.T = t; s0.H = h; s0.W = w; s0.C = p->in_channels; s0.defined = true;
-  s0.bytes = (uint64_t)batch * t * h * w * s0.C * 4;
+  s0.bytes = (uint64_t)batch * t * h * (p->planes_in ? w + 8 : w) * s0.C * 4;
+  if (p->planes_in && (w & 1)) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_plan_configure: the plane-layout stem needs an even width");
   // pass 1: shapes in op order, the largest extent every slot ever has
   struct Shape { int T, H, W, C; };
   std::vector<Shape> src_shape(p->ops.size()), dst_shape(p->ops.size());
@@ -159,12 +174,40 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
         return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: parameters run past the blob", i);
       r.bn = d.cout > 64 ? 128 : 64;
       r.Ci = d.cin; r.Ti = src.T; r.Hi = src.H; r.Wi = src.W;
-      r.tma_a = !p->no_tma_a && !c.fold && d.cin % 32 == 0 && r.pb[0] <= 15 && r.pb[1] <= 15 && r.pb[2] <= 15 && pf[0] <= 15 && pf[1] <= 15 &&
+      r.stem = (d.flags & VAD_FLAG_STEM_PLANES) != 0;
+      if (r.stem) {
+        vad::StemTf32Params& q = r.sp;
+        memset(&q, 0, sizeof(q));
+        q.B = batch; q.To = To; q.Ho = Ho; q.Wo = Wo;
+        q.kt = d.kt; q.kh = d.kh; q.st = d.st; q.pt = pf[0]; q.ph = pf[1];
+        q.tiles_w = (Wo + 7) / 8; q.tiles_h = (Ho + 15) / 16;
+        const long long nt = (long long)batch * To * q.tiles_h * q.tiles_w;
+        if (nt > 0x3fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: too many stem tiles", i);
+        q.num_tiles = (int)nt;
+        q.rows_even = 16 + (d.kh + 1) / 2 - 1;
+        q.rows_odd = 16 + d.kh / 2 - 1;
+        q.box_bytes[0] = (int)align_up((uint64_t)q.rows_even * vad::kStemTf32SegBytes, 128);
+        q.box_bytes[1] = (int)align_up((uint64_t)q.rows_odd * vad::kStemTf32SegBytes, 128);
+        q.stage_bytes = 2 * (q.box_bytes[0] + q.box_bytes[1]);
+        q.relu = c.relu;
+        const int w_bytes = (int)align_up((uint64_t)d.kt * d.kh * 2 * vad::kStemTf32TapBytes, 1024);
+        const int fixed = w_bytes + 2 * vad::kStemTf32StagingBytes + 2 * 32 * 4 + (2 * vad::kStemMaxStages + 5) * 8 + 16 + 1024;
+        int ns = (232448 - fixed) / q.stage_bytes;
+        if (ns > vad::kStemMaxStages) ns = vad::kStemMaxStages;
+        if (ns < 2) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: the stem's weights leave no room for two input stages", i);
+        q.n_stages = ns;
+        r.stem_smem = fixed + ns * q.stage_bytes;
+      }
+      r.tma_a = !r.stem && !p->no_tma_a && !c.fold && d.cin % 32 == 0 && r.pb[0] <= 15 && r.pb[1] <= 15 && r.pb[2] <= 15 && pf[0] <= 15 && pf[1] <= 15 &&
                 pf[2] <= 15 && d.kt <= 16 && d.kh <= 16 && d.kw <= 16 && d.st <= 8 && d.sh <= 8 && d.sw <= 8;
       const long long m_tiles = (M + vad::kBlockM - 1) / vad::kBlockM, n_tiles = (d.cout + r.bn - 1) / r.bn;
       if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
       c.n_tiles = (int)n_tiles; c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;
+      if (r.stem) {  // two CTAs (one per half of the output channels) per tile stream
+        const int pairs = p->sm_count / 2;
+        r.grid = 2 * (r.sp.num_tiles < pairs ? r.sp.num_tiles : pairs);
+      }
       // A 128 x 128 tile of 4-byte operands pulls 32 KB through L2 per 1 MFLOP k-block -- twice the bf16 kernel's bytes per
       // FLOP at half the tensor rate, i.e. the L2 -> shared-memory path binds at a quarter of the tensor peak.  Layers with
       // Cout >= 128 therefore run 256 x BN tiles on CTA pairs (tcgen05 cta_group::2, conv_pair.cuh): each CTA loads its 128
@@ -286,6 +329,44 @@ static int32_t bind_tf32(vad_tf32_plan* p, const void* x, void* ws) {
     const vad_op_desc& d = p->ops[i];
     Tf32Op& r = p->rt[i];
     memset(&r.tmA, 0, sizeof(r.tmA));
+    if (d.kind == VAD_OP_CONV && r.stem) {
+      // input planes [N, T, H, 2, Wh, 4] viewed as (x = Wh * 4 floats, plane, H, T, N); a box is 44 contiguous floats (the union of
+      // 8 overlapping 16-float windows, 4 floats apart) x one plane x rows with stride 2; even / odd input rows are two maps
+      const vad::StemTf32Params& q = r.sp;
+      const uint64_t wh = (uint64_t)(r.Wi + 8) / 2;
+      cuuint64_t rdim[5] = {wh * 4, 2, (cuuint64_t)r.Hi, (cuuint64_t)r.Ti, (cuuint64_t)p->batch};
+      cuuint64_t rstr[4] = {wh * 16, 2 * wh * 16, 2 * wh * 16 * r.Hi, 2 * wh * 16 * r.Hi * r.Ti};
+      cuuint32_t res5[5] = {1, 1, 2, 1, 1};
+      cuuint32_t bE[5] = {(cuuint32_t)(vad::kStemTf32SegBytes / 4), 1, (cuuint32_t)(2 * q.rows_even - 1), 1, 1};
+      cuuint32_t bO[5] = {(cuuint32_t)(vad::kStemTf32SegBytes / 4), 1, (cuuint32_t)(2 * q.rows_odd - 1), 1, 1};
+      CUresult cr = p->encode_tiled(&r.tmE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, rdim, rstr, bE, res5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr == CUDA_SUCCESS)
+        cr = p->encode_tiled(&r.tmOdd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, rdim, rstr, bO, res5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr == CUDA_SUCCESS) {
+        cuuint64_t wdim[2] = {(cuuint64_t)r.K_pad, (cuuint64_t)d.cout};
+        cuuint64_t wstr[1] = {(cuuint64_t)r.K_pad * 4};
+        cuuint32_t wbox[2] = {16, 32};
+        cuuint32_t wes[2] = {1, 1};
+        cr = p->encode_tiled(&r.tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(p->params + d.w_off), wdim, wstr, wbox, wes,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      if (cr == CUDA_SUCCESS) {
+        // output [N, To, Ho, Wo, Cdst] fp32 (channel slice at out_off): one store per epilogue warp = 32 channels x 8 columns x 4 rows
+        const uint64_t cb = (uint64_t)r.cp.ldo * 4;
+        cuuint64_t odim[5] = {(cuuint64_t)d.cout, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.To, (cuuint64_t)p->batch};
+        cuuint64_t ostr[4] = {cb, cb * q.Wo, cb * q.Wo * q.Ho, cb * q.Wo * q.Ho * q.To};
+        cuuint32_t obox[5] = {32, 8, 4, 1, 1};
+        cuuint32_t oes[5] = {1, 1, 1, 1, 1};
+        cr = p->encode_tiled(&r.tmSO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)(static_cast<uint8_t*>(ws) + r.out_off), odim, ostr, obox, oes,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "tf32 op %zu: cuTensorMapEncodeTiled(stem) failed: %d", i, (int)cr);
+      continue;
+    }
     if (d.kind != VAD_OP_CONV || !r.tma_a) continue;
     const uint8_t* src = d.src == 0 ? static_cast<const uint8_t*>(x) : static_cast<const uint8_t*>(ws) + r.in_off;
     // (C, W, H, D, N); the bounding box of base pixels runs from -pad_front to (extent - 1 + pad_back - (k - 1))
@@ -359,7 +440,19 @@ extern "C" int32_t vad_tf32_plan_forward(vad_tf32_plan_t* p, const void* x_dev, 
       c.in = reinterpret_cast<const float*>(src);
       c.out = reinterpret_cast<float*>(ws + r.out_off);
       c.res = d.res > 0 ? reinterpret_cast<const float*>(ws + r.res_off) : nullptr;
-      if (r.pair) {
+      if (r.stem) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          e = cudaFuncSetAttribute(vad::stem_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+          attr_set = (e == cudaSuccess);
+        }
+        if (e == cudaSuccess) {
+          vad::StemTf32Params q = r.sp;
+          q.scale = c.scale; q.shift = c.shift;
+          vad::stem_tf32_kernel<<<r.grid, vad::kStemTf32Threads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, q);
+          e = cudaGetLastError();
+        }
+      } else if (r.pair) {
         vad::ConvParams q = r.pc;
         q.out = reinterpret_cast<__nv_bfloat16*>(c.out);        // fp32 behind the bf16 kernel's pointer types (F32 instantiation)
         q.res = reinterpret_cast<const __nv_bfloat16*>(c.res);
@@ -382,6 +475,17 @@ extern "C" int32_t vad_tf32_plan_forward(vad_tf32_plan_t* p, const void* x_dev, 
     }
     if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "tf32 op %zu launch failed: %s", i, cudaGetErrorString(e));
   }
+  return VAD_OK;
+}
+
+extern "C" int32_t vad_tf32_ingest_ncthw_planes(const float* x_dev, int32_t batch, int32_t t, int32_t h, int32_t w, float* out_dev, void* stream) {
+  if (!x_dev || !out_dev || batch <= 0 || t <= 0 || h <= 0 || w <= 0 || (w & 1)) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_ingest_ncthw_planes: bad arguments (w must be even)");
+  if (reinterpret_cast<uintptr_t>(out_dev) & 15) return fail(VAD_ERR_INVALID_ARGUMENT, "vad_tf32_ingest_ncthw_planes: output must be 16-byte aligned");
+  const long long th = (long long)t * h;
+  vad::ingest_ncthw_f32_to_planes_kernel<<<grid_for((long long)batch * th * (w + 8), 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_dev, batch, th, w, reinterpret_cast<float4*>(out_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(VAD_ERR_CUDA, "vad_tf32_ingest_ncthw_planes launch failed: %s", cudaGetErrorString(e));
   return VAD_OK;
 }
 

@@ -17,6 +17,7 @@
 
 #include "conv_umma.cuh"
 #include "head_kernels.cuh"
+#include "stem_umma.cuh"
 
 namespace vad {
 
@@ -315,6 +316,262 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TF32 stem (VAD_FLAG_STEM_PLANES): conv kt x kh x (kw <= 8), stride 2 in h and w, RGB(+0) -> 64 channels, + BN + ReLU
+// (src/i3d.py:202-209,303-305) on the dedicated-stem design of K2s (stem_umma.cuh), for fp32 operands.
+//
+// Through the general kernel above the stem is half of the TF32 forward: every (dt, dh) tap re-reads a 16 KB activation
+// column and 8 KB of weights through L2.  K2s removes that for bf16 by letting the tensor core read the sliding 8-pixel
+// windows of 8 consecutive output columns straight out of raw input-row segments -- a no-swizzle K-major descriptor whose
+// rows are 16 bytes apart.  bf16 pixels (r, g, b, 0) are 8 bytes, so stride-2 output columns are 16 bytes apart; fp32
+// pixels are 16 bytes and stride 2 would be 32.  So the input is de-interleaved by COLUMN PARITY (vad_tf32_ingest_ncthw_planes):
+// window pixel j of output column w' is padded pixel 2 w' + j, i.e. position w' + j / 2 of plane j & 1 -- in each plane
+// consecutive output columns are one pixel = 16 bytes apart again, a window is 4 pixels = 64 bytes, and a (dt, dh) tap becomes
+// two 16-float "virtual taps" (even plane, odd plane).  Byte for byte that is the bf16 stem's operand geometry (176-byte
+// segments, 64-byte windows, two 32-byte MMAs per virtual tap), with kind::tf32 MMAs.
+//   * Weights: kt * kh * 2 virtual taps x (64 couts x 64 B) = 280 KB in fp32 -- twice shared memory.  A CTA therefore owns
+//     HALF of the output channels (blockIdx.x & 1) and keeps its 140 KB resident; every spatial tile is visited by two CTAs
+//     (the activation segments are 13 KB per input frame, their second read comes from L2).
+//   * A (dt) stage = four TMA boxes: even / odd input rows (vertical stride 2) x even / odd column plane.
+//   * N = 32 MMAs are bound by their operand fetch (A 4 KB + B 1 KB per 128 B/clk: 40 cycles against 16 of math); that is
+//     still 3.6 x fewer cycles than the L2-bound general kernel spends.
+//   * Epilogue: TMEM -> scale / shift + ReLU -> TF32 rounding -> 128B-swizzled fp32 staging tile (128 pixels x 32 channels) ->
+//     one TMA store per warp into the channel half of the fp32 output.
+struct StemTf32Params {
+  int B, To, Ho, Wo;
+  int kt, kh, st, pt, ph;
+  int tiles_w, tiles_h;
+  int num_tiles;            // B * To * tiles_h * tiles_w (each visited by both channel halves)
+  int rows_even, rows_odd;  // box rows: 16 + (#dh taps of that parity) - 1
+  int box_bytes[2];         // bytes of one even-row / odd-row box (rows x 176, padded to 128)
+  int stage_bytes;          // 2 * (box_bytes[0] + box_bytes[1])
+  int n_stages;
+  int relu;
+  const float* scale;
+  const float* shift;
+};
+constexpr int kStemTf32Threads = 192;
+constexpr int kStemTf32TapBytes = 32 * 64;        // one virtual tap of one channel half: 32 couts x 16 floats
+constexpr int kStemTf32StagingBytes = 128 * 128;  // 128 pixels x 32 fp32 channels
+constexpr int kStemTf32SegBytes = 176;            // 8 windows of 64 B, 16 B apart
+
+__device__ __forceinline__ void tma_load_5d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// tmE / tmOdd: input planes viewed as (x = Wh * 4 floats, plane, H, T, N), boxes of 44 floats x 1 x rows (row stride 2);
+// tmW: fp32 weights [64][kt * kh * 32], boxes of 16 floats x 32 rows (SWIZZLE_64B); tmO: output (C, Wo, Ho, To, N), boxes 32 x 8 x 4.
+__global__ void __launch_bounds__(kStemTf32Threads, 1)
+stem_tf32_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmOdd,
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const StemTf32Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int ntaps = p.kt * p.kh * 2;                               // virtual taps
+  uint8_t* w_smem = smem;                                          // ntaps x 2 KB, resident
+  uint8_t* staging = smem + ((ntaps * kStemTf32TapBytes + 1023) & ~1023);   // 2 x 16 KB output staging (1024-aligned)
+  uint8_t* stage_base = staging + 2 * kStemTf32StagingBytes;
+  float* s_scale = reinterpret_cast<float*>(stage_base + p.n_stages * p.stage_bytes);
+  float* s_shift = s_scale + 32;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 32);
+  uint64_t* empty_bar = full_bar + kStemMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kStemMaxStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* w_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.n_stages;
+  const int half = (int)(blockIdx.x & 1u);                         // which 32 of the 64 output channels
+  const int t_first = (int)(blockIdx.x >> 1), t_step = (int)(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmE);
+    tma_prefetch_desc(&tmOdd);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);   // two 32-column accumulators
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 32) {
+      s_scale[t] = p.scale[half * 32 + t];
+      s_shift[t] = p.shift[half * 32 + t];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t box_e = (uint32_t)p.box_bytes[0], box_o = (uint32_t)p.box_bytes[1];
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected thread)
+    if (elect_one_sync()) {
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
+      mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTf32TapBytes));
+      for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTf32TapBytes, &tmW, w_bar, tap * 16, half * 32);
+      const uint32_t tx = (uint32_t)(2 * (p.rows_even + p.rows_odd) * kStemTf32SegBytes);
+      uint32_t s = 0, ph = 0;
+      for (int tile = t_first; tile < p.num_tiles; tile += t_step) {
+        int r = tile;
+        const int wb = r % p.tiles_w; r /= p.tiles_w;
+        const int hb = r % p.tiles_h; r /= p.tiles_h;
+        const int to = r % p.To;
+        const int n = r / p.To;
+        const int h_start = 2 * (hb * 16) - p.ph;
+        const int x_start = wb * 8 * 4;    // 8 windows, one plane pixel (4 floats) apart
+        const int t0 = to * p.st - p.pt;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          mbar_wait_a(empty0 + s * 8, ph ^ 1u);
+          const uint32_t dst = stage0 + s * (uint32_t)p.stage_bytes;
+          const uint32_t fb = full0 + s * 8;
+          mbar_arrive_expect_tx_a(fb, tx);
+          tma_load_5d_a(dst, &tmE, fb, x_start, 0, h_start, t0 + dt, n);
+          tma_load_5d_a(dst + box_e, &tmE, fb, x_start, 1, h_start, t0 + dt, n);
+          tma_load_5d_a(dst + 2 * box_e, &tmOdd, fb, x_start, 0, h_start + 1, t0 + dt, n);
+          tma_load_5d_a(dst + 2 * box_e + box_o, &tmOdd, fb, x_start, 1, h_start + 1, t0 + dt, n);
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_tf32_m128(32);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
+      const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
+      mbar_wait(w_bar, 0);
+      const uint32_t seg16 = kStemTf32SegBytes >> 4;
+      const uint32_t w16 = smem_u32(w_smem) >> 4;
+      const uint64_t a_hi = umma_desc_kmajor_noswizzle(0, 16u, kStemTf32SegBytes);
+      const uint64_t b_hi = umma_desc_kmajor<64>(0);
+      uint32_t s = 0, ph = 0, tc = 0;
+      for (int tile = t_first; tile < p.num_tiles; tile += t_step, ++tc) {
+        const uint32_t acc = tc & 1u;
+        mbar_wait_a(tempty0 + acc * 8, ((tc >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 32u;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          mbar_wait_a(full0 + s * 8, ph);
+          tc_fence_after();
+          const uint32_t st16 = (stage0 + s * (uint32_t)p.stage_bytes) >> 4;
+          uint32_t b_lo = w16 + (uint32_t)(dt * p.kh * 2) * (kStemTf32TapBytes >> 4);
+          for (int dh = 0; dh < p.kh; ++dh) {
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+              const uint32_t box16 = ((dh & 1) ? 2 * box_e + (uint32_t)pl * box_o : (uint32_t)pl * box_e) >> 4;
+              const uint64_t adesc = a_hi | (st16 + box16 + (uint32_t)(dh >> 1) * seg16);
+              const uint64_t bdesc = b_hi | b_lo;
+              umma_tf32(d_tmem, adesc, bdesc, idesc, (dt | dh | pl) ? 1u : 0u);
+              umma_tf32(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              b_lo += kStemTf32TapBytes >> 4;
+            }
+          }
+          umma_commit_a(empty0 + s * 8);
+          if (dt == p.kt - 1) umma_commit_a(tfull0 + acc * 8);
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..5
+    const int q = warp & 3;
+    const int lrow = q * 32 + lane;  // tile row = TMEM lane: (h_i, w_i) = (lrow / 8, lrow % 8)
+    const uint32_t xr = (uint32_t)(lrow & 7);
+    const uint32_t staging0 = smem_u32(staging);
+    uint32_t tc = 0;
+    for (int tile = t_first; tile < p.num_tiles; tile += t_step, ++tc) {
+      int r = tile;
+      const int wb = r % p.tiles_w; r /= p.tiles_w;
+      const int hb = r % p.tiles_h; r /= p.tiles_h;
+      const int to = r % p.To;
+      const int n = r / p.To;
+      const uint32_t sb = tc & 1u, acc = tc & 1u;
+      const uint32_t row_addr = staging0 + sb * kStemTf32StagingBytes + (uint32_t)lrow * 128u;
+      // the TMA store that read this staging buffer two tiles ago must have drained it
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      mbar_wait(&tmem_full_bar[acc], (tc >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32u, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float4 f;
+        f.x = fmaf(__uint_as_float(v[g * 4 + 0]), s_scale[g * 4 + 0], s_shift[g * 4 + 0]);
+        f.y = fmaf(__uint_as_float(v[g * 4 + 1]), s_scale[g * 4 + 1], s_shift[g * 4 + 1]);
+        f.z = fmaf(__uint_as_float(v[g * 4 + 2]), s_scale[g * 4 + 2], s_shift[g * 4 + 2]);
+        f.w = fmaf(__uint_as_float(v[g * 4 + 3]), s_scale[g * 4 + 3], s_shift[g * 4 + 3]);
+        if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+        f.x = tf32_rna(f.x); f.y = tf32_rna(f.y); f.z = tf32_rna(f.z); f.w = tf32_rna(f.w);
+        const uint32_t addr = row_addr + ((((uint32_t)g) ^ xr) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        // this warp's 32 rows = output rows hb*16 + 4q .. +3, columns wb*8 .. +7 (clipped at Ho / Wo by the map)
+        tma_store_5d(&tmO, staging0 + sb * kStemTf32StagingBytes + (uint32_t)q * 4096u, half * 32, wb * 8, hb * 16 + q * 4, to, n);
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// fp32 NCTHW -> column-parity planes [B, T, H, 2, Wh, 4] with Wh = (W + 8) / 2: one thread per output pixel slot
+__global__ void ingest_ncthw_f32_to_planes_kernel(const float* __restrict__ x, int B, long long th, int W, float4* __restrict__ out) {
+  const int Wh = (W + 8) >> 1;
+  const long long total = (long long)B * th * 2 * Wh;
+  const long long plane_sz = th * W;   // one channel of one clip
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pos = (int)(i % Wh);
+    long long r = i / Wh;
+    const int pl = (int)(r & 1);
+    r >>= 1;                           // (b * T + t) * H + h
+    const long long b = r / th, row = r - b * th;
+    const int xs = 2 * pos + pl - 3;   // source column of padded pixel 2 pos + pl
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xs >= 0 && xs < W) {
+      const float* px = x + b * 3 * plane_sz + row * W + xs;
+      o.x = tf32_rna(px[0]); o.y = tf32_rna(px[plane_sz]); o.z = tf32_rna(px[2 * plane_sz]);
+    }
+    out[i] = o;
   }
 }
 

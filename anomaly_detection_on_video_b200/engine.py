@@ -79,7 +79,7 @@ class ParamPacker:
         return off
 
     def add_conv(self, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, fold_w: bool = False,
-                 cin_pad: Optional[int] = None, tf32: bool = False) -> Tuple[int, int, int]:
+                 cin_pad: Optional[int] = None, tf32: bool = False, planes: bool = False) -> Tuple[int, int, int]:
         """weight: [cout, cin, kt, kh, kw] fp32 (torch Conv3d layout).  ``tf32``: keep the weights in fp32 with K padded
         to 32 (the layout of the TF32 precision mode, ``Tf32Plan``)."""
         w = weight.detach().to(torch.float32).cpu()
@@ -92,6 +92,10 @@ class ParamPacker:
                 raise ValueError("fold_w packing needs cin <= 4 and kw <= 8")
             wf = torch.zeros(cout, kt, kh, 8, 4, dtype=torch.float32)
             wf[:, :, :, :kw, :cin] = w
+            if planes:
+                # VAD_FLAG_STEM_PLANES: window pixel j = 2 i + p sits at position i of column-parity plane p, so one
+                # (dt, dh) tap is two 16-float virtual taps [plane][4 px][4 ch]
+                wf = wf.reshape(cout, kt, kh, 4, 2, 4).permute(0, 1, 2, 4, 3, 5).contiguous()
             w2 = wf.reshape(cout, kt * kh * 32)
         else:
             cp = cin_pad or cin
@@ -318,11 +322,19 @@ class Tf32Plan:
         return self._ws[start:start + 4 * n].view(torch.float32).view(batch, t, h, w, c)
 
     def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-        """x: contiguous fp32 [batch, T, H, W, in_channels] on the device."""
+        """x: contiguous fp32 [batch, T, H, W, in_channels] on the device; [batch, T, H, 2, (W + 8) / 2, 4] (``ingest_ncthw_tf32(...,
+        planes=True)``) when the stem op carries VAD_FLAG_STEM_PLANES."""
         _require_cuda(x, "x")
-        if x.dtype != torch.float32 or x.dim() != 5 or x.shape[-1] != self.in_channels or not x.is_contiguous():
-            raise ValueError(f"input must be a contiguous fp32 [batch, T, H, W, {self.in_channels}] tensor")
-        b, t, h, w, _ = x.shape
+        planes = bool(self.ops and self.ops[0].flags & _lib.VAD_FLAG_STEM_PLANES)
+        if planes:
+            if x.dtype != torch.float32 or x.dim() != 6 or x.shape[3] != 2 or x.shape[-1] != 4 or not x.is_contiguous():
+                raise ValueError("input must be a contiguous fp32 [batch, T, H, 2, (W + 8) / 2, 4] plane-layout tensor")
+            b, t, h, _, wh, _ = x.shape
+            w = 2 * wh - 8
+        else:
+            if x.dtype != torch.float32 or x.dim() != 5 or x.shape[-1] != self.in_channels or not x.is_contiguous():
+                raise ValueError(f"input must be a contiguous fp32 [batch, T, H, W, {self.in_channels}] tensor")
+            b, t, h, w, _ = x.shape
         self.configure(b, t, h, w)
         has_feat = any(op.kind == _lib.VAD_OP_AVGPOOL for op in self.ops)
         if has_feat and out is None:
@@ -333,15 +345,23 @@ class Tf32Plan:
         return out if has_feat else None
 
 
-def ingest_ncthw_tf32(x: torch.Tensor) -> torch.Tensor:
-    """fp32 [B, 3, T, H, W] clips -> fp32 [B, T, H, W, 4] (zero fourth channel): the input of a ``Tf32Plan``."""
+def ingest_ncthw_tf32(x: torch.Tensor, planes: bool = False) -> torch.Tensor:
+    """fp32 [B, 3, T, H, W] clips -> fp32 [B, T, H, W, 4] (zero fourth channel): the input of a ``Tf32Plan``.
+    ``planes``: the column-parity plane layout [B, T, H, 2, (W + 8) / 2, 4] of a plan whose stem has VAD_FLAG_STEM_PLANES."""
     _require_cuda(x, "x")
     if x.dtype != torch.float32 or x.dim() != 5 or x.shape[1] != 3:
         raise ValueError("expected a float32 [B, 3, T, H, W] tensor")
     x = x.contiguous()
     b, _, t, h, w = x.shape
-    out = torch.empty(b, t, h, w, 4, dtype=torch.float32, device=x.device)
     lib = _lib.load()
+    if planes:
+        if w % 2:
+            raise ValueError("the plane layout needs an even frame width")
+        out = torch.empty(b, t, h, 2, (w + 8) // 2, 4, dtype=torch.float32, device=x.device)
+        check(lib.vad_tf32_ingest_ncthw_planes(ctypes.c_void_p(x.data_ptr()), b, t, h, w, ctypes.c_void_p(out.data_ptr()),
+                                               ctypes.c_void_p(_stream_ptr(x.device))), "vad_tf32_ingest_ncthw_planes")
+        return out
+    out = torch.empty(b, t, h, w, 4, dtype=torch.float32, device=x.device)
     check(lib.vad_tf32_ingest_ncthw(ctypes.c_void_p(x.data_ptr()), b, t, h, w, ctypes.c_void_p(out.data_ptr()),
                                     ctypes.c_void_p(_stream_ptr(x.device))), "vad_tf32_ingest_ncthw")
     return out

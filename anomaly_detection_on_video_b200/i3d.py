@@ -71,6 +71,7 @@ class _NativeBackbone(nn.Module):
         # "bf16" (production: bf16 activations / weights, fp32 accumulate) or "tf32" (fp32 activations / weights, tcgen05
         # kind::tf32 MMAs, general kernels only: features within 1e-3 of the reference's fp32 path)
         self.precision = "bf16"
+        self.tf32_stem_planes = True  # tf32 mode: dedicated stem kernel on the column-parity plane layout (False: gather stem)
 
     # subclasses return (ops, packer, n_slots)
     def _build_table(self) -> Tuple[List[Op], ParamPacker, int]:
@@ -86,9 +87,15 @@ class _NativeBackbone(nn.Module):
             # fp32 weights, K padded to 32; the RGB stem reads the 4-channel (zero-padded) fp32 input, no folded window
             cin = (conv.in_channels + 3) // 4 * 4
             fold = fold_w and cin == 4 and k[2] <= 8  # RGB stem: contract 8-pixel x 4-channel windows (contiguous 128 B)
-            w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, cin_pad=cin, tf32=True, fold_w=fold)
+            # the dedicated TF32 stem kernel (column-parity plane input): stride 2 in h and w, 64 output channels,
+            # pad 3 in w (window pixel j of output column w' is padded pixel 2 w' + j) and at most 36 (dt, dh) taps (144 KB of
+            # fp32 weights per half of the output channels resident in shared memory): the I3Res50 stem, not Inception's 7x7x7
+            planes = (fold and self.tf32_stem_planes and src == 0 and s[1] == 2 and s[2] == 2 and conv.out_channels == 64
+                      and p[2] == 3 and k[0] * k[1] <= 36 and k[1] > 1 and res < 0 and not dst_c_total)
+            w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, cin_pad=cin, tf32=True, fold_w=fold, planes=planes)
             return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, res=res, cin=cin, cout=conv.out_channels, kernel=k, stride=s, pad=p,
-                      flags=(_lib.VAD_FLAG_RELU if relu else 0) | (_lib.VAD_FLAG_STEM_FOLD_W if fold else 0), dst_c_off=dst_c_off,
+                      flags=(_lib.VAD_FLAG_RELU if relu else 0) | (_lib.VAD_FLAG_STEM_FOLD_W if fold else 0) |
+                            (_lib.VAD_FLAG_STEM_PLANES if planes else 0), dst_c_off=dst_c_off,
                       dst_c_total=dst_c_total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
         w_off, s_off, b_off = packer.add_conv(conv.weight, scale, shift, fold_w=fold_w)
         flags = (_lib.VAD_FLAG_RELU if relu else 0) | (_lib.VAD_FLAG_STEM_FOLD_W if fold_w else 0)
@@ -105,7 +112,7 @@ class _NativeBackbone(nn.Module):
     def plan(self, device: torch.device):
         if self.precision not in ("bf16", "tf32"):
             raise ValueError(f"precision must be 'bf16' or 'tf32', not {self.precision!r}")
-        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool, self.fuse_pool2, self.precision)
+        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool, self.fuse_pool2, self.precision, self.tf32_stem_planes)
         if self._plan is None or self._plan_key != key:
             ops, packer, n_slots = self._build_table()
             if self.precision == "tf32":
@@ -144,7 +151,11 @@ class _NativeBackbone(nn.Module):
             if self.training:
                 raise RuntimeError("the native backbone is inference-only: call .eval() first (extract_features.py:36)")
             self._select_fusions(int(batch.shape[2]))
-            feats = self.plan(batch.device).forward(ingest_ncthw_tf32(batch.float()))
+            plan = self.plan(batch.device)
+            planes = bool(plan.ops[0].flags & _lib.VAD_FLAG_STEM_PLANES) and batch.shape[-1] % 2 == 0
+            if not planes and plan.ops[0].flags & _lib.VAD_FLAG_STEM_PLANES:
+                raise ValueError("the TF32 stem kernel needs an even frame width; set model.tf32_stem_planes = False")
+            feats = plan.forward(ingest_ncthw_tf32(batch.float(), planes=planes))
         else:
             feats = self.forward_stem_layout(ingest_ncthw(batch.float(), self.pad_left))
         return feats.view(feats.shape[0], feats.shape[1], 1, 1, 1)

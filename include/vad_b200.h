@@ -75,8 +75,11 @@ enum {
   VAD_FLAG_POOL_T2 = 16,    /* stem conv (STEM_FOLD_W): max over output frames (2k, 2k+1) fused into
                                the epilogue, i.e. the temporal half of a following MaxPool3d with
                                kt = st = 2, pt = 0 (reference src/i3d.py:212-214); dst has To / 2    */
-  VAD_FLAG_CONV_SAME = 32   /* conv: TF "SAME" padding (InceptionI3d's Unit3D): out = ceil(in / stride),
+  VAD_FLAG_CONV_SAME = 32,  /* conv: TF "SAME" padding (InceptionI3d's Unit3D): out = ceil(in / stride),
                                front pad = total / 2, back pad = total - front; pt/ph/pw are ignored */
+  VAD_FLAG_STEM_PLANES = 64 /* TF32 plans only, with STEM_FOLD_W: slot 0 is the column-parity plane layout of
+                               vad_tf32_ingest_ncthw_planes and the stem runs on the dedicated tcgen05 kind::tf32
+                               stem kernel (stride 2 in h and w, cout = 64, kt * kh <= 36, kw <= 8, pw <= 3)   */
 };
 
 typedef struct vad_op_desc {
@@ -324,6 +327,12 @@ void vad_tf32_plan_destroy(vad_tf32_plan_t* plan);
  * fp32 [batch, T, H, W, 4] with a zero fourth channel: slot 0 of a TF32 plan with in_channels = 4. */
 int32_t vad_tf32_ingest_ncthw(const float* x_dev, int32_t batch, int32_t t, int32_t h, int32_t w, float* out_dev,
                               void* stream);
+/* The same hand-off for a plan whose stem carries VAD_FLAG_STEM_PLANES: fp32 [batch, 3, T, H, W] ->
+ * fp32 [batch, T, H, 2, (W + 8) / 2, 4]: pixel x of a row sits at padded index xp = x + 3, in plane xp & 1 at position xp >> 1
+ * (zero fourth channel, zero pad pixels; W even).  In each plane the 8-pixel windows of consecutive stride-2 output columns
+ * start 16 bytes apart, which is what lets the tensor core read them straight out of raw row segments. */
+int32_t vad_tf32_ingest_ncthw_planes(const float* x_dev, int32_t batch, int32_t t, int32_t h, int32_t w, float* out_dev,
+                                     void* stream);
 
 #ifdef __cplusplus
 }

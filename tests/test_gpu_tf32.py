@@ -128,6 +128,53 @@ def test_stem_folded_window_gather(cuda_device, k, s, same):
     close_tf32(plan.slot_tensor(1).cpu().permute(0, 4, 1, 2, 3), ref)
 
 
+@pytest.mark.parametrize("k,st,B,T,H,W,dst", [((5, 7, 7), 2, 2, 9, 30, 34, (0, 0)), ((5, 7, 7), 2, 1, 16, 224, 224, (0, 0)),
+                                              ((1, 7, 7), 1, 2, 4, 50, 38, (0, 0)), ((3, 5, 8), 2, 1, 6, 33, 70, (32, 128)),
+                                              ((5, 7, 7), 2, 3, 8, 16, 16, (0, 0))])
+def test_stem_plane_kernel(cuda_device, k, st, B, T, H, W, dst):
+    """VAD_FLAG_STEM_PLANES: the dedicated TF32 stem kernel (stem_tf32_kernel) on the column-parity plane layout --
+    sliding 8-pixel windows read by the tensor core out of raw row segments, two CTAs per tile (one per half of the 64 output
+    channels), resident fp32 weights -- against fp32 conv3d, incl. ragged tiles (Ho / Wo not multiples of 16 / 8), a
+    destination channel slice, and the gather stem on the plain layout as a second opinion."""
+    from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
+
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, 3, T, H, W, generator=g)
+    w = torch.randn(64, 3, *k, generator=g) * (2.0 / (3 * k[0] * k[1] * k[2])) ** 0.5
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    s, pad = (st, 2, 2), (k[0] // 2, k[1] // 2, 3)
+    ref = F.relu(F.conv3d(x, w, None, s, pad) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    outs = []
+    for planes in (True, False):
+        pk = eng.ParamPacker()
+        w_off, s_off, b_off = pk.add_conv(w, scale, shift, fold_w=True, tf32=True, planes=planes)
+        flags = lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W | (lib.VAD_FLAG_STEM_PLANES if planes else 0)
+        ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=4, cout=64, kernel=k, stride=s, pad=pad, flags=flags, w_off=w_off,
+                      scale_off=s_off, shift_off=b_off, dst_c_off=dst[0], dst_c_total=dst[1])]
+        plan = eng.Tf32Plan(ops, pk.blob(), 2, cuda_device, in_channels=4)
+        xin = eng.ingest_ncthw_tf32(x.to(cuda_device), planes=planes)
+        if planes:
+            # the plane layout is a pure relayout: padded pixel xp = x + 3 -> plane xp & 1, position xp >> 1
+            want = torch.zeros(B, T, H, W + 8, 4)
+            want[:, :, :, 3:3 + W, :3] = x.permute(0, 2, 3, 4, 1)
+            want = want.view(B, T, H, (W + 8) // 2, 2, 4).permute(0, 1, 2, 4, 3, 5)
+            got = xin.cpu()
+            assert got.shape == want.shape and (got - want).abs().max() <= 2.0 ** -11 * want.abs().max()   # TF32 rounding only
+        if dst[1]:
+            plan.configure(B, T, H, W)
+            plan.slot_tensor(1).fill_(-7.0)
+        plan.forward(xin)
+        torch.cuda.synchronize()
+        out = plan.slot_tensor(1).cpu()
+        if dst[1]:
+            assert (out[..., :dst[0]] == -7.0).all() and (out[..., dst[0] + 64:] == -7.0).all(), "neighbouring channel slices untouched"
+            out = out[..., dst[0]:dst[0] + 64]
+        outs.append(out.permute(0, 4, 1, 2, 3))
+    close_tf32(outs[0], ref)
+    close_tf32(outs[1], ref)
+    close_tf32(outs[0], outs[1], 5e-4)
+
+
 def test_pools_and_channel_slices_are_exact(cuda_device):
     """fp32 max-pools (torch semantics and the SAME-padding port) are exact; two ops write disjoint channel slices of
     one destination (the Inception concat)."""

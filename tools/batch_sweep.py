@@ -20,8 +20,8 @@ for mode in (("bf16", "tf32") if which == "both" else (which,)):
             xs = torch.randn(B, 16, 224, 232, 4, device=dev).to(torch.bfloat16)
             run = lambda: m.forward_stem_layout(xs)
         else:
-            xs = ingest_ncthw_tf32(torch.randn(B, 3, 16, 224, 224, device=dev))
             plan = m.plan(dev)
+            xs = ingest_ncthw_tf32(torch.randn(B, 3, 16, 224, 224, device=dev), planes=bool(plan.ops[0].flags & 64))
             run = lambda: plan.forward(xs)
         for _ in range(3): run()
         n = 20 if B <= 64 else 10
