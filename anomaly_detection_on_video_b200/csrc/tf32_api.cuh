@@ -464,7 +464,13 @@ extern "C" int32_t vad_tf32_plan_forward(vad_tf32_plan_t* p, const void* x_dev, 
       q.in = reinterpret_cast<const float*>(src);
       q.out = reinterpret_cast<float*>(ws + r.out_off);
       const long long total = (long long)q.B * q.To * q.Ho * q.Wo * (q.C / 4);
-      vad::maxpool3d_f32_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, st>>>(q);
+      const bool inb = !q.pt && !q.ph && !q.pw && (q.To - 1) * q.st + q.kt <= q.Ti && (q.Ho - 1) * q.sh + q.kh <= q.Hi &&
+                       (q.Wo - 1) * q.sw + q.kw <= q.Wi;
+      const int g = grid_for(total, 256, 148 * 64);
+      if (inb && q.kt == 2 && q.kh == 3 && q.kw == 3)      vad::maxpool3d_f32_fixed_kernel<2, 3, 3><<<g, 256, 0, st>>>(q);   // maxpool1
+      else if (inb && q.kt == 2 && q.kh == 1 && q.kw == 1) vad::maxpool3d_f32_fixed_kernel<2, 1, 1><<<g, 256, 0, st>>>(q);   // maxpool2
+      else if (inb && q.kt == 1 && q.kh == 1 && q.kw == 1) vad::maxpool3d_f32_fixed_kernel<1, 1, 1><<<g, 256, 0, st>>>(q);   // strided copy
+      else                                                 vad::maxpool3d_f32_kernel<<<g, 256, 0, st>>>(q);
       e = cudaGetLastError();
     } else {
       if (!feat_out_dev) return fail(VAD_ERR_INVALID_ARGUMENT, "plan ends in AVGPOOL but feat_out_dev is null");
