@@ -106,6 +106,8 @@ __device__ __forceinline__ float pair_tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
+constexpr int kPairXposeBytes = 8 * 4096 + 128;   // F32 instantiations: per-warp transposition tiles of the direct epilogue
+
 template <int BN, int KPS, bool EPI = false>
 struct PairCfg {
   static_assert(BN == 256 || BN == 128, "pair tile is 256 x BN");
@@ -173,6 +175,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* res_full_bar = tmem_empty_bar + 2;   // [NB] residual half-tile landed (EPI)
   uint64_t* res_empty_bar = res_full_bar + NB;   // [NB] staging tile free again (EPI)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty_bar + NB);
+  // F32: 8 x 4 KB transposition tiles of the epilogue warps, behind everything else (the launch adds kPairXposeBytes)
+  uint8_t* xpose_base = smem + ((Cfg::kSmemBytes + 127) & ~127);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -434,33 +438,65 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const bool row_ok = row < p.M;
       if constexpr (F32) {
-        float* out_row = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n0 + col0_i;
-        const float* res_row = p.res ? reinterpret_cast<const float*>(p.res) + (long long)row * p.ldr + n0 + col0_i : nullptr;
+        // fp32 rows: a thread's 32 accumulator columns are one full 128-byte line of ITS row, so register-direct accesses
+        // would touch 32 different lines per instruction (the layer1 conv3 launches ran at 0.43 of HBM that way).  Each warp
+        // transposes through its own 4 KB shared-memory tile (32 rows x 8 sixteen-byte chunks, chunk index XOR row & 7:
+        // conflict-free both ways): residual and output move as four whole 128-byte row segments per instruction.
+        float* outp = reinterpret_cast<float*>(p.out);
+        const float* resp = reinterpret_cast<const float*>(p.res);
+        const uint32_t tw = smem_u32(xpose_base) + (uint32_t)(warp - 2) * 4096u;
+        const int r_sub = lane >> 3, c_sub = lane & 7;   // coalesced phases: this lane covers row 4 k + r_sub, chunk c_sub
+        const uint32_t own = tw + (uint32_t)lane * 128u;
+        const uint32_t lx = (uint32_t)(lane & 7);
 #pragma unroll 1
         for (int c = 0; c < cpw_i / 32; ++c) {
+          const int colbase = n0 + col0_i + c * 32;
           uint32_t v[32];
           tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-          tmem_ld_wait();
-          if (row_ok) {
+          float4 rr[8];
+          if (resp) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int col = c * 32 + g * 4;
-              if (n0 + col0_i + col < p.N) {
-                float4 f;
-                f.x = fmaf(__uint_as_float(v[g * 4 + 0]), s_scale[col0_i + col + 0], s_shift[col0_i + col + 0]);
-                f.y = fmaf(__uint_as_float(v[g * 4 + 1]), s_scale[col0_i + col + 1], s_shift[col0_i + col + 1]);
-                f.z = fmaf(__uint_as_float(v[g * 4 + 2]), s_scale[col0_i + col + 2], s_shift[col0_i + col + 2]);
-                f.w = fmaf(__uint_as_float(v[g * 4 + 3]), s_scale[col0_i + col + 3], s_shift[col0_i + col + 3]);
-                if (res_row) {
-                  const float4 r = *reinterpret_cast<const float4*>(res_row + col);
-                  f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
-                }
-                if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
-                f.x = pair_tf32_rna(f.x); f.y = pair_tf32_rna(f.y); f.z = pair_tf32_rna(f.z); f.w = pair_tf32_rna(f.w);
-                *reinterpret_cast<float4*>(out_row + col) = f;
-              }
+            for (int k = 0; k < 8; ++k) {
+              const int row_l = 4 * k + r_sub;
+              const long long grow = (long long)m0 + q * 32 + row_l;
+              float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grow < p.M && colbase + c_sub * 4 < p.N) rv = *reinterpret_cast<const float4*>(resp + grow * p.ldr + colbase + c_sub * 4);
+              const uint32_t a = tw + (uint32_t)row_l * 128u + ((((uint32_t)c_sub) ^ (uint32_t)(row_l & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(rv.x), "f"(rv.y), "f"(rv.z), "f"(rv.w) : "memory");
             }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rr[j].x), "=f"(rr[j].y), "=f"(rr[j].z), "=f"(rr[j].w)
+                           : "r"(own + ((((uint32_t)j) ^ lx) << 4)));
+            __syncwarp();
           }
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int sc = col0_i + c * 32 + g * 4;
+            float4 f;
+            f.x = fmaf(__uint_as_float(v[g * 4 + 0]), s_scale[sc + 0], s_shift[sc + 0]);
+            f.y = fmaf(__uint_as_float(v[g * 4 + 1]), s_scale[sc + 1], s_shift[sc + 1]);
+            f.z = fmaf(__uint_as_float(v[g * 4 + 2]), s_scale[sc + 2], s_shift[sc + 2]);
+            f.w = fmaf(__uint_as_float(v[g * 4 + 3]), s_scale[sc + 3], s_shift[sc + 3]);
+            if (resp) { f.x += rr[g].x; f.y += rr[g].y; f.z += rr[g].z; f.w += rr[g].w; }
+            if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+            f.x = pair_tf32_rna(f.x); f.y = pair_tf32_rna(f.y); f.z = pair_tf32_rna(f.z); f.w = pair_tf32_rna(f.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(own + ((((uint32_t)g) ^ lx) << 4)), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w)
+                         : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int row_l = 4 * k + r_sub;
+            const long long grow = (long long)m0 + q * 32 + row_l;
+            float4 o;
+            const uint32_t a = tw + (uint32_t)row_l * 128u + ((((uint32_t)c_sub) ^ (uint32_t)(row_l & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(a));
+            if (grow < p.M && colbase + c_sub * 4 < p.N) *reinterpret_cast<float4*>(outp + grow * p.ldo + colbase + c_sub * 4) = o;
+          }
+          __syncwarp();
         }
         tc_fence_before();
         __syncwarp();

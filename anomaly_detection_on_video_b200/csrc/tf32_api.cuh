@@ -397,11 +397,12 @@ static cudaError_t launch_conv_tf32_pair(const Tf32Op& r, const vad::ConvParams&
   auto kern = vad::conv_pair_kernel<BN, KPS, false, true>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + vad::kPairXposeBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, false, 2, r.tmA, r.tmB, r.tmA, r.tmA, c);
+  static_assert(Cfg::kSmemBytes + vad::kPairXposeBytes <= 232448, "pair kernel + transposition tiles exceed shared memory");
+  return launch_k(kern, r.grid, Cfg::kThreads, Cfg::kSmemBytes + vad::kPairXposeBytes, st, false, 2, r.tmA, r.tmB, r.tmA, r.tmA, c);
 }
 
 template <int BN, bool TMA_A>
