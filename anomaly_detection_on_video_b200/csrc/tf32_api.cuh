@@ -16,6 +16,7 @@ struct Tf32Op {
   bool pair = false;     // 256 x BN tiles on CTA pairs: Cout >= 128 layers with a TMA activation tile
   bool tma_a = false;  // activation tile through a rank-5 fp32 im2col map (Cin % 32 == 0, TMA-expressible geometry)
   bool stem = false;   // VAD_FLAG_STEM_PLANES: dedicated stem kernel on the column-parity plane input
+  bool stem_pair = false;  // ... on CTA pairs (stem_tf32_pair_kernel)
   vad::StemTf32Params sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
   int stem_smem = 0;
@@ -191,7 +192,7 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
         q.stage_bytes = 2 * (q.box_bytes[0] + q.box_bytes[1]);
         q.relu = c.relu;
         const int w_bytes = (int)align_up((uint64_t)d.kt * d.kh * 2 * vad::kStemTf32TapBytes, 1024);
-        const int fixed = w_bytes + 2 * vad::kStemTf32StagingBytes + 2 * 32 * 4 + (2 * vad::kStemMaxStages + 5) * 8 + 16 + 1024;
+        const int fixed = w_bytes + 2 * vad::kStemTf32StagingBytes + 2 * 64 * 4 + (2 * vad::kStemMaxStages + 5) * 8 + 16 + 1024;
         int ns = (232448 - fixed) / q.stage_bytes;
         if (ns > vad::kStemMaxStages) ns = vad::kStemMaxStages;
         if (ns < 2) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: the stem's weights leave no room for two input stages", i);
@@ -204,9 +205,13 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
       if (m_tiles * n_tiles > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: grid too large", i);
       c.n_tiles = (int)n_tiles; c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;
-      if (r.stem) {  // two CTAs (one per half of the output channels) per tile stream
+      if (r.stem) {
+        // CTA pairs: one item = two tiles (rank 0 / rank 1), each CTA holding half of the weights; without pairs two CTAs (one per
+        // half of the output channels) walk the same tile stream
         const int pairs = p->sm_count / 2;
-        r.grid = 2 * (r.sp.num_tiles < pairs ? r.sp.num_tiles : pairs);
+        r.stem_pair = !p->no_pair && (p->sm_count & 1) == 0;
+        const int items = r.stem_pair ? (r.sp.num_tiles + 1) / 2 : r.sp.num_tiles;
+        r.grid = 2 * (items < pairs ? items : pairs);
       }
       // A 128 x 128 tile of 4-byte operands pulls 32 KB through L2 per 1 MFLOP k-block -- twice the bf16 kernel's bytes per
       // FLOP at half the tensor rate, i.e. the L2 -> shared-memory path binds at a quarter of the tensor peak.  Layers with
@@ -447,11 +452,20 @@ extern "C" int32_t vad_tf32_plan_forward(vad_tf32_plan_t* p, const void* x_dev, 
           e = cudaFuncSetAttribute(vad::stem_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
           attr_set = (e == cudaSuccess);
         }
+        static bool attr_pair = false;
+        if (e == cudaSuccess && !attr_pair) {
+          e = cudaFuncSetAttribute(vad::stem_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+          attr_pair = (e == cudaSuccess);
+        }
         if (e == cudaSuccess) {
           vad::StemTf32Params q = r.sp;
           q.scale = c.scale; q.shift = c.shift;
-          vad::stem_tf32_kernel<<<r.grid, vad::kStemTf32Threads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, q);
-          e = cudaGetLastError();
+          if (r.stem_pair) {
+            e = launch_k(vad::stem_tf32_pair_kernel, r.grid, vad::kStemTf32PairThreads, (size_t)r.stem_smem, st, false, 2, r.tmE, r.tmOdd, r.tmW, r.tmSO, q);
+          } else {
+            vad::stem_tf32_kernel<<<r.grid, vad::kStemTf32Threads, r.stem_smem, st>>>(r.tmE, r.tmOdd, r.tmW, r.tmSO, q);
+            e = cudaGetLastError();
+          }
         }
       } else if (r.pair) {
         vad::ConvParams q = r.pc;

@@ -19,6 +19,7 @@
 #include "conv_umma.cuh"
 #include "head_kernels.cuh"
 #include "stem_umma.cuh"
+#include "conv_pair.cuh"
 
 namespace vad {
 
@@ -552,6 +553,227 @@ stem_tf32_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same stem on CTA PAIRS (tcgen05 cta_group::2): stem_tf32_kernel's N = 32 MMAs spend 40 cycles fetching operands for 16
+// cycles of math.  Here the two CTAs of a cluster take two spatial tiles (M = 256), each still keeps only ITS half of the
+// output channels' weights resident (140 KB) -- and the pair MMA reads the B operand's two halves from both CTAs' shared
+// memory, so every MMA is N = 64: A 4 KB + B 2 KB per CTA for 32 cycles of math, and every tile is loaded once instead of twice.
+// Protocol as in conv_pair.cuh: both CTAs' TMA loads complete on the LEADER's full barrier; the leader's elected thread issues
+// the MMAs; tcgen05.commit multicasts the stage release and the accumulator-ready signal into both CTAs; the epilogue warps of
+// both CTAs arrive on the leader's accumulator-empty barrier.  Item i = tiles 2 i (rank 0) and 2 i + 1 (rank 1); an odd CTA
+// without a tile loads out-of-range boxes (zeros) and stores nothing.
+constexpr int kStemTf32PairThreads = 192;
+
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kStemTf32PairThreads, 1)
+stem_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmOdd,
+                      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const StemTf32Params p) {
+  extern __shared__ __align__(1024) uint8_t stem_pair_smem[];
+  uint8_t* smem = stem_pair_smem;
+  if (smem_u32(smem) & 1023u) __trap();
+  const int crank = (int)cluster_ctarank();
+  const int ntaps = p.kt * p.kh * 2;                               // virtual taps
+  uint8_t* w_smem = smem;                                          // this CTA's 32 output channels of every tap, resident
+  uint8_t* staging = smem + ((ntaps * kStemTf32TapBytes + 1023) & ~1023);   // ONE 32 KB staging tile: two [128 px x 32 ch] halves
+  uint8_t* stage_base = staging + 2 * kStemTf32StagingBytes;
+  float* s_scale = reinterpret_cast<float*>(stage_base + p.n_stages * p.stage_bytes);
+  float* s_shift = s_scale + 64;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 64);  // used in the leader only
+  uint64_t* empty_bar = full_bar + kStemMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kStemMaxStages;            // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                    // [2] leader only: arrivals from both CTAs' epilogue warps
+  uint64_t* w_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.n_stages;
+  const int i_first = (int)(blockIdx.x >> 1), i_step = (int)(gridDim.x >> 1);
+  const int n_items = (p.num_tiles + 1) >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmE);
+    tma_prefetch_desc(&tmOdd);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 2 * 4);   // four epilogue warps in each CTA
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+    // this CTA's half of the weights (rows 32 crank .. + 31 of every virtual tap)
+    mbar_arrive_expect_tx(w_bar, (uint32_t)(ntaps * kStemTf32TapBytes));
+    for (int tap = 0; tap < ntaps; ++tap) tma_load_2d(w_smem + tap * kStemTf32TapBytes, &tmW, w_bar, tap * 16, crank * 32);
+    mbar_wait(w_bar, 0);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 128);   // two 64-column accumulators per CTA
+    tmem_relinquish_pair();
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 64) {
+      s_scale[t] = p.scale[t];
+      s_shift[t] = p.shift[t];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers, TMEM and resident weights are in place before anything is signalled or multiplied
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t box_e = (uint32_t)p.box_bytes[0], box_o = (uint32_t)p.box_bytes[1];
+  auto tile_coords = [&](int tile, int& wb, int& hb, int& to, int& n) {
+    int r = tile;
+    wb = r % p.tiles_w; r /= p.tiles_w;
+    hb = r % p.tiles_h; r /= p.tiles_h;
+    to = r % p.To;
+    n = r / p.To;   // == B for the tile-less odd CTA of the last item: every box out of range
+  };
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected thread, both CTAs)
+    if (elect_one_sync()) {
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
+      const uint32_t lfull0 = mapa_u32(full0, 0);
+      const uint32_t tx = (uint32_t)(2 * (p.rows_even + p.rows_odd) * kStemTf32SegBytes);
+      uint32_t s = 0, ph = 0;
+      for (int item = i_first; item < n_items; item += i_step) {
+        int wb, hb, to, n;
+        tile_coords(2 * item + crank, wb, hb, to, n);
+        const int h_start = 2 * (hb * 16) - p.ph;
+        const int x_start = wb * 8 * 4;
+        const int t0 = to * p.st - p.pt;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          mbar_wait_a(empty0 + s * 8, ph ^ 1u);
+          const uint32_t dst = stage0 + s * (uint32_t)p.stage_bytes;
+          const uint32_t fb = lfull0 + s * 8;
+          if (crank == 0) mbar_arrive_expect_tx_a(full0 + s * 8, 2u * tx);   // both CTAs' bytes
+          tma_load_5d_pair(dst, &tmE, fb, x_start, 0, h_start, t0 + dt, n);
+          tma_load_5d_pair(dst + box_e, &tmE, fb, x_start, 1, h_start, t0 + dt, n);
+          tma_load_5d_pair(dst + 2 * box_e, &tmOdd, fb, x_start, 0, h_start + 1, t0 + dt, n);
+          tma_load_5d_pair(dst + 2 * box_e + box_o, &tmOdd, fb, x_start, 1, h_start + 1, t0 + dt, n);
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (crank == 0 && elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_tf32_m256(64);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(stage_base);
+      const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
+      const uint32_t seg16 = kStemTf32SegBytes >> 4;
+      const uint32_t w16 = smem_u32(w_smem) >> 4;
+      const uint64_t a_hi = umma_desc_kmajor_noswizzle(0, 16u, kStemTf32SegBytes);
+      const uint64_t b_hi = umma_desc_kmajor<64>(0);
+      uint32_t s = 0, ph = 0, tc = 0;
+      for (int item = i_first; item < n_items; item += i_step, ++tc) {
+        const uint32_t acc = tc & 1u;
+        mbar_wait_a(tempty0 + acc * 8, ((tc >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained it
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64u;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          mbar_wait_a(full0 + s * 8, ph);
+          tc_fence_after();
+          const uint32_t st16 = (stage0 + s * (uint32_t)p.stage_bytes) >> 4;
+          uint32_t b_lo = w16 + (uint32_t)(dt * p.kh * 2) * (kStemTf32TapBytes >> 4);
+          for (int dh = 0; dh < p.kh; ++dh) {
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+              const uint32_t box16 = ((dh & 1) ? 2 * box_e + (uint32_t)pl * box_o : (uint32_t)pl * box_e) >> 4;
+              const uint64_t adesc = a_hi | (st16 + box16 + (uint32_t)(dh >> 1) * seg16);
+              const uint64_t bdesc = b_hi | b_lo;
+              umma_tf32_pair(d_tmem, adesc, bdesc, idesc, (dt | dh | pl) ? 1u : 0u);
+              umma_tf32_pair(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              b_lo += kStemTf32TapBytes >> 4;
+            }
+          }
+          umma_commit_pair(empty0 + s * 8);                             // frees the slot in both CTAs
+          if (dt == p.kt - 1) umma_commit_pair(tfull0 + acc * 8);       // both CTAs' accumulators complete
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..5 (both CTAs)
+    const int q = warp & 3;
+    const int lrow = q * 32 + lane;
+    const uint32_t xr = (uint32_t)(lrow & 7);
+    const uint32_t staging0 = smem_u32(staging);
+    const uint32_t ltempty0 = mapa_u32(smem_u32(tmem_empty_bar), 0);
+    uint32_t tc = 0;
+    for (int item = i_first; item < n_items; item += i_step, ++tc) {
+      const int tile = 2 * item + crank;
+      int wb, hb, to, n;
+      tile_coords(tile, wb, hb, to, n);
+      const uint32_t acc = tc & 1u;
+      const uint32_t row_addr = staging0 + (uint32_t)lrow * 128u;
+      // single staging tile: the store issued one tile ago (a whole tile time back) must have been read out
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      mbar_wait(&tmem_full_bar[acc], (tc >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u, v0);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u + 32u, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + acc * 8);   // hands this CTA's accumulator back to the leader
+      auto half_tile = [&](const uint32_t (&v)[32], int hc) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int sc = hc * 32 + g * 4;
+          float4 f;
+          f.x = fmaf(__uint_as_float(v[g * 4 + 0]), s_scale[sc + 0], s_shift[sc + 0]);
+          f.y = fmaf(__uint_as_float(v[g * 4 + 1]), s_scale[sc + 1], s_shift[sc + 1]);
+          f.z = fmaf(__uint_as_float(v[g * 4 + 2]), s_scale[sc + 2], s_shift[sc + 2]);
+          f.w = fmaf(__uint_as_float(v[g * 4 + 3]), s_scale[sc + 3], s_shift[sc + 3]);
+          if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+          f.x = tf32_rna(f.x); f.y = tf32_rna(f.y); f.z = tf32_rna(f.z); f.w = tf32_rna(f.w);
+          const uint32_t addr = row_addr + (uint32_t)hc * kStemTf32StagingBytes + ((((uint32_t)g) ^ xr) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
+        }
+      };
+      half_tile(v0, 0);
+      half_tile(v1, 1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (tile < p.num_tiles) {
+          tma_store_5d(&tmO, staging0 + (uint32_t)q * 4096u, 0, wb * 8, hb * 16 + q * 4, to, n);
+          tma_store_5d(&tmO, staging0 + kStemTf32StagingBytes + (uint32_t)q * 4096u, 32, wb * 8, hb * 16 + q * 4, to, n);
+        }
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody leaves while the peer may still signal into this CTA or read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 128);
   }
 }
 

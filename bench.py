@@ -626,6 +626,38 @@ def main():
         except Exception as exc:
             inception_info = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- BASELINE config 3's second precision mode: the same backbone with fp32 activations / weights on tcgen05 kind::tf32
+    # (features within 1e-3 of the fp32 reference); backbone forward at 128 clip-crops, beside the bf16 numbers, never in `value`
+    tf32_info = None
+    if rank == 0 and args.backbone == "i3res50" and os.environ.get("VAD_BENCH_NO_TF32") != "1":
+        try:
+            from anomaly_detection_on_video_b200.engine import ingest_ncthw_tf32
+            model.precision = "tf32"
+            plan32 = model.plan(dev)
+            nb32 = 128
+            x32 = ingest_ncthw_tf32(torch.randn(nb32, 3, 16, 224, 224, device=dev), planes=bool(plan32.ops[0].flags & _lib.VAD_FLAG_STEM_PLANES))
+            for _ in range(3):
+                plan32.forward(x32)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            f0.record()
+            n32 = 10
+            for _ in range(n32):
+                plan32.forward(x32)
+            f1.record()
+            torch.cuda.synchronize(dev)
+            ms32 = f0.elapsed_time(f1) / n32
+            tf32_info = {"model": "I3Res50, precision = tf32", "clip_crops_per_forward": nb32, "ms_per_forward": ms32,
+                         "clips_per_s": nb32 / (ms32 / 1e3), "tflops": nb32 * flop_per_clip / (ms32 / 1e3) / 1e12,
+                         "launches_per_forward": plan32.num_launches, "n_gpus": 1,
+                         "note": "backbone forward from the fp32 plane layout, HBM-resident input; parity 4-6e-4 vs the fp32 reference "
+                                 "goldens (tests/test_gpu_tf32.py); rank 0 only"}
+            del x32, plan32
+        except Exception as exc:
+            tf32_info = {"error": f"{type(exc).__name__}: {exc}"}
+        finally:
+            model.precision = "bf16"
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -731,6 +763,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "head": head_info,
             "inception": inception_info,
+            "tf32": tf32_info,
             "host": host_info,
             "tflops_whole_step": value * flop_per_clip / 1e12,
             "step_breakdown": {"step_ms": ms / K, "profiled_pass_step_ms": (ms_profiled / K) if prof else None,

@@ -131,7 +131,7 @@ def test_stem_folded_window_gather(cuda_device, k, s, same):
 @pytest.mark.parametrize("k,st,B,T,H,W,dst", [((5, 7, 7), 2, 2, 9, 30, 34, (0, 0)), ((5, 7, 7), 2, 1, 16, 224, 224, (0, 0)),
                                               ((1, 7, 7), 1, 2, 4, 50, 38, (0, 0)), ((3, 5, 8), 2, 1, 6, 33, 70, (32, 128)),
                                               ((5, 7, 7), 2, 3, 8, 16, 16, (0, 0))])
-def test_stem_plane_kernel(cuda_device, k, st, B, T, H, W, dst):
+def test_stem_plane_kernel(cuda_device, k, st, B, T, H, W, dst, monkeypatch):
     """VAD_FLAG_STEM_PLANES: the dedicated TF32 stem kernel (stem_tf32_kernel) on the column-parity plane layout --
     sliding 8-pixel windows read by the tensor core out of raw row segments, two CTAs per tile (one per half of the 64 output
     channels), resident fp32 weights -- against fp32 conv3d, incl. ragged tiles (Ho / Wo not multiples of 16 / 8), a
@@ -145,7 +145,10 @@ def test_stem_plane_kernel(cuda_device, k, st, B, T, H, W, dst):
     s, pad = (st, 2, 2), (k[0] // 2, k[1] // 2, 3)
     ref = F.relu(F.conv3d(x, w, None, s, pad) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
     outs = []
-    for planes in (True, False):
+    # the CTA-pair form (two tiles per cluster, N = 64 MMAs reading the weight halves of both CTAs), the single-CTA form
+    # (VAD_TF32_NO_PAIR=1: two CTAs per tile, N = 32), and the gather stem on the plain layout
+    for planes, no_pair in ((True, "0"), (True, "1"), (False, "0")):
+        monkeypatch.setenv("VAD_TF32_NO_PAIR", no_pair)
         pk = eng.ParamPacker()
         w_off, s_off, b_off = pk.add_conv(w, scale, shift, fold_w=True, tf32=True, planes=planes)
         flags = lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W | (lib.VAD_FLAG_STEM_PLANES if planes else 0)
@@ -171,8 +174,9 @@ def test_stem_plane_kernel(cuda_device, k, st, B, T, H, W, dst):
             out = out[..., dst[0]:dst[0] + 64]
         outs.append(out.permute(0, 4, 1, 2, 3))
     close_tf32(outs[0], ref)
-    close_tf32(outs[1], ref)
-    close_tf32(outs[0], outs[1], 5e-4)
+    close_tf32(outs[2], ref)
+    close_tf32(outs[0], outs[2], 5e-4)
+    assert torch.equal(outs[0], outs[1]), "pair and single-CTA stem kernels contract in the same order"
 
 
 def test_pools_and_channel_slices_are_exact(cuda_device):
