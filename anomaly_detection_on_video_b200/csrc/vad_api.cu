@@ -18,6 +18,7 @@
 #include "conv_thalo.cuh"
 #include "conv_s3x3.cuh"
 #include "conv_pair.cuh"
+#include "stem_pair.cuh"
 #include "conv_tail.cuh"
 
 using namespace vad;
@@ -104,6 +105,8 @@ struct OpRuntime {
   bool stem = false;  // dedicated stem kernel (spatial tiles, resident weights)
   StemParams sp;
   CUtensorMap tmE, tmOdd, tmW, tmSO;
+  CUtensorMap tmWh;         // stem_pair: the weight matrix with 32-row boxes (one channel half of a tap)
+  bool stem_pair = false;   // stem on CTA pairs with half of the weights resident per CTA (taps that do not fit one CTA: 7x7x7)
   int stem_smem = 0;
   bool pair_epi = false; // CTA-pair kernel with the staged residual epilogue (conv3 of layer 4: cout % 256 == 0, >= 8 k-blocks)
   CUtensorMap tmBh;      // pair kernels: weight map with (64 x BN/2)-row boxes
@@ -140,6 +143,7 @@ struct vad_plan {
   int sm_count = 148;
   bool stem_v3 = false;      // VAD_STEM_V3=1: one-output-frame-per-tile stem kernel instead of the multi-frame one
   bool stem_generic = false; // VAD_STEM_GENERIC=1: run the stem through the generic implicit-GEMM kernel
+  bool stem_no_pair = false; // VAD_STEM_NO_PAIR=1: a stem whose taps exceed one CTA streams its weights instead of running on CTA pairs
   bool no_epi = false;       // VAD_NO_EPI=1: residual layers use the direct (register) epilogue
   bool no_tail = false;      // VAD_NO_TAIL=1: no conv2 -> conv3 (+ downsample) fusion in layer1 (A/B and bit-identity tests)
   std::vector<std::pair<int, void*>> fold_bufs;  // (op index, 64 KB device buffer): BN-scaled [W3 | Wd] of a tail = 2 op
@@ -252,6 +256,7 @@ extern "C" int32_t vad_plan_create(vad_plan_t** plan, const vad_op_desc* ops, in
   { const char* k = getenv("VAD_NO_THALO"); p->no_thalo = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR"); p->pair_mode = k ? atoi(k) : 1; }
   { const char* k = getenv("VAD_NO_BK32"); p->no_bk32 = k && k[0] == '1'; }
+  { const char* k = getenv("VAD_STEM_NO_PAIR"); p->stem_no_pair = k && k[0] == '1'; }
   { const char* k = getenv("VAD_NO_PAIR_SPLIT"); p->no_pair_split = k && k[0] == '1'; }
   { const char* k = getenv("VAD_PAIR_MIN_KB"); p->pair_min_kb = k ? atoi(k) : 12; }
   { const char* k = getenv("VAD_PAIR_EPI_MIN_KB"); p->pair_epi_min_kb = k ? atoi(k) : 8; }
@@ -475,7 +480,11 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         q.off_odd = (int)align_up((uint64_t)q.rows_even * q.seg_bytes, 128);
         q.stage_bytes = (int)align_up((uint64_t)q.off_odd + (uint64_t)q.rows_odd * q.seg_bytes, 128);
         int w_bytes = d.kt * d.kh * kStemTapBytes;
-        if (w_bytes > 150 * 1024) {
+        r.stem_pair = w_bytes > 150 * 1024 && w_bytes <= 300 * 1024 && q.pool_t == 1 && (p->sm_count & 1) == 0 && !p->stem_no_pair;
+        if (r.stem_pair) {
+          // too many taps for one CTA (7x7x7: 196 KB): a CTA pair, each CTA keeping half of the output channels' weights resident
+          w_bytes = (int)align_up((uint64_t)w_bytes / 2, 1024);
+        } else if (w_bytes > 150 * 1024) {
           // too many taps to keep resident (7x7x7: 196 KB): the kh taps of one dt ride in that dt's stage
           q.w_stream = 1;
           q.off_w = (int)align_up((uint64_t)q.stage_bytes, 1024);
@@ -487,7 +496,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
         if (ns > kStemMaxStages) ns = kStemMaxStages;
         // multi-frame variant: all output frames of a spatial tile live in TMEM (8 x 64 columns), input frames are
         // walked once; needs the I3D temporal geometry (kt 5, stride 2, pad 2) and at most 8 output frames
-        r.stem_mf = !p->stem_v3 && d.kt == 5 && d.st == 2 && pt == 2 && To <= 8 && To >= 1 && d.kh <= 7;
+        r.stem_mf = !r.stem_pair && !p->stem_v3 && d.kt == 5 && d.st == 2 && pt == 2 && To <= 8 && To >= 1 && d.kh <= 7;
         if (r.stem_mf) {
           nu = (long long)batch * q.tiles_h * q.tiles_w;
           r.stem_ti = src.T;
@@ -501,6 +510,10 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
           r.stem_smem = fixed + ns * q.stage_bytes;
           r.stem = true;
           r.grid = q.num_units < p->sm_count ? q.num_units : p->sm_count;
+          if (r.stem_pair) {   // one item = two tiles
+            const int items = (q.num_units + 1) / 2, pairs = p->sm_count / 2;
+            r.grid = 2 * (items < pairs ? items : pairs);
+          }
         }
       }
       if (pool_t2 && fold) {
@@ -812,6 +825,12 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
           cr = p->encode_tiled(&r.tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), wdim, wstr, wbox,
                                wes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cr == CUDA_SUCCESS && r.stem_pair) {
+            cuuint32_t hbox[2] = {32, 32};
+            cr = p->encode_tiled(&r.tmWh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(p->params + d.w_off), wdim, wstr, hbox,
+                                 wes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          }
         }
         if (cr == CUDA_SUCCESS) {
           // output [N, To_out, Ho, Wo, Cdst] (channel slice at c.out): one store per epilogue warp = 64 channels x
@@ -1122,7 +1141,15 @@ static int32_t run_ops(vad_plan* p, const void* x_dev, void* workspace_dev, floa
           e = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
           stem_attr = (e == cudaSuccess);
         }
-        if (e == cudaSuccess && r.stem_mf) {
+        if (e == cudaSuccess && r.stem_pair) {
+          static bool pair_attr = false;
+          if (!pair_attr) {
+            e = cudaFuncSetAttribute(stem_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            pair_attr = (e == cudaSuccess);
+          }
+          if (e == cudaSuccess)
+            e = launch_k(stem_umma_pair_kernel, r.grid, kStemPairThreads, (size_t)r.stem_smem, st, g_pdl, 2, r.tmE, r.tmOdd, r.tmWh, r.tmSO, r.sp);
+        } else if (e == cudaSuccess && r.stem_mf) {
           static bool mf_attr = false;
           if (!mf_attr) {
             e = cudaFuncSetAttribute(stem_umma_mf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -158,7 +158,7 @@ def test_stem_through_the_generic_kernel(cuda_device, k, kps, monkeypatch):
     assert_bf16_close(plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3), ref)
 
 
-@pytest.mark.parametrize("shape", [(1, 16, 224, 224), (2, 9, 50, 38), (1, 4, 32, 32)])
+@pytest.mark.parametrize("shape", [(1, 16, 224, 224), (2, 9, 50, 38), (1, 4, 32, 32), (3, 5, 16, 8)])
 def test_inception_stem_streams_its_weights(cuda_device, shape, monkeypatch):
     """The 7x7x7 / 2 SAME-padded stem of the Inception port through the dedicated stem kernel: its 49 taps (196 KB) do not
     fit in shared memory next to the pipeline, so the 7 taps of each frame tap travel with that frame's stage
@@ -180,15 +180,18 @@ def test_inception_stem_streams_its_weights(cuda_device, shape, monkeypatch):
     ops = [eng.Op(kind=lib.VAD_OP_CONV, src=0, dst=1, cin=4, cout=64, kernel=k, stride=s_,
                   flags=lib.VAD_FLAG_RELU | lib.VAD_FLAG_STEM_FOLD_W | lib.VAD_FLAG_CONV_SAME, w_off=w_off, scale_off=s_off, shift_off=b_off)]
     outs = []
-    for generic in ("0", "1"):
+    # default: CTA pairs, each CTA keeping half of the output channels' taps resident (stem_umma_pair_kernel); VAD_STEM_NO_PAIR=1:
+    # one CTA per tile with the weights streamed per stage; VAD_STEM_GENERIC=1: the generic implicit-GEMM kernel
+    for generic, no_pair in (("0", "0"), ("0", "1"), ("1", "0")):
         monkeypatch.setenv("VAD_STEM_GENERIC", generic)
+        monkeypatch.setenv("VAD_STEM_NO_PAIR", no_pair)
         plan = eng.BackbonePlan(ops, pk.blob(), 2, 2, cuda_device)
         plan.forward(eng.ingest_ncthw(x.to(cuda_device), 2))
         torch.cuda.synchronize()
         outs.append(plan.slot_tensor(1).float().cpu().permute(0, 4, 1, 2, 3).clone())
     assert outs[0].shape == ref.shape
     assert_bf16_close(outs[0], ref)
-    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 @pytest.mark.parametrize("shape,slice_", [((1, 16, 224, 224), (0, 0)), ((2, 10, 64, 48), (0, 0)), ((1, 8, 50, 38), (64, 192))])
