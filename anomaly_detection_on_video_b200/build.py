@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libvad_b200.so")
 SOURCES = ["vad_api.cu"]
-HEADERS = ["ptx_sm100.cuh", "conv_umma.cuh", "stem_umma.cuh", "conv_thalo.cuh", "conv_s3x3.cuh", "conv_pair.cuh", "stem_pair.cuh", "conv_tail.cuh", "aux_kernels.cuh", "aux_api.cuh", "head_kernels.cuh", "head_api.cuh", "head_train_kernels.cuh", "head_train_api.cuh", "tf32_kernels.cuh", "tf32_api.cuh", os.path.join("..", "..", "include", "vad_b200.h")]
+HEADERS = ["ptx_sm100.cuh", "conv_umma.cuh", "stem_umma.cuh", "conv_thalo.cuh", "conv_s3x3.cuh", "conv_pair.cuh", "stem_pair.cuh", "conv_tail.cuh", "aux_kernels.cuh", "aux_api.cuh", "plan_configure.cuh", "plan_bind.cuh", "plan_run.cuh", "head_kernels.cuh", "head_api.cuh", "head_train_kernels.cuh", "head_train_api.cuh", "tf32_kernels.cuh", "tf32_api.cuh", os.path.join("..", "..", "include", "vad_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
