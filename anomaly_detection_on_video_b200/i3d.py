@@ -69,7 +69,7 @@ class _NativeBackbone(nn.Module):
         self.fuse_stem_pool = True  # temporal half of maxpool1 in the stem epilogue (VAD_FLAG_POOL_T2)
         self.fuse_pool2 = False     # maxpool2 in layer1's last conv3 epilogue; set per forward from the clip length
         # "bf16" (production: bf16 activations / weights, fp32 accumulate) or "tf32" (fp32 activations / weights, tcgen05
-        # kind::tf32 MMAs, general kernels only: features within 1e-3 of the reference's fp32 path)
+        # kind::tf32 MMAs; dedicated stem + CTA-pair kernels, otherwise general ones: features within 1e-3 of the reference's fp32 path)
         self.precision = "bf16"
         self.tf32_stem_planes = True  # tf32 mode: dedicated stem kernel on the column-parity plane layout (False: gather stem)
 
