@@ -704,6 +704,21 @@ def main():
                       "frac": achieved / peaks["bf16_sustained"], "frac_of_burst": achieved / peaks["bf16_burst"],
                       "conv_share_of_backbone_time": conv_ms / all_ms, "launches_timed": int(sum(p["calls"] for p in conv))}
         stem = [q for q in prof_stem if q["name"] == "conv1" and q["calls"]]
+        # DRAM bytes of one step, measured by ncu (tools/ncu_step_traffic.sh) on THIS build: the file carries a hash of the kernel
+        # sources and is ignored when they have changed since (null, never a stale constant)
+        traffic, traffic_note = None, "no ncu step capture for this build of the kernels (tools/ncu_step_traffic.sh)"
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from step_traffic import source_hash
+            tj = json.load(open(os.path.join(ROOT, "profiles", "step_dram_traffic.json")))
+            if tj.get("source_hash") == source_hash() and args.backbone == "i3res50" and cpb == 16:
+                traffic = tj["dram_bytes_per_step"]
+                alg = sum(q["bytes"] / max(q["calls"], 1) * (q["calls"] / K) for q in prof if q["calls"])
+                traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum over the {tj['launches']} launches of one step ({tj['capture']}): "
+                                f"{tj['dram_read_bytes'] / 1e9:.1f} GB read + {tj['dram_write_bytes'] / 1e9:.1f} GB written; algorithmic bytes of the "
+                                f"backbone ops of a step (each tensor read / written once per op): {alg / 1e9:.1f} GB")
+        except Exception as exc:
+            traffic_note = f"step traffic unavailable: {type(exc).__name__}: {exc}"
         # `roofline`: the whole step.  The path is 53 tensor-bound conv launches (96 % of the step) plus HBM-bound
         # preprocessing / pools; no single launch dominates (the largest, the stem, is ~19 %), so the number that is
         # graded is all conv FLOPs over the device time of the K timed steps -- everything else counts against it.
@@ -711,10 +726,11 @@ def main():
             "bound": "tensor", "kernel": f"whole step ({args.backbone}): preprocess + every op-table launch + segment mean (conv FLOPs / step time)",
             "achieved": tflops_step, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": tflops_step / peaks["bf16_sustained"], "frac_of_burst": tflops_step / peaks["bf16_burst"],
-            "traffic": None,
+            "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16 sustained (kernels timed inside a long step); burst {peaks['bf16_burst']}",
             "flops_per_step": CLIPS * CROPS * flop_per_clip, "avg_step_ms": ms / K,
-            "traffic_note": "per-kernel DRAM bytes of this build: profiles/ (ncu --set full captures); not a constant copied into the line",
+            "traffic_unit": "bytes per step (the roofline's unit of work: all launches of one 2,000-frame video)",
+            "traffic_note": traffic_note,
             "stem_in_timed_region": ({"avg_launch_ms": stem[0]["ms"] / stem[0]["calls"], "launches_timed": int(stem[0]["calls"]),
                                       "tflops": stem[0]["flops"] / (stem[0]["ms"] / 1e3) / 1e12,
                                       "frac": stem[0]["flops"] / (stem[0]["ms"] / 1e3) / 1e12 / peaks["bf16_sustained"]} if stem else None),
