@@ -93,6 +93,14 @@ class OpDesc(ctypes.Structure):
         ("w_off", c_uint64),
         ("scale_off", c_uint64),
         ("shift_off", c_uint64),
+        ("dst1", c_int32),
+        ("dst2", c_int32),
+        ("split1", c_int32),
+        ("split2", c_int32),
+        ("seg_w0", c_int32),
+        ("seg_w1", c_int32),
+        ("seg_w2", c_int32),
+        ("reserved0", c_int32),
     ]
 
 

@@ -58,6 +58,11 @@ struct ConvParams {
   const float* shift;
   const __nv_bfloat16* res;
   __nv_bfloat16* out;
+  // fused sibling 1x1x1 convs (vad_op_desc.dst1 ...; direct epilogue of conv_umma_kernel): output columns
+  // [split1, split2) go to out1 (row pitch ldo1), [split2, N) to out2; of each part only the first seg_w columns are stored
+  __nv_bfloat16* out1;
+  __nv_bfloat16* out2;
+  int ldo1, ldo2, split1, split2, seg_w0, seg_w1, seg_w2;
 };
 
 constexpr int kBlockM = 128;
@@ -504,10 +509,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         continue;
       }
       const bool row_ok = row < p.M;
-      __nv_bfloat16* out_row = p.out + (long long)row * p.ldo + n0 + col0;
       const __nv_bfloat16* res_row = p.res ? p.res + (long long)row * p.ldr + n0 + col0 : nullptr;
 #pragma unroll 1
       for (int c = 0; c < CPW / 32; ++c) {
+        // destination of this 32-column chunk: the op's own, or one of the sibling outputs of a fused 1x1x1 conv (parts start on
+        // multiples of 64 columns, so a chunk never straddles two of them)
+        const int gc = n0 + col0 + c * 32;   // first output column of the chunk
+        __nv_bfloat16* o_base = p.out;
+        int o_ld = p.ldo, o_start = 0, o_lim = p.N;
+        if (p.split1) {
+          if (gc >= p.split2)      { o_base = p.out2; o_ld = p.ldo2; o_start = p.split2; o_lim = p.split2 + p.seg_w2; }
+          else if (gc >= p.split1) { o_base = p.out1; o_ld = p.ldo1; o_start = p.split1; o_lim = p.split1 + p.seg_w1; }
+          else                     { o_lim = p.seg_w0; }
+        }
+        __nv_bfloat16* out_chunk = o_base + (long long)row * o_ld + (gc - o_start);
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
@@ -515,7 +530,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = c * 32 + g * 8;  // relative to col0
-            if (n0 + col0 + col < p.N) {
+            if (gc + g * 8 < o_lim) {
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -530,7 +545,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint4 o;
               if (p.relu) { o.x = pack_bf16x2_relu(f[0], f[1]); o.y = pack_bf16x2_relu(f[2], f[3]); o.z = pack_bf16x2_relu(f[4], f[5]); o.w = pack_bf16x2_relu(f[6], f[7]); }
               else        { o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]); }
-              *reinterpret_cast<uint4*>(out_row + col) = o;
+              *reinterpret_cast<uint4*>(out_chunk + g * 8) = o;
             }
           }
         }

@@ -19,6 +19,8 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
       const bool fold = d.flags & VAD_FLAG_STEM_FOLD_W;
       c.in = reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.src)) + (fold ? (p->in_pad_left - r.pf[2]) * 4 : 0);
       c.out = reinterpret_cast<__nv_bfloat16*>(slot_ptr(d.dst)) + d.dst_c_off;
+      c.out1 = d.dst1 > 0 ? reinterpret_cast<__nv_bfloat16*>(slot_ptr(d.dst1)) : nullptr;   // fused sibling 1x1x1 convs
+      c.out2 = (d.dst1 > 0 && d.dst2 > 0) ? reinterpret_cast<__nv_bfloat16*>(slot_ptr(d.dst2)) : nullptr;
       c.res = d.res >= 0 ? reinterpret_cast<const __nv_bfloat16*>(slot_ptr(d.res)) : nullptr;
       c.scale = reinterpret_cast<const float*>(p->params + d.scale_off);
       c.shift = reinterpret_cast<const float*>(p->params + d.shift_off);

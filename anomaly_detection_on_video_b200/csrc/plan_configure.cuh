@@ -54,8 +54,20 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       const int pt = r.pf[0], ph = r.pf[1], pw = r.pf[2];
       const bool sym_pad = r.pf[0] == r.pb[0] && r.pf[1] == r.pb[1] && r.pf[2] == r.pb[2];
       if (To <= 0 || Ho <= 0 || Wo <= 0) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: empty output", i);
-      Cdst = d.dst_c_total ? d.dst_c_total : d.cout;
-      if (d.dst_c_off + d.cout > Cdst) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: channel slice exceeds dst_c_total", i);
+      Cdst = d.dst_c_total ? d.dst_c_total : (d.dst1 > 0 ? d.seg_w0 : d.cout);
+      if (d.dst1 <= 0 && d.dst_c_off + d.cout > Cdst) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: channel slice exceeds dst_c_total", i);
+      const bool multi = d.dst1 > 0;   // fused sibling 1x1x1 convs: output columns routed to up to three slots
+      if (multi) {
+        const bool unit1 = d.kt == 1 && d.kh == 1 && d.kw == 1 && d.st == 1 && d.sh == 1 && d.sw == 1;
+        const int s2 = d.dst2 > 0 ? d.split2 : d.cout;
+        if (!unit1 || d.res >= 0 || fold || d.dst1 >= p->n_slots || d.dst2 >= p->n_slots || d.dst1 == d.src || d.dst2 == d.src ||
+            d.dst1 == d.dst || (d.dst2 > 0 && (d.dst2 == d.dst || d.dst2 == d.dst1)) || d.split1 <= 0 || d.split1 % 64 || s2 % 64 && d.dst2 > 0 ||
+            d.split1 >= s2 || s2 > d.cout || (d.dst2 > 0 && s2 >= d.cout) || d.seg_w0 <= 0 || d.seg_w0 > d.split1 || d.seg_w0 % 8 ||
+            d.seg_w1 <= 0 || d.seg_w1 > s2 - d.split1 || d.seg_w1 % 8 || (d.dst2 > 0 && (d.seg_w2 <= 0 || d.seg_w2 > d.cout - s2 || d.seg_w2 % 8)) ||
+            d.dst_c_off + d.seg_w0 > Cdst || (d.flags & VAD_FLAG_POOL_T2))
+          return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: bad fused-sibling description (1x1x1 stride 1, no residual; parts start on multiples of "
+                      "64 columns, widths multiples of 8 inside their parts, distinct slots)", i);
+      }
       const long long M = (long long)batch * To * Ho * Wo;
       if (M > 0x7fffffffLL - 256) return fail(VAD_ERR_INVALID_ARGUMENT, "op %zu: too many output pixels (%lld)", i, M);
       if (fold && d.sw * (Wo - 1) - pw + p->in_pad_left + 7 > src.W - 1)
@@ -86,7 +98,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       r.bk = 64;
       // Cin % 64 == 32 (Inception's 96 / 160 / 480-channel inputs, 32-channel 5x5 branches): TMA operands with 32-wide
       // k-blocks (64-byte rows, SWIZZLE_64B) -- direct epilogue only; anything else that is not a multiple of 64: gather
-      const bool epi_wanted = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
+      const bool epi_wanted = !multi && !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
       // ... and Cin % 32 == 16 (16 / 48 / 112 / 144 / 528 channels) with 16-wide ones (32-byte rows, SWIZZLE_32B, one MMA each)
       const int sub_k = (fold || epi_wanted || p->no_bk32) ? 0 : ((d.cin % 64) == 32 ? 32 : ((d.cin % 32) == 16 ? 16 : 0));
       const bool half_k = sub_k != 0;
@@ -106,9 +118,15 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       c.num_kb = r.bk == 64 ? r.K_pad / 64 : (K + r.bk - 1) / r.bk;
       // staged epilogue (two 128 x BN tiles in smem, TMA store; residual prefetched by TMA): residual layers, and
       // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections)
-      r.epi = !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
-      r.bn = (d.cout > 128 && !r.epi && r.bk == 64) ? 256 : (d.cout > 64 ? 128 : 64);
-      r.pair_epi = r.epi && p->pair_mode > 0 && p->pair_epi_min_kb > 0 && d.res >= 0 && r.a_mode != A_GATHER && r.bk == 64 && d.cout % 256 == 0 &&
+      r.epi = !multi && !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
+      if (multi) r.epi = false;   // parts are routed per 32-column chunk by the direct epilogue of the generic (single-CTA) kernel
+      r.bn = (d.cout > 128 && !r.epi && r.bk == 64 && !multi) ? 256 : (d.cout > 64 ? 128 : 64);   // fused siblings: 128-wide tiles waste less of a ragged N
+      if (multi) {
+        c.split1 = d.split1; c.split2 = d.dst2 > 0 ? d.split2 : d.cout;
+        c.seg_w0 = d.seg_w0; c.seg_w1 = d.seg_w1; c.seg_w2 = d.dst2 > 0 ? d.seg_w2 : 0;
+        c.ldo1 = d.seg_w1; c.ldo2 = d.seg_w2;
+      }
+      r.pair_epi = !multi && r.epi && p->pair_mode > 0 && p->pair_epi_min_kb > 0 && d.res >= 0 && r.a_mode != A_GATHER && r.bk == 64 && d.cout % 256 == 0 &&
                    !(d.flags & VAD_FLAG_POOL_T2) && (p->sm_count % 2) == 0 && c.num_kb >= p->pair_epi_min_kb && M > kBlockM;
       if (r.pair_epi) r.bn = 256;
       r.kps = (r.a_mode != A_GATHER && r.bk == 64 && r.bn <= 128 && c.num_kb >= 2 && !r.epi) ? 2 : 1;
@@ -166,7 +184,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       c.num_tiles = (int)(m_tiles * n_tiles);
       r.grid = c.num_tiles < p->sm_count ? c.num_tiles : p->sm_count;  // persistent: one CTA per SM
       // CTA pairs pay off where the L2 -> shared-memory path is the limit (long K); short-K layers are output bound
-      r.pair = p->pair_mode > 0 && (r.bn == 256 || r.bn == 128) && !r.epi && r.a_mode != A_GATHER && r.bk == 64 && !r.thalo && !r.s3 &&
+      r.pair = !multi && p->pair_mode > 0 && (r.bn == 256 || r.bn == 128) && !r.epi && r.a_mode != A_GATHER && r.bk == 64 && !r.thalo && !r.s3 &&
                !r.pool_tp && d.cout % r.bn == 0 && (p->sm_count % 2) == 0 && m_tiles >= 2 && c.num_kb >= p->pair_min_kb;
       if (r.pair || r.pair_epi) {
         c.mc_items = (int)(((m_tiles + 1) / 2) * n_tiles);
@@ -263,7 +281,8 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       }
       if (r.pool_tp) To = To / 2;  // shape of the dst slot (the residual above has the unpooled shape)
       const int cin_real = fold ? 3 : d.cin;
-      p->op_flops[i] = 2.0 * (double)M * d.cout * d.kt * d.kh * d.kw * cin_real;  // frames the reference conv produces
+      const int cout_real = d.dst1 > 0 ? d.seg_w0 + d.seg_w1 + (d.dst2 > 0 ? d.seg_w2 : 0) : d.cout;   // fused siblings: without the alignment gaps
+      p->op_flops[i] = 2.0 * (double)M * cout_real * d.kt * d.kh * d.kw * cin_real;  // frames the reference conv produces
       p->flops += p->op_flops[i];
       // activations read once, weights once, output written once (+ residual read)
       p->op_bytes[i] = 2.0 * ((double)batch * src.T * src.H * src.W * src.C + (double)d.cout * r.K_pad +
@@ -314,6 +333,16 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
     }
     const uint64_t bytes = (uint64_t)batch * To * Ho * Wo * Cdst * 2;
     if (bytes > dst.bytes) dst.bytes = bytes;
+    if (d.kind == VAD_OP_CONV && d.dst1 > 0) {   // the sibling outputs of a fused 1x1x1 conv: tensors of exactly seg_w channels
+      const int extra[2][2] = {{d.dst1, d.seg_w1}, {d.dst2, d.seg_w2}};
+      for (int e = 0; e < 2; ++e) {
+        if (extra[e][0] <= 0) continue;
+        SlotInfo& ds = p->slots[extra[e][0]];
+        ds.T = To; ds.H = Ho; ds.W = Wo; ds.C = extra[e][1]; ds.defined = true;
+        const uint64_t b2 = (uint64_t)batch * To * Ho * Wo * extra[e][1] * 2;
+        if (b2 > ds.bytes) ds.bytes = b2;
+      }
+    }
   }
   // ---- bottleneck-tail fusion: a (1,3,3) 64 -> 64 halo-tile conv whose output feeds only the next 1x1x1 64 -> 256
   // residual conv runs both in one launch (conv_tail.cuh); when the residual is the block's own 1x1x1 downsample of a

@@ -64,6 +64,8 @@ extern "C" int32_t vad_tf32_plan_create(vad_tf32_plan_t** plan, const vad_op_des
       return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: bad dst slot %d", i, d.dst);
     if (d.flags & VAD_FLAG_POOL_T2)
       return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: the TF32 mode takes the unfused op table (no POOL_T2)", i);
+    if (d.kind == VAD_OP_CONV && d.dst1 > 0)
+      return fail(VAD_ERR_INVALID_ARGUMENT, "op %d: the TF32 mode takes the unfused op table (no fused sibling convs)", i);
     if (d.flags & VAD_FLAG_STEM_PLANES) {
       if (i != 0 || d.kind != VAD_OP_CONV || !(d.flags & VAD_FLAG_STEM_FOLD_W) || d.src != 0 || d.cin != 4 || d.cout != 64 || d.sh != 2 ||
           d.sw != 2 || d.pw != 3 || d.kw > 8 || d.kh < 2 || d.kt * d.kh > 36 || d.res >= 0 || (d.flags & VAD_FLAG_CONV_SAME) || in_channels != 4)

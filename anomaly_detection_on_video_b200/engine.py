@@ -45,6 +45,12 @@ class Op:
     scale_off: int = 0
     shift_off: int = 0
     name: str = ""
+    # sibling 1x1x1 convs fused into one launch (vad_op_desc.dst1 ...): columns [split1, split2) -> slot dst1, [split2, cout) -> dst2
+    dst1: int = 0
+    dst2: int = 0
+    split1: int = 0
+    split2: int = 0
+    seg_w: Tuple[int, int, int] = (0, 0, 0)
 
     def to_c(self) -> OpDesc:
         d = OpDesc()
@@ -56,6 +62,8 @@ class Op:
         d.flags = self.flags
         d.dst_c_off, d.dst_c_total = self.dst_c_off, self.dst_c_total
         d.w_off, d.scale_off, d.shift_off = self.w_off, self.scale_off, self.shift_off
+        d.dst1, d.dst2, d.split1, d.split2 = self.dst1, self.dst2, self.split1, self.split2
+        d.seg_w0, d.seg_w1, d.seg_w2 = self.seg_w
         return d
 
 

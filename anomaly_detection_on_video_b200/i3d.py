@@ -112,7 +112,8 @@ class _NativeBackbone(nn.Module):
     def plan(self, device: torch.device):
         if self.precision not in ("bf16", "tf32"):
             raise ValueError(f"precision must be 'bf16' or 'tf32', not {self.precision!r}")
-        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool, self.fuse_pool2, self.precision, self.tf32_stem_planes)
+        key = (self._param_key(), str(device), self.force_gather, self.fuse_stem_pool, self.fuse_pool2, self.precision, self.tf32_stem_planes,
+               getattr(self, "fuse_siblings", None), getattr(self, "pad_branches", None))
         if self._plan is None or self._plan_key != key:
             ops, packer, n_slots = self._build_table()
             if self.precision == "tf32":

@@ -96,6 +96,7 @@ class InceptionI3d(_NativeBackbone):
             raise NotImplementedError("only the RGB stream is built (the flow stream has 2 input channels)")
         self.fuse_stem_pool = False
         self.pad_branches = True   # BRANCH_PAD; False keeps every temporary at its nominal width (A/B and tests)
+        self.fuse_siblings = True  # b0 | b1a | b2a of a Mixed block as one launch (bf16 mode); False: three launches
         self.Conv3d_1a_7x7 = Unit3D(3, 64, (7, 7, 7), (2, 2, 2))
         self.MaxPool3d_2a_3x3 = MaxPool3dSamePadding((1, 3, 3), (1, 2, 2))
         self.Conv3d_2b_1x1 = Unit3D(64, 64)
@@ -148,6 +149,32 @@ class InceptionI3d(_NativeBackbone):
                   kernel=tuple(conv.kernel_size), stride=tuple(conv.stride), pad=(0, 0, 0), flags=flags, dst_c_off=off,
                   dst_c_total=total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
 
+    def _siblings(self, pk: ParamPacker, m: "InceptionModule", src: int, dst: int, t1: int, t2: int, name: str, total: int,
+                  w1: int, w2: int) -> Op:
+        """b0 | b1a | b2a of one Mixed block as one 1x1x1 conv: the weight matrix stacks their output channels, every sibling
+        starting on a multiple of 64 columns (zero rows in between, never stored); columns [0, split1) -> the concat slice,
+        [split1, split2) -> branch temporary t1 (w1 channels incl. the BRANCH_PAD zeros), [split2, ..) -> t2 (w2 channels)."""
+        units = (m.b0, m.b1a, m.b2a)
+        cin = m.b0.conv3d.in_channels
+        b0 = m.b0.conv3d.out_channels
+        split1 = (b0 + 63) // 64 * 64
+        split2 = split1 + (w1 + 63) // 64 * 64
+        cout = split2 + w2
+        dev = m.b0.conv3d.weight.device
+        w = torch.zeros(cout, cin, 1, 1, 1, dtype=torch.float32, device=dev)
+        sc = torch.zeros(cout, dtype=torch.float32, device=dev)
+        sh = torch.zeros(cout, dtype=torch.float32, device=dev)
+        for u, start in zip(units, (0, split1, split2)):
+            n = u.conv3d.out_channels
+            scale, shift = fold_bn(u.bn.weight, u.bn.bias, u.bn.running_mean, u.bn.running_var, u.bn.eps)
+            w[start:start + n] = u.conv3d.weight.detach().float()
+            sc[start:start + n] = scale
+            sh[start:start + n] = shift
+        w_off, s_off, b_off = pk.add_conv(w, sc, sh)
+        return Op(kind=_lib.VAD_OP_CONV, src=src, dst=dst, cin=cin, cout=cout, kernel=(1, 1, 1), stride=(1, 1, 1), pad=(0, 0, 0),
+                  flags=_lib.VAD_FLAG_RELU | _lib.VAD_FLAG_CONV_SAME, dst_c_off=0, dst_c_total=total, w_off=w_off, scale_off=s_off,
+                  shift_off=b_off, name=name + ".b0+b1a+b2a", dst1=t1, dst2=t2, split1=split1, split2=split2, seg_w=(b0, w1, w2))
+
     @staticmethod
     def _pool(p: MaxPool3dSamePadding, src: int, dst: int, name: str) -> Op:
         return Op(kind=_lib.VAD_OP_MAXPOOL, src=src, dst=dst, kernel=p.kernel_size, stride=p.stride, flags=_lib.VAD_FLAG_POOL_SAME,
@@ -172,12 +199,17 @@ class InceptionI3d(_NativeBackbone):
             nxt = 2 if cur == 1 else 1
             total = outs[0] + outs[2] + outs[4] + outs[5]
             # torch.cat([b0, b1, b2, b3], dim=1): every branch writes its channel slice of the output in place
-            ops.append(self._unit(pk, m.b0, cur, nxt, name + ".b0", off=0, total=total))
             p1 = BRANCH_PAD.get(outs[1], 0) if self.pad_branches else 0
             p2 = BRANCH_PAD.get(outs[3], 0) if self.pad_branches else 0
-            ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a", cout_pad=p1))
+            if self.fuse_siblings and self.precision != "tf32" and not self.force_gather:
+                # b0, b1a and b2a are 1x1x1 convs over the same block input, each bound by reading it: ONE launch reads it once and
+                # routes its output columns to the concat slice (b0) and the two branch temporaries (vad_op_desc.dst1 / dst2)
+                ops.append(self._siblings(pk, m, cur, nxt, T1, T2, name, total, p1 or outs[1], p2 or outs[3]))
+            else:
+                ops.append(self._unit(pk, m.b0, cur, nxt, name + ".b0", off=0, total=total))
+                ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a", cout_pad=p1))
+                ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a", cout_pad=p2))
             ops.append(self._unit(pk, m.b1b, T1, nxt, name + ".b1b", off=outs[0], total=total, cin_pad=p1))
-            ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a", cout_pad=p2))
             ops.append(self._unit(pk, m.b2b, T2, nxt, name + ".b2b", off=outs[0] + outs[2], total=total, cin_pad=p2))
             ops.append(self._pool(m.b3a, cur, T3, name + ".b3a"))
             ops.append(self._unit(pk, m.b3b, T3, nxt, name + ".b3b", off=outs[0] + outs[2] + outs[4], total=total))

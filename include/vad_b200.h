@@ -99,6 +99,17 @@ typedef struct vad_op_desc {
                              order is (kt, kh, kw, cin), K_pad = K rounded up to 64, zero padded    */
   uint64_t scale_off;     /* CONV: byte offset of fp32 scale[cout]  (gamma / sqrt(var + eps))       */
   uint64_t shift_off;     /* CONV: byte offset of fp32 shift[cout]  (beta - mean * scale)           */
+  /* Sibling 1x1x1 convs over the same input run as ONE conv (bf16 plans; InceptionI3d's b0 | b1a | b2a): the weight matrix
+   * stacks their output channels, each sibling starting on a multiple of 64 columns, and the output columns are routed to up
+   * to three destinations.  dst1 > 0 switches it on:
+   *   columns [0, split1)      -> slot dst (dst_c_off / dst_c_total as usual), only the first seg_w0 of them are stored
+   *   columns [split1, split2) -> slot dst1 (a tensor of seg_w1 channels)
+   *   columns [split2, cout)   -> slot dst2 (a tensor of seg_w2 channels); dst2 <= 0: no third part, split2 == cout
+   * Columns between a sibling's width and the next start carry zero weights and are not stored.  All zero: ordinary conv. */
+  int32_t dst1, dst2;
+  int32_t split1, split2;
+  int32_t seg_w0, seg_w1, seg_w2;
+  int32_t reserved0;
 } vad_op_desc;
 
 typedef struct vad_plan vad_plan_t;

@@ -51,13 +51,33 @@ def test_widened_branch_temporaries_do_not_change_the_features(model, cuda_devic
     plain.load_state_dict(OI.seeded_state_dict(0), strict=True)
     plain = plain.eval().to(cuda_device)
     widths = {op.name: (op.cin, op.cout) for op in model.op_table()}
-    assert widths["Mixed_4e.b1a"] == (512, 192) and widths["Mixed_4e.b1b"] == (192, 288) and widths["Mixed_3b.b2b"] == (64, 32)
+    assert widths["Mixed_4e.b1b"] == (192, 288) and widths["Mixed_3b.b2b"] == (64, 32)
+    fused = {op.name: op for op in model.op_table()}["Mixed_4e.b0+b1a+b2a"]     # 112 | 144 -> 192 | 32
+    assert (fused.cin, fused.cout, fused.split1, fused.split2, fused.seg_w) == (512, 128 + 192 + 32, 128, 320, (112, 192, 32))
     assert {op.name: (op.cin, op.cout) for op in plain.op_table()}["Mixed_4e.b1b"] == (144, 288)
     x = torch.randn(2, 3, 16, 224, 224, generator=torch.Generator().manual_seed(5)).clamp(-2.0, 2.4444).to(cuda_device)
     a, b = model(x).view(2, -1).float(), plain(x).view(2, -1).float()
     err = float((a - b).abs().max() / b.abs().max())
     print(f"padded vs nominal branch widths: max-normalised difference {err:.2e}")
     assert err <= 2e-3
+
+
+def test_fused_sibling_convs_are_bit_identical(model, cuda_device):
+    """b0 | b1a | b2a of every Mixed block as ONE 1x1x1 conv whose output columns are routed to the concat slice and the two
+    branch temporaries (vad_op_desc.dst1 / dst2): every output element is the same k-ordered contraction as in its own launch,
+    so the features are bit-identical to the three-launch table."""
+    from anomaly_detection_on_video_b200.inception import InceptionI3d
+    from oracle import inception as OI
+
+    three = InceptionI3d()
+    three.fuse_siblings = False
+    three.load_state_dict(OI.seeded_state_dict(0), strict=True)
+    three = three.eval().to(cuda_device)
+    assert len(model.op_table()) == len(three.op_table()) - 2 * 9
+    x = torch.randn(3, 3, 16, 224, 224, generator=torch.Generator().manual_seed(6)).clamp(-2.0, 2.4444).to(cuda_device)
+    a, b = model(x), three(x)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
 
 
 def test_extract_features_is_forward_and_shape_is_checked(model, cuda_device):
