@@ -191,9 +191,17 @@ def test_inception_oracle_layer_table_matches_survey_appendix_b():
     m = InceptionI3d()
     missing, unexpected = m.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
+    m.fuse_siblings = False   # the three-launch table: one op per Unit3D of Appendix B
     ops = m.op_table()
-    convs = [o for o in ops if o.kind == 1 or o.cout]
     assert len(ops) == 71 and sum(1 for o in ops if o.cout) == 57
+    # default table: b0 | b1a | b2a of each of the nine Mixed blocks is one op with routed output columns
+    m.fuse_siblings = True
+    fused = m.op_table()
+    assert len(fused) == 71 - 2 * 9 and sum(1 for o in fused if o.dst1) == 9
+    for o in fused:
+        if o.dst1:
+            assert o.split1 % 64 == 0 and o.split2 % 64 == 0 and o.seg_w[0] <= o.split1 and o.seg_w[1] <= o.split2 - o.split1
+            assert o.seg_w[2] == o.cout - o.split2 and len({o.dst, o.dst1, o.dst2, o.src}) == 4
     # every Inception branch writes a channel slice of the concatenated tensor: slices tile [0, total) exactly
     for name in ("Mixed_3b", "Mixed_4f", "Mixed_5c"):
         sl = sorted((o.dst_c_off, o.cout, o.dst_c_total) for o in ops if o.name.startswith(name) and o.dst_c_total)
