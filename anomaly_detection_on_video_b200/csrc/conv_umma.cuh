@@ -510,8 +510,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const bool row_ok = row < p.M;
       const __nv_bfloat16* res_row = p.res ? p.res + (long long)row * p.ldr + n0 + col0 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < CPW / 32; ++c) {
+      // one 32-column chunk: scale / shift as 128-bit shared-memory loads (the scalar form was 64 dependent LDS per chunk and the
+      // FFMAs behind them were this epilogue's top stall), routed to its destination, 16 bytes per store
+      auto chunk = [&](const uint32_t (&v)[32], int c) {
         // destination of this 32-column chunk: the op's own, or one of the sibling outputs of a fused 1x1x1 conv (parts start on
         // multiples of 64 columns, so a chunk never straddles two of them)
         const int gc = n0 + col0 + c * 32;   // first output column of the chunk
@@ -523,32 +524,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else                     { o_lim = p.seg_w0; }
         }
         __nv_bfloat16* out_chunk = o_base + (long long)row * o_ld + (gc - o_start);
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        if (row_ok) {
+        if (!row_ok) return;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = c * 32 + g * 8;  // relative to col0
-            if (gc + g * 8 < o_lim) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                f[j] = fmaf(__uint_as_float(v[g * 8 + j]), s_scale[col0 + col + j], s_shift[col0 + col + j]);
-              if (res_row) {
-                const uint4 r = *reinterpret_cast<const uint4*>(res_row + col);
-                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-              }
-              uint4 o;
-              if (p.relu) { o.x = pack_bf16x2_relu(f[0], f[1]); o.y = pack_bf16x2_relu(f[2], f[3]); o.z = pack_bf16x2_relu(f[4], f[5]); o.w = pack_bf16x2_relu(f[6], f[7]); }
-              else        { o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]); }
-              *reinterpret_cast<uint4*>(out_chunk + g * 8) = o;
+        for (int g = 0; g < 4; ++g) {
+          const int col = c * 32 + g * 8;  // relative to col0
+          if (gc + g * 8 < o_lim) {
+            const float4 sa = *reinterpret_cast<const float4*>(s_scale + col0 + col), sb = *reinterpret_cast<const float4*>(s_scale + col0 + col + 4);
+            const float4 ha = *reinterpret_cast<const float4*>(s_shift + col0 + col), hb = *reinterpret_cast<const float4*>(s_shift + col0 + col + 4);
+            float f[8];
+            f[0] = fmaf(__uint_as_float(v[g * 8 + 0]), sa.x, ha.x); f[1] = fmaf(__uint_as_float(v[g * 8 + 1]), sa.y, ha.y);
+            f[2] = fmaf(__uint_as_float(v[g * 8 + 2]), sa.z, ha.z); f[3] = fmaf(__uint_as_float(v[g * 8 + 3]), sa.w, ha.w);
+            f[4] = fmaf(__uint_as_float(v[g * 8 + 4]), sb.x, hb.x); f[5] = fmaf(__uint_as_float(v[g * 8 + 5]), sb.y, hb.y);
+            f[6] = fmaf(__uint_as_float(v[g * 8 + 6]), sb.z, hb.z); f[7] = fmaf(__uint_as_float(v[g * 8 + 7]), sb.w, hb.w);
+            if (res_row) {
+              const uint4 r = *reinterpret_cast<const uint4*>(res_row + col);
+              f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+              f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+              f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+              f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
             }
+            uint4 o;
+            if (p.relu) { o.x = pack_bf16x2_relu(f[0], f[1]); o.y = pack_bf16x2_relu(f[2], f[3]); o.z = pack_bf16x2_relu(f[4], f[5]); o.w = pack_bf16x2_relu(f[6], f[7]); }
+            else        { o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]); }
+            *reinterpret_cast<uint4*>(out_chunk + g * 8) = o;
           }
         }
+      };
+      if constexpr (CPW >= 64) {
+#pragma unroll 1
+        for (int c = 0; c < CPW / 32; c += 2) {   // two TMEM loads in flight per wait
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32), v0);
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32 + 32), v1);
+          tmem_ld_wait();
+          chunk(v0, c);
+          chunk(v1, c + 1);
+        }
+      } else {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        chunk(v, 0);
       }
       tc_fence_before();
       __syncwarp();
