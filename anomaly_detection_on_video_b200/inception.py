@@ -47,9 +47,11 @@ MIXED: Tuple[Tuple[str, int, Tuple[int, int, int, int, int, int]], ...] = (
 # channels (zero weight rows in the producing 1x1x1 conv: relu(0 * x + 0) = 0; zero weight columns in the consumer): the
 # consumer then contracts whole 64-channel k-blocks through the im2col TMA path.  Measured per 160 clip-crops (round 2):
 # Cin = 144 (16-wide k-blocks, one 32-byte sector per TMA row) ran at 0.26 of the tensor peak, 112 at 0.28, 16 at 0.05, 24 on
-# the cp.async gather at 0.08; a 64-multiple Cin reaches 0.8, so even 4 x the FLOPs (16 -> 64) is the faster launch.  Internal
-# to a Mixed block: results are unchanged (the extra terms are exact zeros).
-BRANCH_PAD = {16: 64, 24: 64, 48: 64, 112: 128, 144: 192, 160: 192}
+# the cp.async gather at 0.08; a 64-multiple Cin reaches 0.8, so even 4 x the FLOPs (16 -> 64) is the faster launch; 96 -> 128 takes
+# Mixed_3b.b1b off the 32-wide k-block path (0.78 -> 0.65 ms); 32 -> 64 was measured and LOSES (Mixed_3c.b2b 0.33 -> 0.40 ms: that
+# small-N layer is bound by its im2col traffic through L2, which doubles).  Internal to a Mixed block: results are unchanged (the
+# extra terms are exact zeros).
+BRANCH_PAD = {16: 64, 24: 64, 48: 64, 96: 128, 112: 128, 144: 192, 160: 192}
 
 POOL_BEFORE = {"Mixed_4b": ("MaxPool3d_4a_3x3", (3, 3, 3), (2, 2, 2)), "Mixed_5b": ("MaxPool3d_5a_2x2", (2, 2, 2), (2, 2, 2))}
 
