@@ -254,6 +254,8 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
           { const char* sd = getenv("VAD_STEM_DEBUG"); q.dbg = sd ? atoi(sd) : 0; }
           r.stem_smem = fixed + ns * q.stage_bytes;
           r.stem = true;
+          // pair kernel: both tiles of an item must share their output frame for the out-of-clip frame taps to be skipped
+          q.Ti = (r.stem_pair && (q.tiles_w * q.tiles_h) % 2 == 0) ? src.T : 0;
           r.grid = q.num_units < p->sm_count ? q.num_units : p->sm_count;
           if (r.stem_pair) {   // one item = two tiles
             const int items = (q.num_units + 1) / 2, pairs = p->sm_count / 2;

@@ -113,7 +113,9 @@ stem_umma_pair_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
         const int h_start = 2 * (hb * 16) - p.ph;
         const int x_start = wb * 8 * 8;   // 8 windows x (2 px x 4 ch) elements
         const int t0 = to * p.st - p.pt;
-        for (int dt = 0; dt < p.kt; ++dt) {
+        // frame taps outside the clip contribute zeros: skipped (the SAME-padded 7x7x7 stem spends 6 of its 56 (to, dt) pairs there)
+        const int dt_lo = (p.Ti && t0 < 0) ? -t0 : 0, dt_hi = (p.Ti && t0 + p.kt > p.Ti) ? p.Ti - t0 : p.kt;
+        for (int dt = dt_lo; dt < dt_hi; ++dt) {
           mbar_wait_a(empty0 + s * 8, ph ^ 1u);
           const uint32_t dst = stage0 + s * (uint32_t)p.stage_bytes;
           const uint32_t fb = lfull0 + s * 8;
@@ -141,7 +143,11 @@ stem_umma_pair_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
         mbar_wait_a(tempty0 + acc * 8, ((tc >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained it
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 64u;
-        for (int dt = 0; dt < p.kt; ++dt) {
+        int wb_, hb_, to_, n_;
+        tile_coords(2 * item, wb_, hb_, to_, n_);
+        const int t0 = to_ * p.st - p.pt;
+        const int dt_lo = (p.Ti && t0 < 0) ? -t0 : 0, dt_hi = (p.Ti && t0 + p.kt > p.Ti) ? p.Ti - t0 : p.kt;
+        for (int dt = dt_lo; dt < dt_hi; ++dt) {
           mbar_wait_a(full0 + s * 8, ph);
           tc_fence_after();
           const uint32_t st16 = (stage0 + s * (uint32_t)p.stage_bytes) >> 4;
@@ -150,12 +156,12 @@ stem_umma_pair_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
           for (int dh = 0; dh < p.kh; ++dh) {
             const uint64_t adesc = a_hi | (((dh & 1) ? a_odd : a_even) + (uint32_t)(dh >> 1) * seg16);
             const uint64_t bdesc = b_hi | b_lo;
-            umma_f16_pair(d_tmem, adesc, bdesc, idesc, (dt | dh) ? 1u : 0u);
+            umma_f16_pair(d_tmem, adesc, bdesc, idesc, (dt > dt_lo || dh) ? 1u : 0u);
             umma_f16_pair_acc(d_tmem, adesc + 2, bdesc + 2, idesc);
             b_lo += kStemPairTapBytes >> 4;
           }
           umma_commit_pair(empty0 + s * 8);                             // frees the slot in both CTAs
-          if (dt == p.kt - 1) umma_commit_pair(tfull0 + acc * 8);       // both CTAs' accumulators complete
+          if (dt == dt_hi - 1) umma_commit_pair(tfull0 + acc * 8);      // both CTAs' accumulators complete
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
       }

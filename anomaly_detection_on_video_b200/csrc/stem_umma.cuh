@@ -49,6 +49,7 @@ struct StemParams {
                             // 1: the kh taps of frame tap dt travel with dt's stage (InceptionI3d's 7x7x7: 196 KB)
   int off_w;                // w_stream: byte offset of the kh x 4 KB of weights inside a stage (1024-aligned)
   int relu;
+  int Ti;   // input frames when frame taps outside the clip may be skipped (stem_pair.cuh), else 0
   int dbg;  // VAD_STEM_DEBUG bit mask (bottleneck hunting only): 1 = no global stores, 2 = no MMA issue, 4 = no A loads,
             // multi-frame kernel also: 8 = no tcgen05.ld, 16 = no tcgen05.st zeroing, 32 = no epilogue math / staging
   const float* scale;

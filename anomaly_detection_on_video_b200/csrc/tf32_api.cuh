@@ -212,6 +212,8 @@ extern "C" int32_t vad_tf32_plan_configure(vad_tf32_plan_t* p, int32_t batch, in
         // half of the output channels) walk the same tile stream
         const int pairs = p->sm_count / 2;
         r.stem_pair = !p->no_pair && (p->sm_count & 1) == 0;
+        // out-of-clip frame taps are skipped; on pairs only when both tiles of an item share their output frame
+        r.sp.Ti = (!r.stem_pair || (r.sp.tiles_w * r.sp.tiles_h) % 2 == 0) ? src.T : 0;
         const int items = r.stem_pair ? (r.sp.num_tiles + 1) / 2 : r.sp.num_tiles;
         r.grid = 2 * (items < pairs ? items : pairs);
       }

@@ -352,6 +352,8 @@ struct StemTf32Params {
   int stage_bytes;          // 2 * (box_bytes[0] + box_bytes[1])
   int n_stages;
   int relu;
+  int Ti;                   // input frames: frame taps outside the clip are skipped (pair kernel: only when both tiles of an item
+                            // share their output frame, else 0 = no skipping)
   const float* scale;
   const float* shift;
 };
@@ -445,7 +447,8 @@ stem_tf32_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
         const int h_start = 2 * (hb * 16) - p.ph;
         const int x_start = wb * 8 * 4;    // 8 windows, one plane pixel (4 floats) apart
         const int t0 = to * p.st - p.pt;
-        for (int dt = 0; dt < p.kt; ++dt) {
+        const int dt_lo = (p.Ti && t0 < 0) ? -t0 : 0, dt_hi = (p.Ti && t0 + p.kt > p.Ti) ? p.Ti - t0 : p.kt;   // taps inside the clip
+        for (int dt = dt_lo; dt < dt_hi; ++dt) {
           mbar_wait_a(empty0 + s * 8, ph ^ 1u);
           const uint32_t dst = stage0 + s * (uint32_t)p.stage_bytes;
           const uint32_t fb = full0 + s * 8;
@@ -476,7 +479,9 @@ stem_tf32_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
         mbar_wait_a(tempty0 + acc * 8, ((tc >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 32u;
-        for (int dt = 0; dt < p.kt; ++dt) {
+        const int t0 = ((tile / (p.tiles_w * p.tiles_h)) % p.To) * p.st - p.pt;
+        const int dt_lo = (p.Ti && t0 < 0) ? -t0 : 0, dt_hi = (p.Ti && t0 + p.kt > p.Ti) ? p.Ti - t0 : p.kt;
+        for (int dt = dt_lo; dt < dt_hi; ++dt) {
           mbar_wait_a(full0 + s * 8, ph);
           tc_fence_after();
           const uint32_t st16 = (stage0 + s * (uint32_t)p.stage_bytes) >> 4;
@@ -487,13 +492,13 @@ stem_tf32_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant_
               const uint32_t box16 = ((dh & 1) ? 2 * box_e + (uint32_t)pl * box_o : (uint32_t)pl * box_e) >> 4;
               const uint64_t adesc = a_hi | (st16 + box16 + (uint32_t)(dh >> 1) * seg16);
               const uint64_t bdesc = b_hi | b_lo;
-              umma_tf32(d_tmem, adesc, bdesc, idesc, (dt | dh | pl) ? 1u : 0u);
+              umma_tf32(d_tmem, adesc, bdesc, idesc, (dt > dt_lo || dh || pl) ? 1u : 0u);
               umma_tf32(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
               b_lo += kStemTf32TapBytes >> 4;
             }
           }
           umma_commit_a(empty0 + s * 8);
-          if (dt == p.kt - 1) umma_commit_a(tfull0 + acc * 8);
+          if (dt == dt_hi - 1) umma_commit_a(tfull0 + acc * 8);
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
       }
@@ -659,7 +664,8 @@ stem_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
         const int h_start = 2 * (hb * 16) - p.ph;
         const int x_start = wb * 8 * 4;
         const int t0 = to * p.st - p.pt;
-        for (int dt = 0; dt < p.kt; ++dt) {
+        const int dt_lo = (p.Ti && t0 < 0) ? -t0 : 0, dt_hi = (p.Ti && t0 + p.kt > p.Ti) ? p.Ti - t0 : p.kt;   // taps inside the clip
+        for (int dt = dt_lo; dt < dt_hi; ++dt) {
           mbar_wait_a(empty0 + s * 8, ph ^ 1u);
           const uint32_t dst = stage0 + s * (uint32_t)p.stage_bytes;
           const uint32_t fb = lfull0 + s * 8;
@@ -689,7 +695,9 @@ stem_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
         mbar_wait_a(tempty0 + acc * 8, ((tc >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained it
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 64u;
-        for (int dt = 0; dt < p.kt; ++dt) {
+        const int t0 = (((2 * item) / (p.tiles_w * p.tiles_h)) % p.To) * p.st - p.pt;
+        const int dt_lo = (p.Ti && t0 < 0) ? -t0 : 0, dt_hi = (p.Ti && t0 + p.kt > p.Ti) ? p.Ti - t0 : p.kt;
+        for (int dt = dt_lo; dt < dt_hi; ++dt) {
           mbar_wait_a(full0 + s * 8, ph);
           tc_fence_after();
           const uint32_t st16 = (stage0 + s * (uint32_t)p.stage_bytes) >> 4;
@@ -700,13 +708,13 @@ stem_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
               const uint32_t box16 = ((dh & 1) ? 2 * box_e + (uint32_t)pl * box_o : (uint32_t)pl * box_e) >> 4;
               const uint64_t adesc = a_hi | (st16 + box16 + (uint32_t)(dh >> 1) * seg16);
               const uint64_t bdesc = b_hi | b_lo;
-              umma_tf32_pair(d_tmem, adesc, bdesc, idesc, (dt | dh | pl) ? 1u : 0u);
+              umma_tf32_pair(d_tmem, adesc, bdesc, idesc, (dt > dt_lo || dh || pl) ? 1u : 0u);
               umma_tf32_pair(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
               b_lo += kStemTf32TapBytes >> 4;
             }
           }
           umma_commit_pair(empty0 + s * 8);                             // frees the slot in both CTAs
-          if (dt == p.kt - 1) umma_commit_pair(tfull0 + acc * 8);       // both CTAs' accumulators complete
+          if (dt == dt_hi - 1) umma_commit_pair(tfull0 + acc * 8);      // both CTAs' accumulators complete
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
       }
