@@ -12,7 +12,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 SECTIONS = ["conv_tma2d", "conv_im2col", "conv_gather", "conv_stem", "pools", "preproc", "segment", "net_small",

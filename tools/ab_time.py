@@ -16,13 +16,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     from anomaly_detection_on_video_b200.i3d import I3Res50
-    from oracle import i3res50 as O
 
     variants = sys.argv[1:] or ["", "VAD_PAIR=0"]
     dev = torch.device("cuda", 0)
     B = int(os.environ.get("AB_BATCH", "160"))
     xs = torch.randn(B, 16, 224, 232, 4, device=dev).to(torch.bfloat16)
-    sd = O.seeded_state_dict(0)
+    torch.manual_seed(0)
+    sd = I3Res50().state_dict()   # one constructor initialisation shared by every variant
     models = []
     for v in variants:
         kv = [x.split("=", 1) for x in v.split(",") if x]

@@ -14,11 +14,10 @@ import torch
 from anomaly_detection_on_video_b200.dataset import TenCropVideoFrameDataset
 from anomaly_detection_on_video_b200.engine import segment_mean
 from anomaly_detection_on_video_b200.i3d import I3Res50
-from oracle import i3res50 as O
 
 dev = torch.device("cuda", 0)
-m = I3Res50()
-m.load_state_dict(O.seeded_state_dict(0))
+torch.manual_seed(0)
+m = I3Res50()   # constructor initialisation: the kernels' time does not depend on the weights
 m.eval().to(dev)
 frames = torch.from_numpy(np.random.default_rng(0).integers(0, 256, size=(16 * 16, 240, 320, 3), dtype=np.uint8)).to(dev)
 ds = TenCropVideoFrameDataset(frames, device=dev)

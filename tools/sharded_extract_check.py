@@ -43,15 +43,14 @@ def main():
         from anomaly_detection_on_video_b200.extract_features import _rows_from_dir, extract, segment
         from anomaly_detection_on_video_b200.i3d import I3Res50
         from anomaly_detection_on_video_b200.workqueue import WorkQueue
-        from oracle import i3res50 as O  # seeded synthetic weights only
 
         world = int(os.environ.get("WORLD_SIZE", "1"))
         rank = int(os.environ.get("RANK", "0"))
         queue = WorkQueue.from_env()
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dev = torch.device("cuda", torch.cuda.current_device())
+        torch.manual_seed(0)   # every rank and every run: the same constructor initialisation
         model = I3Res50()
-        model.load_state_dict(O.seeded_state_dict(0))
         model.eval().to(dev)
         out = os.path.join(a.dir, f"out_w{world}")
         rows = _rows_from_dir(vdir)
