@@ -211,10 +211,11 @@ class InceptionI3d(_NativeBackbone):
                 ops.append(self._unit(pk, m.b0, cur, nxt, name + ".b0", off=0, total=total))
                 ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a", cout_pad=p1))
                 ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a", cout_pad=p2))
-            ops.append(self._unit(pk, m.b1b, T1, nxt, name + ".b1b", off=outs[0], total=total, cin_pad=p1))
-            ops.append(self._unit(pk, m.b2b, T2, nxt, name + ".b2b", off=outs[0] + outs[2], total=total, cin_pad=p2))
+            # the pooling branch right behind the 1x1x1 convs: it reads the same block input, part of which is still in L2
             ops.append(self._pool(m.b3a, cur, T3, name + ".b3a"))
             ops.append(self._unit(pk, m.b3b, T3, nxt, name + ".b3b", off=outs[0] + outs[2] + outs[4], total=total))
+            ops.append(self._unit(pk, m.b1b, T1, nxt, name + ".b1b", off=outs[0], total=total, cin_pad=p1))
+            ops.append(self._unit(pk, m.b2b, T2, nxt, name + ".b2b", off=outs[0] + outs[2], total=total, cin_pad=p2))
             cur = nxt
         ops.append(Op(kind=_lib.VAD_OP_AVGPOOL, src=cur, name="avg_pool"))
         return ops, pk, 6
