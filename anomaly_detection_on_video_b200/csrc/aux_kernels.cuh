@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256) maxpool3d_fixed_kernel(const PoolParams p
 }
 
 // Padded windows with compile-time extents (the SAME-padding pools of the Inception port between stages: (1,3,3)/(1,2,2),
-// (3,3,3)/(2,2,2), (2,2,2)/(2,2,2)): every tap's 128-bit load is issued (predicated on its bounds) before the first max,
+// (3,3,3)/(2,2,2), (2,2,2)/(2,2,2)): every tap's 128-bit load is issued (out-of-frame taps clamped) before the first max,
 // instead of the dependent load -> max chain of the general kernel.
 // read-only 128-bit load that DOES allocate in L1: neighbouring threads of the sliding-window pool re-read the same lines
 __device__ __forceinline__ uint4 ld_nc_16(const void* ptr) {
@@ -486,7 +486,6 @@ __global__ void __launch_bounds__(256) maxpool3d_checked_kernel(const PoolParams
   const int cv = p.C >> 3;
   const long long total = (long long)p.B * p.To * p.Ho * p.Wo * cv;
   const long long sW = p.C, sH = (long long)p.Wi * p.C, sT = sH * p.Hi;
-  const uint32_t neg_inf2 = 0xFF80FF80u;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
     long long m = i / cv;
@@ -495,19 +494,24 @@ __global__ void __launch_bounds__(256) maxpool3d_checked_kernel(const PoolParams
     const int ho = (int)(m % p.Ho); m /= p.Ho;
     const int to = (int)(m % p.To); m /= p.To;
     const int t0 = to * p.st - p.pt, h0 = ho * p.sh - p.ph, w0 = wo * p.sw - p.pw;
-    const __nv_bfloat16* base = p.in + (m * p.Ti + t0) * sT + (long long)h0 * sH + (long long)w0 * sW + v * 8;
+    // A tap outside the frame is clamped onto the nearest tap inside it: the padding is narrower than the window, so
+    // that tap belongs to the same window and the maximum is unchanged -- and every load is unconditional.
+    const __nv_bfloat16* base = p.in + m * p.Ti * sT + v * 8;
+    long long ot[KT], oh[KH], ow[KW];
+#pragma unroll
+    for (int dt = 0; dt < KT; ++dt) ot[dt] = (long long)min(max(t0 + dt, 0), p.Ti - 1) * sT;
+#pragma unroll
+    for (int dh = 0; dh < KH; ++dh) oh[dh] = (long long)min(max(h0 + dh, 0), p.Hi - 1) * sH;
+#pragma unroll
+    for (int dw = 0; dw < KW; ++dw) ow[dw] = (long long)min(max(w0 + dw, 0), p.Wi - 1) * sW;
+    const bool any_oob = t0 < 0 || h0 < 0 || w0 < 0 || t0 + KT > p.Ti || h0 + KH > p.Hi || w0 + KW > p.Wi;
     uint4 x[KT * KH * KW];
-    bool any_oob = false;
 #pragma unroll
     for (int dt = 0; dt < KT; ++dt)
 #pragma unroll
       for (int dh = 0; dh < KH; ++dh)
 #pragma unroll
-        for (int dw = 0; dw < KW; ++dw) {
-          const bool ok = (unsigned)(t0 + dt) < (unsigned)p.Ti && (unsigned)(h0 + dh) < (unsigned)p.Hi && (unsigned)(w0 + dw) < (unsigned)p.Wi;
-          any_oob |= !ok;
-          x[(dt * KH + dh) * KW + dw] = ok ? ld_stream_16(base + dt * sT + dh * sH + dw * sW) : make_uint4(neg_inf2, neg_inf2, neg_inf2, neg_inf2);
-        }
+        for (int dw = 0; dw < KW; ++dw) x[(dt * KH + dh) * KW + dw] = ld_stream_16(base + ot[dt] + oh[dh] + ow[dw]);
     uint4 acc = x[0];
 #pragma unroll
     for (int k = 1; k < KT * KH * KW; ++k) {

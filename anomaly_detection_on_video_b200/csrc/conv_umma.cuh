@@ -150,7 +150,9 @@ template <int BN, int BK, int KPS, bool GATHER, bool EPI>
 __global__ void __launch_bounds__(ConvCfg<BN, BK, KPS, GATHER, EPI>::kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
-                 const ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmO2, const ConvParams p) {
+  // (tmO2: third output of a fused sibling conv in the staged epilogue; its second output travels in the tmR slot, which such
+  // an op -- no residual -- does not otherwise use)
   using Cfg = ConvCfg<BN, BK, KPS, GATHER, EPI>;
   constexpr int STAGES = Cfg::kStages;
   // work distribution: item w -> (n tile, m tile), n fastest
@@ -197,6 +199,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (EPI) {
       tma_prefetch_desc(&tmR);
       tma_prefetch_desc(&tmO);
+      if (p.split1) tma_prefetch_desc(&tmO2);
     }
     fence_barrier_init();
   }
@@ -493,9 +496,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may start tile i+2
 #pragma unroll
           for (int j = col0 / 64; j < (col0 + CPW) / 64; ++j)
-            if (n0 + 64 * j < p.N)
-              tma_store_2d(&tmO, epi_base + eb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes + q * 32 * 128, n0 + 64 * j,
-                           m0 + q * 32);
+            if (n0 + 64 * j < p.N) {
+              // fused sibling 1x1x1 convs: every 64-column sub-tile belongs to one part (they start on multiples of 64) and goes
+              // through that part's own tensor map, which clips the columns beyond the part's width
+              const int gc = n0 + 64 * j;
+              const CUtensorMap* om = &tmO;
+              int oc = gc;
+              if (p.split1) {
+                if (gc >= p.split2)      { om = &tmO2; oc = gc - p.split2; }
+                else if (gc >= p.split1) { om = &tmR;  oc = gc - p.split1; }
+              }
+              tma_store_2d(om, epi_base + eb * Cfg::kEpiBufBytes + j * Cfg::kEpiSubBytes + q * 32 * 128, oc, m0 + q * 32);
+            }
           tma_store_commit();
           // The store engine needs a few hundred cycles to read the tile out of shared memory; waiting for THIS store
           // here would put that on every tile's critical path.  Wait for the PREVIOUS tile's store instead and release

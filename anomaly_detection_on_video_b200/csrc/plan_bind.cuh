@@ -39,6 +39,7 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
       memset(&r.tmA, 0, sizeof(r.tmA));
       memset(&r.tmR, 0, sizeof(r.tmR));
       memset(&r.tmO, 0, sizeof(r.tmO));
+      memset(&r.tmO2, 0, sizeof(r.tmO2));
       memset(&r.tmBh, 0, sizeof(r.tmBh));
       if (r.pair || r.pair_epi) {
         // each CTA of a pair loads half of the BN weight rows
@@ -92,13 +93,26 @@ static int32_t bind_plan(vad_plan* p, const void* x, void* ws, cudaStream_t st) 
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(residual) failed: %d", i, (int)cr);
         }
-        cuuint64_t odim[2] = {(cuuint64_t)d.cout, (cuuint64_t)c.M};
+        cuuint64_t odim[2] = {(cuuint64_t)(d.dst1 > 0 ? d.seg_w0 : d.cout), (cuuint64_t)c.M};   // fused siblings: the map clips at the part's width
         cuuint64_t ostr[1] = {(cuuint64_t)r.dst_c * 2};
         cuuint32_t obox[2] = {64, 32};
         cr = p->encode_tiled(&r.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c.out, odim, ostr, obox, es2,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(output) failed: %d", i, (int)cr);
+        if (d.dst1 > 0) {   // the sibling outputs: tensors of exactly seg_w channels; the second one rides in the (unused) residual slot
+          const int parts[2][2] = {{d.dst1, d.seg_w1}, {d.dst2, d.seg_w2}};
+          CUtensorMap* maps[2] = {&r.tmR, &r.tmO2};
+          for (int e = 0; e < 2 && cr == CUDA_SUCCESS; ++e) {
+            if (parts[e][0] <= 0) continue;
+            cuuint64_t pdim[2] = {(cuuint64_t)parts[e][1], (cuuint64_t)c.M};
+            cuuint64_t pstr[1] = {(cuuint64_t)parts[e][1] * 2};
+            cr = p->encode_tiled(maps[e], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, slot_ptr(parts[e][0]), pdim, pstr, obox, es2,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          }
+          if (cr != CUDA_SUCCESS) return fail(VAD_ERR_CUDA, "op %zu: cuTensorMapEncodeTiled(sibling output) failed: %d", i, (int)cr);
+        }
         }
       }
       if (r.stem) {

@@ -119,7 +119,9 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       // staged epilogue (two 128 x BN tiles in smem, TMA store; residual prefetched by TMA): residual layers, and
       // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections)
       r.epi = !multi && !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
-      if (multi) r.epi = false;   // parts are routed per 32-column chunk by the direct epilogue of the generic (single-CTA) kernel
+      // fused siblings: the staged TMA-store epilogue (one tensor map per part) where the k-blocks are 64 wide; the direct epilogue
+      // (parts routed per 32-column chunk; ncu: 7,900 cycles of epilogue latency per 128 x 256 tile) for the 32- / 16-wide k-block layers
+      if (multi) r.epi = !p->no_epi && r.bk == 64 && r.a_mode != A_GATHER;
       r.bn = (d.cout > 128 && !r.epi && r.bk == 64 && !multi) ? 256 : (d.cout > 64 ? 128 : 64);   // fused siblings: 128-wide tiles waste less of a ragged N
       if (multi) {
         c.split1 = d.split1; c.split2 = d.dst2 > 0 ? d.split2 : d.cout;

@@ -43,7 +43,7 @@ static cudaError_t launch_conv(const OpRuntime& r, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_k(conv_umma_kernel<BN, BK, KPS, GATHER, EPI>, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmR, r.tmO, r.cp);
+  return launch_k(conv_umma_kernel<BN, BK, KPS, GATHER, EPI>, r.grid, Cfg::kThreads, Cfg::kSmemBytes, st, g_pdl, 1, r.tmA, r.tmB, r.tmR, r.tmO, r.tmO2, r.cp);
 }
 
 template <int BN, bool EPI>
@@ -214,7 +214,9 @@ static int32_t run_ops(vad_plan* p, const void* x_dev, void* workspace_dev, floa
       else if (q.kt == 3 && q.kh == 3 && q.kw == 3 && q.st == 1 && q.sh == 1 && q.sw == 1 && q.pt == 1 && q.ph == 1 && q.pw == 1 &&
                q.To == q.Ti && q.Ho == q.Hi && q.Wo == q.Wi) {          // Inception branch pools
         maxpool3d_k3s1_kernel<<<grid_for((long long)q.B * q.Hi * q.Wi * (q.C / 8), 256, 148 * 64), 256, 0, st>>>(q);
-      } else if ((q.kt == 1 || q.kt == 3) && q.kh == 3 && q.kw == 3 || (q.kt == 2 && q.kh == 2 && q.kw == 2)) {
+      } else if (((q.kt == 1 || q.kt == 3) && q.kh == 3 && q.kw == 3 || (q.kt == 2 && q.kh == 2 && q.kw == 2)) &&
+                 q.pt < q.kt && q.ph < q.kh && q.pw < q.kw && (q.To - 1) * q.st - q.pt < q.Ti &&
+                 (q.Ho - 1) * q.sh - q.ph < q.Hi && (q.Wo - 1) * q.sw - q.pw < q.Wi) {   // every window meets the frame
         // MaxPool3d_2a / 3a ((1,3,3) / (1,2,2)), 4a ((3,3,3) / 2), 5a ((2,2,2) / 2), SAME padding: one block per output row
         const int items = q.Wo * (q.C / 8);
         const int iters = (items + 511) / 512;

@@ -93,6 +93,7 @@ struct OpRuntime {
   ConvParams cp;
   PoolParams pp;
   CUtensorMap tmA, tmB, tmR, tmO;
+  CUtensorMap tmO2;         // third output of a fused sibling conv (staged epilogue)
   bool epi = false;   // residual prefetched / output stored by TMA through shared memory
   int res_c = 0, dst_c = 0;
   int bn = 0;

@@ -15,5 +15,5 @@ e1.record(); torch.cuda.synchronize()
 prof = plan.profile_end()
 ms = e0.elapsed_time(e1) / 3
 print(f"InceptionI3d forward B={B}: {ms:.3f} ms, {B / ms * 1e3:.0f} clips/s, {B * 55.575e9 / ms / 1e9:.0f} TFLOP/s")
-for p in sorted(prof, key=lambda p: -p["ms"])[:14]:
+for p in sorted(prof, key=lambda p: -p["ms"])[:int(os.environ.get("TOP", "14"))]:
     print(f"{p['name']:24s} {p['ms'] / p['calls']:8.3f} ms  {p['flops'] / max(p['ms'], 1e-9) / 1e9:8.1f} TFLOP/s")
