@@ -223,7 +223,10 @@ static int32_t run_ops(vad_plan* p, const void* x_dev, void* workspace_dev, floa
         const int threads = ((items + iters - 1) / iters + 31) / 32 * 32;
         const long long rows = (long long)q.B * q.To * q.Ho;
         if (rows > 0x7fffffffLL) return fail(VAD_ERR_INVALID_ARGUMENT, "max-pool: too many output rows for one launch");
-        if (q.C < 128 || getenv("VAD_POOL_OLD")) {
+        // measured on B200 (160 clip-crops): the row kernel wins only for the wide (1,3,3) pool (3a: 0.38 vs 0.41 ms);
+        // the clamped grid-stride kernel wins for 2a (C = 64), 4a (0.27 vs 0.33 ms) and 5a (0.038 vs 0.055 ms)
+        const bool by_rows = getenv("VAD_POOL_ROWS") ? atoi(getenv("VAD_POOL_ROWS")) != 0 : (q.kt == 1 && q.C >= 128);
+        if (!by_rows) {
           if (q.kt == 1)      maxpool3d_checked_kernel<1, 3, 3><<<g, 256, 0, st>>>(q);
           else if (q.kt == 3) maxpool3d_checked_kernel<3, 3, 3><<<g, 256, 0, st>>>(q);
           else                maxpool3d_checked_kernel<2, 2, 2><<<g, 256, 0, st>>>(q);

@@ -269,12 +269,19 @@ def test_maxpool_same_padding_into_channel_slice(cuda_device):
                                          ((3, 3, 3), (2, 2, 2), 480, 8, 28, 28), ((3, 3, 3), (2, 2, 2), 64, 5, 9, 11),
                                          ((2, 2, 2), (2, 2, 2), 832, 4, 14, 14), ((2, 2, 2), (2, 2, 2), 64, 3, 7, 5)])
 @pytest.mark.parametrize("negative", [False, True], ids=["randn", "all-negative"])
-def test_inception_same_padding_pools_are_exact(cuda_device, k, s, C, T, H, W, negative):
-    """Every MaxPool3dSamePadding geometry of the Inception port through its specialised kernel (sliding 3-frame window for
-    the 3x3x3 / 1 branch pools, unrolled predicated windows for the strided ones).  SAME padding pads with ZEROS, which
-    only shows on all-negative inputs: border outputs are then 0, interior ones negative."""
+@pytest.mark.parametrize("rows", [None, "0", "1"], ids=["default", "grid-stride", "row-per-block"])
+def test_inception_same_padding_pools_are_exact(cuda_device, monkeypatch, k, s, C, T, H, W, negative, rows):
+    """Every MaxPool3dSamePadding geometry of the Inception port through its specialised kernels (sliding 3-frame window for
+    the 3x3x3 / 1 branch pools; for the strided ones both the grid-stride kernel with clamped taps and the row-per-block
+    kernel, whichever the plan picks by default).  SAME padding pads with ZEROS, which only shows on all-negative inputs:
+    border outputs are then 0, interior ones negative."""
     from anomaly_detection_on_video_b200 import _lib as lib, engine as eng
     from oracle.inception import _same_pad
+
+    if rows is None:
+        monkeypatch.delenv("VAD_POOL_ROWS", raising=False)
+    else:
+        monkeypatch.setenv("VAD_POOL_ROWS", rows)
 
     x = torch.randn(2, C, T, H, W, generator=torch.Generator().manual_seed(8))
     if negative:

@@ -37,7 +37,8 @@ if __name__ == "__main__":
         launches.setdefault(int(r[0]), {"name": r[ki]})[r[mi]] = (float(r[vi].replace(",", "")), r[ui])
     ids = list(launches)
     seg = [i for i in ids if "segment_mean" in launches[i]["name"]]
-    lo, hi = (seg[2] + 1, seg[3] + 1) if len(seg) >= 4 else (ids[0], ids[-1] + 1)   # the step before the last (timed) one
+    # one whole step = the launches after one segment mean up to and including the next; the last such pair is the timed step
+    lo, hi = (seg[-2] + 1, seg[-1] + 1) if len(seg) >= 2 else (ids[0], ids[-1] + 1)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     rd = wr = ns = 0.0
     per = OrderedDict()
