@@ -52,6 +52,12 @@ MIXED: Tuple[Tuple[str, int, Tuple[int, int, int, int, int, int]], ...] = (
 # small-N layer is bound by its im2col traffic through L2, which doubles).  Internal to a Mixed block: results are unchanged (the
 # extra terms are exact zeros).
 BRANCH_PAD = {16: 64, 24: 64, 48: 64, 96: 128, 112: 128, 144: 192, 160: 192}
+# The same for a whole block output: Mixed_4e's 528-channel concat (8 x 64 + 16) puts all of Mixed_4f's 1x1x1 convs on the 16-wide
+# k-block path (ncu, 160 clip-crops: the fused sibling launch 180 us against 72-74 us for its 512-channel peers, b3b 58 against
+# 28 us).  The last branch conv of 4e writes 48 zero channels behind the concat and 4f's convs carry zero weight columns for them;
+# 4f's branch pool moves 9 % more bytes.  480 (Mixed_3c -> MaxPool3d_4a -> 4b, 32-wide k-blocks) is left alone: the pools in
+# between would pay more than the convs gain.
+CONCAT_PAD = {528: 576}
 
 POOL_BEFORE = {"Mixed_4b": ("MaxPool3d_4a_3x3", (3, 3, 3), (2, 2, 2)), "Mixed_5b": ("MaxPool3d_5a_2x2", (2, 2, 2), (2, 2, 2))}
 
@@ -152,12 +158,13 @@ class InceptionI3d(_NativeBackbone):
                   dst_c_total=total, w_off=w_off, scale_off=s_off, shift_off=b_off, name=name)
 
     def _siblings(self, pk: ParamPacker, m: "InceptionModule", src: int, dst: int, t1: int, t2: int, name: str, total: int,
-                  w1: int, w2: int) -> Op:
+                  w1: int, w2: int, cin_pad: int = 0) -> Op:
         """b0 | b1a | b2a of one Mixed block as one 1x1x1 conv: the weight matrix stacks their output channels, every sibling
         starting on a multiple of 64 columns (zero rows in between, never stored); columns [0, split1) -> the concat slice,
         [split1, split2) -> branch temporary t1 (w1 channels incl. the BRANCH_PAD zeros), [split2, ..) -> t2 (w2 channels)."""
         units = (m.b0, m.b1a, m.b2a)
-        cin = m.b0.conv3d.in_channels
+        cin_nom = m.b0.conv3d.in_channels
+        cin = cin_pad or cin_nom   # CONCAT_PAD: the block input carries zero channels behind the nominal ones
         b0 = m.b0.conv3d.out_channels
         split1 = (b0 + 63) // 64 * 64
         split2 = split1 + (w1 + 63) // 64 * 64
@@ -169,7 +176,7 @@ class InceptionI3d(_NativeBackbone):
         for u, start in zip(units, (0, split1, split2)):
             n = u.conv3d.out_channels
             scale, shift = fold_bn(u.bn.weight, u.bn.bias, u.bn.running_mean, u.bn.running_var, u.bn.eps)
-            w[start:start + n] = u.conv3d.weight.detach().float()
+            w[start:start + n, :cin_nom] = u.conv3d.weight.detach().float()
             sc[start:start + n] = scale
             sh[start:start + n] = shift
         w_off, s_off, b_off = pk.add_conv(w, sc, sh)
@@ -192,6 +199,8 @@ class InceptionI3d(_NativeBackbone):
         ops.append(self._unit(pk, self.Conv3d_2c_3x3, 1, 2, "Conv3d_2c_3x3"))
         ops.append(self._pool(self.MaxPool3d_3a_3x3, 2, 1, "MaxPool3d_3a_3x3"))
         cur = 1
+        cur_pad = 0   # width of the current block input when CONCAT_PAD widened it, else 0
+        widen = self.pad_branches and self.precision != "tf32"
         for name, _, outs in MIXED:
             if name in POOL_BEFORE:
                 nxt = 2 if cur == 1 else 1
@@ -199,24 +208,28 @@ class InceptionI3d(_NativeBackbone):
                 cur = nxt
             m: InceptionModule = getattr(self, name)
             nxt = 2 if cur == 1 else 1
-            total = outs[0] + outs[2] + outs[4] + outs[5]
+            nominal = outs[0] + outs[2] + outs[4] + outs[5]
+            total = CONCAT_PAD.get(nominal, nominal) if widen else nominal
             # torch.cat([b0, b1, b2, b3], dim=1): every branch writes its channel slice of the output in place
             p1 = BRANCH_PAD.get(outs[1], 0) if self.pad_branches else 0
             p2 = BRANCH_PAD.get(outs[3], 0) if self.pad_branches else 0
             if self.fuse_siblings and self.precision != "tf32" and not self.force_gather:
                 # b0, b1a and b2a are 1x1x1 convs over the same block input, each bound by reading it: ONE launch reads it once and
                 # routes its output columns to the concat slice (b0) and the two branch temporaries (vad_op_desc.dst1 / dst2)
-                ops.append(self._siblings(pk, m, cur, nxt, T1, T2, name, total, p1 or outs[1], p2 or outs[3]))
+                ops.append(self._siblings(pk, m, cur, nxt, T1, T2, name, total, p1 or outs[1], p2 or outs[3], cin_pad=cur_pad))
             else:
-                ops.append(self._unit(pk, m.b0, cur, nxt, name + ".b0", off=0, total=total))
-                ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a", cout_pad=p1))
-                ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a", cout_pad=p2))
+                ops.append(self._unit(pk, m.b0, cur, nxt, name + ".b0", off=0, total=total, cin_pad=cur_pad))
+                ops.append(self._unit(pk, m.b1a, cur, T1, name + ".b1a", cin_pad=cur_pad, cout_pad=p1))
+                ops.append(self._unit(pk, m.b2a, cur, T2, name + ".b2a", cin_pad=cur_pad, cout_pad=p2))
             # the pooling branch right behind the 1x1x1 convs: it reads the same block input, part of which is still in L2
             ops.append(self._pool(m.b3a, cur, T3, name + ".b3a"))
-            ops.append(self._unit(pk, m.b3b, T3, nxt, name + ".b3b", off=outs[0] + outs[2] + outs[4], total=total))
+            # the last branch also writes the CONCAT_PAD zero channels behind its own (zero weights, zero scale and shift)
+            ops.append(self._unit(pk, m.b3b, T3, nxt, name + ".b3b", off=outs[0] + outs[2] + outs[4], total=total, cin_pad=cur_pad,
+                                  cout_pad=outs[5] + total - nominal if total != nominal else 0))
             ops.append(self._unit(pk, m.b1b, T1, nxt, name + ".b1b", off=outs[0], total=total, cin_pad=p1))
             ops.append(self._unit(pk, m.b2b, T2, nxt, name + ".b2b", off=outs[0] + outs[2], total=total, cin_pad=p2))
             cur = nxt
+            cur_pad = total if total != nominal else 0
         ops.append(Op(kind=_lib.VAD_OP_AVGPOOL, src=cur, name="avg_pool"))
         return ops, pk, 6
 
