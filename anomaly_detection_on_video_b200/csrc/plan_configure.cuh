@@ -98,7 +98,13 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       r.bk = 64;
       // Cin % 64 == 32 (Inception's 96 / 160 / 480-channel inputs, 32-channel 5x5 branches): TMA operands with 32-wide
       // k-blocks (64-byte rows, SWIZZLE_64B) -- direct epilogue only; anything else that is not a multiple of 64: gather
-      const bool epi_wanted = !multi && !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
+      // HBM-bound plain 1x1x1 convs with one k-block and few output channels (Inception's Conv3d_2b_1x1, 64 -> 64 over 4 M rows:
+      // 0.247 -> 0.207 ms per 160 clip-crops through the staged epilogue).  Measured with larger limits as well: the pooling-branch
+      // projections (K = 192 .. 832) gain nothing or lose (Mixed_3b.b3b 0.082 -> 0.090 ms), so the default stops at K = 64.
+      const int epi_unit_max_k = getenv("VAD_EPI_UNIT_MAXK") ? atoi(getenv("VAD_EPI_UNIT_MAXK")) : 64;
+      const bool epi_unit = unit && d.res < 0 && !multi && d.cout <= 128 && (d.cin % 64) == 0 && K <= epi_unit_max_k &&
+                            !(d.flags & (VAD_FLAG_FORCE_GATHER | VAD_FLAG_POOL_T2));
+      const bool epi_wanted = !multi && !p->no_epi && (d.res >= 0 || epi_unit || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
       // ... and Cin % 32 == 16 (16 / 48 / 112 / 144 / 528 channels) with 16-wide ones (32-byte rows, SWIZZLE_32B, one MMA each)
       const int sub_k = (fold || epi_wanted || p->no_bk32) ? 0 : ((d.cin % 64) == 32 ? 32 : ((d.cin % 32) == 16 ? 16 : 0));
       const bool half_k = sub_k != 0;
@@ -118,7 +124,7 @@ extern "C" int32_t vad_plan_configure(vad_plan_t* p, int32_t batch, int32_t t, i
       c.num_kb = r.bk == 64 ? r.K_pad / 64 : (K + r.bk - 1) / r.bk;
       // staged epilogue (two 128 x BN tiles in smem, TMA store; residual prefetched by TMA): residual layers, and
       // output-dominated small-K layers without one (K <= 256, cout >= 2K: the first downsample projections)
-      r.epi = !multi && !p->no_epi && (d.res >= 0 || (d.cout >= 128 && K <= 256 && d.cout >= 2 * K));
+      r.epi = epi_wanted;
       // fused siblings: the staged TMA-store epilogue (one tensor map per part) where the k-blocks are 64 wide; the direct epilogue
       // (parts routed per 32-column chunk; ncu: 7,900 cycles of epilogue latency per 128 x 256 tile) for the 32- / 16-wide k-block layers
       if (multi) r.epi = !p->no_epi && r.bk == 64 && r.a_mode != A_GATHER;

@@ -19,6 +19,7 @@ taps of half of the output channels resident (csrc/stem_pair.cuh).  11.5 k clips
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Sequence, Tuple
 
 import torch
@@ -47,17 +48,21 @@ MIXED: Tuple[Tuple[str, int, Tuple[int, int, int, int, int, int]], ...] = (
 # channels (zero weight rows in the producing 1x1x1 conv: relu(0 * x + 0) = 0; zero weight columns in the consumer): the
 # consumer then contracts whole 64-channel k-blocks through the im2col TMA path.  Measured per 160 clip-crops (round 2):
 # Cin = 144 (16-wide k-blocks, one 32-byte sector per TMA row) ran at 0.26 of the tensor peak, 112 at 0.28, 16 at 0.05, 24 on
-# the cp.async gather at 0.08; a 64-multiple Cin reaches 0.8, so even 4 x the FLOPs (16 -> 64) is the faster launch; 96 -> 128 takes
+# the cp.async gather at 0.08; a 64-multiple Cin reaches 0.8; 96 -> 128 takes
 # Mixed_3b.b1b off the 32-wide k-block path (0.78 -> 0.65 ms); 32 -> 64 was measured and LOSES (Mixed_3c.b2b 0.33 -> 0.40 ms: that
 # small-N layer is bound by its im2col traffic through L2, which doubles).  Internal to a Mixed block: results are unchanged (the
 # extra terms are exact zeros).
-BRANCH_PAD = {16: 64, 24: 64, 48: 64, 96: 128, 112: 128, 144: 192, 160: 192}
+# 16 and 24 channels go to 32, not 64 (32-wide k-blocks): Mixed_3b.b2b 0.366 -> 0.256 ms, 4b / 4c / 4d.b2b 0.049 -> 0.043 ms -- the
+# same im2col-traffic argument as for 32 -> 64; 48 -> 64 stays (one 64-wide k-block per tap instead of a 32- and a 16-wide one).
+BRANCH_PAD = {16: 32, 24: 32, 48: 64, 96: 128, 112: 128, 144: 192, 160: 192}
 # The same for a whole block output: Mixed_4e's 528-channel concat (8 x 64 + 16) puts all of Mixed_4f's 1x1x1 convs on the 16-wide
 # k-block path (ncu, 160 clip-crops: the fused sibling launch 180 us against 72-74 us for its 512-channel peers, b3b 58 against
 # 28 us).  The last branch conv of 4e writes 48 zero channels behind the concat and 4f's convs carry zero weight columns for them;
 # 4f's branch pool moves 9 % more bytes.  480 (Mixed_3c -> MaxPool3d_4a -> 4b, 32-wide k-blocks) is left alone: the pools in
 # between would pay more than the convs gain.
 CONCAT_PAD = {528: 576}
+if os.environ.get("VAD_BRANCH_PAD"):   # A/B: "16:32,24:32"
+    BRANCH_PAD.update({int(a): int(b) for a, b in (kv.split(":") for kv in os.environ["VAD_BRANCH_PAD"].split(","))})
 
 POOL_BEFORE = {"Mixed_4b": ("MaxPool3d_4a_3x3", (3, 3, 3), (2, 2, 2)), "Mixed_5b": ("MaxPool3d_5a_2x2", (2, 2, 2), (2, 2, 2))}
 

@@ -41,7 +41,7 @@ def test_features_match_fp32_oracle(model, cuda_device):
 
 def test_widened_branch_temporaries_do_not_change_the_features(model, cuda_device):
     """BRANCH_PAD (zero channels added to the 16/24/48/112/144/160-channel branch temporaries so that the 3x3x3 convs contract
-    64-wide k-blocks): the extra terms are exact zeros, so the features move only by the fp32 summation order inside the
+    whole 32- or 64-wide k-blocks) and CONCAT_PAD (Mixed_4e's 528-channel output widened to 576): the extra terms are exact zeros, so the features move only by the fp32 summation order inside the
     tensor core's k-blocks -- far below the bf16 storage noise that separates either variant from the fp32 oracle."""
     from anomaly_detection_on_video_b200.inception import InceptionI3d
     from oracle import inception as OI
@@ -51,10 +51,12 @@ def test_widened_branch_temporaries_do_not_change_the_features(model, cuda_devic
     plain.load_state_dict(OI.seeded_state_dict(0), strict=True)
     plain = plain.eval().to(cuda_device)
     widths = {op.name: (op.cin, op.cout) for op in model.op_table()}
-    assert widths["Mixed_4e.b1b"] == (192, 288) and widths["Mixed_3b.b2b"] == (64, 32)
+    assert widths["Mixed_4e.b1b"] == (192, 288) and widths["Mixed_3b.b2b"] == (32, 32) and widths["Mixed_5c.b2b"] == (64, 128)
     fused = {op.name: op for op in model.op_table()}["Mixed_4e.b0+b1a+b2a"]     # 112 | 144 -> 192 | 32
     assert (fused.cin, fused.cout, fused.split1, fused.split2, fused.seg_w) == (512, 128 + 192 + 32, 128, 320, (112, 192, 32))
-    assert {op.name: (op.cin, op.cout) for op in plain.op_table()}["Mixed_4e.b1b"] == (144, 288)
+    assert widths["Mixed_4e.b3b"] == (512, 64 + 48) and widths["Mixed_4f.b3b"] == (576, 128) and widths["Mixed_5b.b3b"] == (832, 128)
+    nominal = {op.name: (op.cin, op.cout) for op in plain.op_table()}
+    assert nominal["Mixed_4e.b1b"] == (144, 288) and nominal["Mixed_4f.b3b"] == (528, 128)
     x = torch.randn(2, 3, 16, 224, 224, generator=torch.Generator().manual_seed(5)).clamp(-2.0, 2.4444).to(cuda_device)
     a, b = model(x).view(2, -1).float(), plain(x).view(2, -1).float()
     err = float((a - b).abs().max() / b.abs().max())

@@ -96,6 +96,22 @@ def test_conv_half_width_k_blocks(cuda_device, case):
     assert torch.equal(tma, gather)
 
 
+@pytest.mark.parametrize("relu", [False, True])
+def test_single_k_block_unit_conv_staged_epilogue_is_bit_identical(cuda_device, monkeypatch, relu):
+    """Plain 64 -> 64 1x1x1 convs (Inception's Conv3d_2b_1x1) leave through the staged TMA-store epilogue by default;
+    VAD_EPI_UNIT_MAXK=0 keeps them on the register-direct one.  Same accumulators, same BN / ReLU / rounding: bit-identical,
+    ragged last m-tile included."""
+    from gpu_util import assert_bf16_close, run_conv_case
+
+    case = (64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 2, 3, 11, 13, False, relu)
+    monkeypatch.delenv("VAD_EPI_UNIT_MAXK", raising=False)
+    staged, ref = run_conv_case(*case)
+    monkeypatch.setenv("VAD_EPI_UNIT_MAXK", "0")
+    direct, _ = run_conv_case(*case)
+    assert_bf16_close(staged, ref)
+    assert torch.equal(staged, direct)
+
+
 @pytest.mark.parametrize("case", GATHER_ONLY, ids=[c[0] for c in GATHER_ONLY])
 def test_conv_narrow_channels(cuda_device, case):
     from gpu_util import assert_bf16_close, run_conv_case
