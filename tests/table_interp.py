@@ -31,16 +31,25 @@ def _same_pads(size: Tuple[int, int, int], k, s) -> List[int]:
     return pads
 
 
-def _weights(blob: torch.Tensor, op: Op) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """-> ([cout, cin, kt, kh, kw] fp32, scale [cout], shift [cout]) decoded from the packed blob."""
+def _weights(blob: torch.Tensor, op: Op, tf32: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> ([cout, cin, kt, kh, kw] fp32, scale [cout], shift [cout]) decoded from the packed blob (bf16 rows padded to 64, or --
+    TF32 precision mode -- fp32 rows padded to 32)."""
     kt, kh, kw = op.kernel
     fold = bool(op.flags & _lib.VAD_FLAG_STEM_FOLD_W)
     k = kt * kh * 32 if fold else kt * kh * kw * op.cin
-    k_pad = (k + KBLOCK - 1) // KBLOCK * KBLOCK
-    raw = blob[op.w_off:op.w_off + op.cout * k_pad * 2].view(torch.bfloat16).float().reshape(op.cout, k_pad)
+    kblock = 32 if tf32 else KBLOCK
+    k_pad = (k + kblock - 1) // kblock * kblock
+    if tf32:
+        raw = blob[op.w_off:op.w_off + op.cout * k_pad * 4].view(torch.float32).reshape(op.cout, k_pad)
+        assert not (raw.view(torch.int32) & 0x1FFF).any(), f"{op.name}: fp32 weights are not TF32 values"
+    else:
+        raw = blob[op.w_off:op.w_off + op.cout * k_pad * 2].view(torch.bfloat16).float().reshape(op.cout, k_pad)
     assert not raw[:, k:].any(), f"{op.name}: K padding of the packed weights is not zero"
     if fold:
-        w = raw[:, :k].reshape(op.cout, kt, kh, 8, 4)
+        w = raw[:, :k]
+        if op.flags & _lib.VAD_FLAG_STEM_PLANES:   # [plane][4 positions][4 channels] per (dt, dh) tap: pixel j = 2 i + plane
+            w = w.reshape(op.cout, kt, kh, 2, 4, 4).permute(0, 1, 2, 4, 3, 5)
+        w = w.reshape(op.cout, kt, kh, 8, 4)
         assert not w[:, :, :, kw:].any() and not w[..., 3].any(), f"{op.name}: folded-window padding taps are not zero"
         w = w[:, :, :, :kw, :3].permute(0, 4, 1, 2, 3)
     else:
@@ -51,19 +60,23 @@ def _weights(blob: torch.Tensor, op: Op) -> Tuple[torch.Tensor, torch.Tensor, to
 
 
 @torch.no_grad()
-def run_table(ops: List[Op], blob: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """x: [B, 3, T, H, W] fp32 clips -> [B, C] features, executing `ops` row by row on NCDHW fp32 slot tensors."""
+def run_table(ops: List[Op], blob: torch.Tensor, x: torch.Tensor, tf32: bool = False) -> torch.Tensor:
+    """x: [B, 3, T, H, W] fp32 clips -> [B, C] features, executing `ops` row by row on NCDHW fp32 slot tensors.
+    ``tf32``: the table and blob of the TF32 precision mode (fp32 weights; an RGB conv that is not folded reads 4 channels)."""
     slots: Dict[int, torch.Tensor] = {0: x}
     concat_owner: Dict[int, str] = {}
     out = None
     for op in ops:
         src = slots[op.src]
         if op.kind == _lib.VAD_OP_CONV:
-            w, scale, shift = _weights(blob, op)
+            w, scale, shift = _weights(blob, op, tf32)
             fold = bool(op.flags & _lib.VAD_FLAG_STEM_FOLD_W)
             cin_have = src.shape[1]
             if fold:
                 assert op.cin == 4 and cin_have == 3, op.name
+            elif tf32 and op.src == 0 and op.cin == 4 and cin_have == 3:
+                assert not w[:, 3].any(), f"{op.name}: weights of the zero input channel are not zero"
+                w = w[:, :3].contiguous()
             else:
                 assert op.cin == cin_have, f"{op.name}: cin {op.cin} but slot {op.src} holds {cin_have} channels"
             if op.flags & _lib.VAD_FLAG_CONV_SAME:

@@ -70,6 +70,45 @@ def test_i3res50_table_executes_to_the_oracle_features(fuse_stem_pool, fuse_pool
     assert _err(got, ref.reshape(1, -1)) <= TOL
 
 
+def _tf32_weights(sd):
+    def rna(v):   # round to nearest TF32, ties away from zero (cvt.rna.tf32.f32), like ParamPacker
+        return ((v.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return {k: (rna(v.float()) if v.dim() == 5 else v) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("backbone,planes", [("i3res50", True), ("i3res50", False), ("inception", False)],
+                         ids=["i3res50-plane-stem", "i3res50-gather-stem", "inception"])
+def test_tf32_mode_tables_execute_to_the_oracle_features(backbone, planes):
+    """The TF32 precision mode builds its own tables (fp32 weights rounded to TF32, K padded to 32, unfused pools, the stem's
+    folded-window weights in plane order when VAD_FLAG_STEM_PLANES)."""
+    from anomaly_detection_on_video_b200 import _lib
+
+    if backbone == "i3res50":
+        from anomaly_detection_on_video_b200.i3d import I3Res50 as Model
+        from oracle import i3res50 as O
+
+        sd = O.seeded_state_dict(0)
+        x = _clip(14, h=160, w=192)
+        ref = lambda: O.forward(x, _tf32_weights(sd))[0].reshape(1, -1)   # noqa: E731
+    else:
+        from anomaly_detection_on_video_b200.inception import InceptionI3d as Model
+        from oracle import inception as O
+
+        sd = O.seeded_state_dict(0)
+        x = _clip(15)
+        ref = lambda: O.extract_features(x, _tf32_weights(sd))   # noqa: E731
+    m = Model()
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    m.precision = "tf32"
+    m.tf32_stem_planes = planes
+    ops, pk, _ = m._build_table()
+    assert not any(op.flags & _lib.VAD_FLAG_POOL_T2 for op in ops) and not any(op.dst1 for op in ops)
+    assert bool(ops[0].flags & _lib.VAD_FLAG_STEM_PLANES) == (planes and backbone == "i3res50")
+    got = run_table(ops, pk.blob(), x, tf32=True)
+    assert _err(got, ref()) <= TOL
+
+
 def test_ptv_i3d_r50_table_executes_to_the_oracle_features():
     from anomaly_detection_on_video_b200.ptv_resnet import I3D8x8R50
     from oracle import i3d_r50_ptv as R
