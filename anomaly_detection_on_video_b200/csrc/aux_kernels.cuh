@@ -590,8 +590,10 @@ __global__ void __launch_bounds__(256) maxpool3d_k3s1_kernel(const PoolParams p)
 // maxpool3d_rows_kernel<KT, KH, KW>: a block owns one output row (b, to, ho); a thread one (wo, 8-channel vector) item.
 // The (dt, dh) bounds are block-uniform, every index is 32-bit, the window loads allocate in L1 (neighbouring wo share
 // columns), and all loads of a thread are issued before the first max.  Measured per 160 clip-crops against the
-// thread-per-output kernel: MaxPool3d_3a (192 ch) 0.46 -> 0.38 ms, 4a (480 ch) 0.43 -> 0.32 ms; 2a (64 ch: 448 one-item
-// threads per block) 0.59 -> 0.62 ms, so layers under 128 channels stay on the other kernel.  Also measured and rejected: a
+// thread-per-output kernel with predicated taps: MaxPool3d_3a (192 ch) 0.46 -> 0.38 ms, 4a (480 ch) 0.43 -> 0.32 ms; 2a (64 ch:
+// 448 one-item threads per block) 0.59 -> 0.62 ms.  Once that kernel clamped its taps instead (maxpool3d_checked_kernel above) it
+// took 4a to 0.27 and 5a to 0.038 ms, so the plan now uses this kernel for the wide (1,3,3) pool only (3a: 0.38 vs 0.41 ms;
+// VAD_POOL_ROWS forces either, both stay under test).  Also measured and rejected: a
 // persistent grid-strided form (3a: 0.55 ms) and a separable row-per-block form of the 3x3x3 / 1 branch pools (column max
 // through shared memory, one barrier per frame: 0.40 vs 0.30 ms on Mixed_3c).
 template <int KT, int KH, int KW>

@@ -3,7 +3,7 @@
 
     python tools/step_traffic.py <tag>
 """
-import csv, hashlib, json, os, sys
+import csv, hashlib, json, os, re, sys
 from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,11 +15,19 @@ STEP_SOURCES = ("ptx_sm100.cuh", "aux_kernels.cuh", "aux_api.cuh", "conv_umma.cu
                 "conv_pair.cuh", "conv_tail.cuh", "plan_configure.cuh", "plan_bind.cuh", "plan_run.cuh")
 
 
-def source_hash() -> str:
+def _code_only(text: str) -> str:
+    """The source without comments and with runs of white space collapsed: editing a comment does not change what was measured."""
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    return " ".join(text.split())
+
+
+def source_hash(code_only: bool = True) -> str:
     h = hashlib.sha256()
     d = os.path.join(ROOT, "anomaly_detection_on_video_b200", "csrc")
     for f in STEP_SOURCES:
-        h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+        raw = open(os.path.join(d, f), "rb").read()
+        h.update(f.encode()); h.update(_code_only(raw.decode()).encode() if code_only else raw)
     return h.hexdigest()[:16]
 
 
