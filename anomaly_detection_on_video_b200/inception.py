@@ -9,13 +9,16 @@ REFERENCE: the oracle (``oracle/inception.py``) is our own fp32 restatement of t
 
 What maps onto which kernel:
   Unit3D (conv3d, TF-"SAME" padding, no bias + BatchNorm3d(eps 1e-3) + ReLU)  -> K2 with ``VAD_FLAG_CONV_SAME``;
-      16/24/32/48-channel and 480/528-channel inputs (Cin % 64 != 0) take the cp.async gather producer
+      Cin % 64 == 32 inputs take TMA operands with 32-wide k-blocks; the narrow branch temporaries (16 .. 160 channels) and
+      Mixed_4e's 528-channel output are widened with zero channels so that they do too, or take 64-wide ones (BRANCH_PAD,
+      CONCAT_PAD below); b0 | b1a | b2a of a block are one launch with routed output columns (``_siblings``)
   MaxPool3dSamePadding                                                        -> K3 with ``VAD_FLAG_POOL_SAME``
   Inception branch concat                                                     -> every branch conv writes its
       channel slice of the concatenated tensor directly (``dst_c_off`` / ``dst_c_total``): no copy kernel
   AvgPool3d([2, 7, 7]) on the final 2 x 7 x 7 map                             -> K4 (global mean)
 The 7x7x7 / 2 stem (49 taps x 4 KB of weights: too many for one CTA's shared memory) runs on CTA pairs, each CTA keeping the
-taps of half of the output channels resident (csrc/stem_pair.cuh).  11.5 k clips/s per B200 (0.46 of the sustained bf16 peak).
+taps of half of the output channels resident (csrc/stem_pair.cuh).  12.5 k clips/s per B200 at 160 clip-crops per forward (0.49-0.50 of
+the sustained bf16 peak), 11.5 k for a whole video end to end.
 """
 from __future__ import annotations
 
